@@ -1,0 +1,263 @@
+// FP64 GEMM core for sm_100a: DMMA.8x8x4 tiles fed by TMA through an mbarrier ring.
+//
+//   C[M x N] = alpha * A * B + beta * Cin,   A given as At (K x M, column-major, lda),
+//                                            B given as Bm (K x N, column-major, ldb)
+// i.e. the BLAS "TN" form: BOTH operands are contiguous along K.  Every contraction of the BSFG
+// sweep is arranged to have this form (DESIGN.md "layouts"), so one kernel serves all of them:
+// U'Y, U'F (BSFG_functions_c.cpp:107-108), the weighted Gram product behind Qlam (:120-122),
+// Design_U'Y (:65), Y_tilde*Lmsg and Lambda'Lmsg (:149-152), and the F*Lambda' cross terms.
+//
+// Tile = BM x BN x 16 doubles per stage.  A stage's operand tile is [rows][16 doubles] = 128-byte
+// rows written by ONE cp.async.bulk.tensor.2d (SWIZZLE_128B).  The 4 k-indices one DMMA consumes
+// are {2j, 2j+1, 2j+8, 2j+9} (j = 0..3) rather than {4j..4j+3}: summation order over k is free, and
+// with this choice the 16 lanes of a half-warp (4 rows x 4 k) hit 16 distinct 8-byte bank pairs
+// under the hardware swizzle (chunk' = chunk ^ (row & 7)), so fragment loads are conflict-free
+// LDS.64 with no padding and no repacking.
+//
+// Warp roles: 8 warps, each owning a 64 x 32 sub-tile of the 128 x 128 CTA tile (8 x 4 DMMA
+// accumulators = 64 FP64 values = 128 registers per thread).  Thread 0 also issues the TMA loads,
+// STAGES-1 k-tiles ahead (a 9th producer warp would round the CTA up to 384 threads for register
+// allocation and cap the kernel at 168 registers -> spills in the DMMA loop).  Split-K
+// writes raw partial tiles to a workspace that `splitk_reduce_kernel` sums in a FIXED order, so
+// results are bit-reproducible run to run and rank to rank (no FP64 atomics).
+#pragma once
+#include "common.cuh"
+
+namespace bsfg {
+
+constexpr int GEMM_BK = 16;          // doubles per stage row = 128 bytes
+constexpr int GEMM_CONSUMERS = 8;    // consumer warps
+constexpr int GEMM_THREADS = GEMM_CONSUMERS * 32;   // no dedicated producer warp: 256 threads keep the 255-register budget
+
+struct GemmArgs {
+    int M, N, K;
+    double* C;
+    long ldc;
+    const double* Cin;     // may be null (beta ignored) or alias C
+    long ldcin;
+    double alpha, beta;
+    int splits;            // >= 1
+    int ktiles_per_split;
+    double* ws;            // [splits][N][M] raw partials when splits > 1
+    int tiles_m, tiles_n;
+    int group_n;           // rasterisation: tiles are walked m-fastest inside groups of `group_n` n-tiles
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+template <int BM, int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * GEMM_BK * 8;
+    static constexpr int B_BYTES = BN * GEMM_BK * 8;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // + barriers + align slack
+};
+
+// ---- the kernel -----------------------------------------------------------------------------
+template <int BM, int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+    static_assert(BM == 128 && BN == 128, "warp layout below is written for 128x128 CTA tiles");
+    using S = GemmSmem<BM, BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates: grouped rasterisation so co-resident CTAs share operand panels in L2
+    int tile = blockIdx.x;
+    const int split = blockIdx.y;
+    const int group_sz = g.group_n * g.tiles_m;
+    const int grp = tile / group_sz;
+    const int first_n = grp * g.group_n;
+    const int gn = min(g.group_n, g.tiles_n - first_n);
+    const int in_grp = tile - grp * group_sz;
+    const int tile_n = first_n + in_grp % gn;
+    const int tile_m = in_grp / gn;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+
+    const int total_ktiles = (g.K + GEMM_BK - 1) / GEMM_BK;
+    const int kt_begin = split * g.ktiles_per_split;
+    const int kt_end = min(total_ktiles, kt_begin + g.ktiles_per_split);
+    const int nkt = max(0, kt_end - kt_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], GEMM_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ===================== DMMA consumers =====================
+    const int gq = lane >> 2;      // row inside an 8x8 fragment (0..7)
+    const int q = lane & 3;        // k slot (0..3)
+    const int wm0 = (warp & 1) * 64;
+    const int wn0 = (warp >> 1) * 32;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // byte offset inside a 128-byte row for k-step j: chunk = j + 4*(q>>1), swizzled by (row&7)==gq
+    uint32_t koff[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) koff[j] = (uint32_t)((((j + 4 * (q >> 1)) ^ gq) << 4) + ((q & 1) << 3));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t a_row = (uint32_t)((wm0 + gq) * 128);
+    const uint32_t b_row = (uint32_t)(S::A_BYTES + (wn0 + gq) * 128);
+
+    // TMA issue is folded into consumer warp 0 (lane 0): it runs STAGES-1 k-tiles ahead of the math.
+    auto issue = [&](int nx) {
+        const int s2 = nx % STAGES;
+        mbar_wait(&empty_bar[s2], ((nx / STAGES) & 1) ^ 1);   // passes immediately on first use of a slot
+        mbar_expect_tx(&full_bar[s2], S::STAGE_BYTES);
+        uint8_t* sa = smem + s2 * S::STAGE_BYTES;
+        const int kc = (kt_begin + nx) * GEMM_BK;
+        tma_load_2d(sa, &tmA, &full_bar[s2], kc, m0);
+        tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s2], kc, n0);
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int nx = 0; nx < STAGES - 1 && nx < nkt; nx++) issue(nx);
+    }
+    __syncwarp();
+
+    for (int it = 0; it < nkt; it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        if (threadIdx.x == 0 && it + STAGES - 1 < nkt) issue(it + STAGES - 1);
+        __syncwarp();
+        mbar_wait(&full_bar[s], ph);
+        const uint32_t sbase = smem_base + s * S::STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = lds_f64(sbase + a_row + i * 8 * 128 + koff[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) b[i] = lds_f64(sbase + b_row + i * 8 * 128 + koff[j]);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    // ===================== epilogue =====================
+    // thread owns C[m0+wm0+8i+gq][n0+wn0+8j+2q+{0,1}]
+    if (g.splits > 1) {
+        double* ws = g.ws + (size_t)split * (size_t)g.M * (size_t)g.N;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int m = m0 + wm0 + 8 * i + gq;
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int n = n0 + wn0 + 8 * j + 2 * q + c;
+                    if (n < g.N) ws[(size_t)n * g.M + m] = acc[i][j][c];
+                }
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int m = m0 + wm0 + 8 * i + gq;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int n = n0 + wn0 + 8 * j + 2 * q + c;
+                if (n < g.N) {
+                    double v = g.alpha * acc[i][j][c];
+                    if (g.Cin) v += g.beta * g.Cin[(size_t)n * g.ldcin + m];
+                    g.C[(size_t)n * g.ldc + m] = v;
+                }
+            }
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(GemmArgs g) {
+    const size_t total = (size_t)g.M * g.N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx % g.M);
+        const int n = (int)(idx / g.M);
+        double acc = 0.0;
+        for (int s = 0; s < g.splits; s++) acc += g.ws[(size_t)s * total + idx];   // fixed order
+        double v = g.alpha * acc;
+        if (g.Cin) v += g.beta * g.Cin[(size_t)n * g.ldcin + m];
+        g.C[(size_t)n * g.ldc + m] = v;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+struct GemmPlan;   // opaque to callers; see gemm_host.cu
+
+// C = alpha * At' * Bm + beta * Cin.  At: K x M (lda), Bm: K x N (ldb); all column-major, lda/ldb
+// even, pointers 16-byte aligned.  `ws`/`ws_doubles` is scratch for split-K (may be null: no split).
+void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
+              const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
+              double* ws, size_t ws_doubles);
+
+}  // namespace bsfg

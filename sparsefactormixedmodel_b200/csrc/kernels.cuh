@@ -1,0 +1,583 @@
+// Non-GEMM kernels of the BSFG sweep (sm_100a): element-wise producers, the per-trait k x k
+// Cholesky solve, the discrete h2 grid draws, triangular row solves, Gamma draws and reductions.
+// All matrices are column-major FP64 with explicit leading dimensions.
+#pragma once
+#include "common.cuh"
+
+namespace bsfg {
+
+// variate source: injected (ptr != null, column-major with leading dimension ld) or device Philox
+struct VarSrc {
+    const double* ptr;
+    long ld;
+    RngStream rs;
+    long col_offset;   // global index of local column 0 (trait sharding) for Philox addressing
+    long rows_total;   // rows of the full logical block (for Philox element index)
+};
+__device__ __forceinline__ double var_normal(const VarSrc& v, long row, long col) {
+    if (v.ptr) return v.ptr[col * v.ld + row];
+    return philox_normal(v.rs, (uint64_t)((col + v.col_offset) * v.rows_total + row));
+}
+__device__ __forceinline__ double var_uniform(const VarSrc& v, long row, long col) {
+    if (v.ptr) return v.ptr[col * v.ld + row];
+    return philox_uniform(v.rs, (uint64_t)((col + v.col_offset) * v.rows_total + row));
+}
+__device__ __forceinline__ double var_gamma(const VarSrc& v, long row, long col, double shape) {
+    if (v.ptr) return v.ptr[col * v.ld + row];
+    return philox_gamma(v.rs, (uint64_t)((col + v.col_offset) * v.rows_total + row), shape);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum, result valid in thread 0 (and broadcast through smem to all)
+__device__ __forceinline__ double block_sum(double v, double* red /* >= 32 doubles */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) {
+        t = warp_sum(t);
+        if (l == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+// ------------------------------------------------------------------------------------
+// transpose: out (cols x rows, ldo) = in' (rows x cols, ldi), optional row scaling of `in`
+// (out[c][r] = in[r][c] * rowscale[r] if rowscale) -- 32x32 tiles through padded smem.
+// ------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const double* __restrict__ in, long ldi, long rows, long cols,
+                                 double* __restrict__ out, long ldo) {
+    __shared__ double tile[32][33];
+    const long r0 = (long)blockIdx.x * 32, c0 = (long)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        long r = r0 + threadIdx.x, c = c0 + j;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[c * ldi + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        long c = c0 + threadIdx.x, r = r0 + j;
+        if (r < rows && c < cols) out[r * ldo + c] = tile[threadIdx.x][j];
+    }
+}
+
+// out[r,c] = in[r,c] * rowscale[r] (rowscale may be null) * colscale[c] (may be null)
+__global__ void scale_kernel(const double* __restrict__ in, long ldi, long rows, long cols,
+                             const double* __restrict__ rowscale, const double* __restrict__ colscale,
+                             double* __restrict__ out, long ldo) {
+    const long total = rows * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long r = idx % rows, c = idx / rows;
+        double v = in[c * ldi + r];
+        if (rowscale) v *= rowscale[r];
+        if (colscale) v *= colscale[c];
+        out[c * ldo + r] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// sample_Lambda producers
+// ------------------------------------------------------------------------------------
+// Khatri-Rao ("Gram feature") build: Gt[i, pair(a,b)] = UtF[i,a] * UtF[i,b], a >= b,
+// pair = a(a+1)/2 + b.  The weighted Gram Qlam_j = sum_i w_ij f_i f_i' (cpp:120-122) then is the
+// plain GEMM  Q = Gt' W.
+__global__ void gram_features_kernel(const double* __restrict__ UtF, long ldf, int n, int k,
+                                     double* __restrict__ Gt, long ldg) {
+    const int pair = blockIdx.y;
+    int a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);
+    while ((a + 1) * (a + 2) / 2 <= pair) a++;
+    while (a * (a + 1) / 2 > pair) a--;
+    const int b = pair - a * (a + 1) / 2;
+    const double* fa = UtF + (long)a * ldf;
+    const double* fb = UtF + (long)b * ldf;
+    double* g = Gt + (long)pair * ldg;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) g[i] = fa[i] * fb[i];
+}
+
+// W[i,j]  = ep_j / (s_i + ep_j / rp_j)                                   (cpp:120, the sweep weights)
+// WY[i,j] = W[i,j] * (UtY[i,j] - sum_c UtX[i,c] B[c,j])                  (U'(Y - X B), R:189 rotated)
+__global__ void lambda_weights_kernel(const double* __restrict__ UtY, long ldy, int n, int p,
+                                      const double* __restrict__ s, const double* __restrict__ rp,
+                                      const double* __restrict__ ep, const double* __restrict__ UtX, long ldx,
+                                      const double* __restrict__ B, long ldb, int b,
+                                      double* __restrict__ W, long ldw, double* __restrict__ WY, long ldwy) {
+    const int j = blockIdx.y;
+    if (j >= p) return;
+    const double epj = ep[j];
+    const double c = epj / rp[j];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double w = epj / (s[i] + c);
+        double y = UtY[(long)j * ldy + i];
+        for (int cc = 0; cc < b; cc++) y -= UtX[(long)cc * ldx + i] * B[(long)j * ldb + cc];
+        W[(long)j * ldw + i] = w;
+        WY[(long)j * ldwy + i] = w * y;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Batched k x k Cholesky + the three triangular solves of cpp:124-130, one CTA per system.
+//   Q_j   = unpack(Qp[:, j]) + diag(dadd_j)        (packed lower, pair = a(a+1)/2 + b)
+//   L L'  = Q_j                                     (L = t(chol(Qlam)), cpp:124)
+//   out_j = L'^-1 (L^-1 m_j + z_j)                 (= mlam + ylam, cpp:125-130)
+// Shared memory: packed L (k(k+1)/2 doubles) + 2k doubles.  If Lout != null the factor is also
+// written (packed) -- used by sample_factors_scores for its single k x k system.
+// ------------------------------------------------------------------------------------
+template <int KT>   // KT = ceil(k/32) entries per lane in the solve phase
+__global__ void __launch_bounds__(128)
+chol_solve_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys,
+                  const double* __restrict__ dadd, long dadd_sys_stride, long dadd_elem_stride,
+                  const double* __restrict__ rhs, long ldr, VarSrc zsrc,
+                  double* __restrict__ out, long ldo, double* __restrict__ Lout, int* __restrict__ fail_flag) {
+    extern __shared__ double sm[];
+    const int npairs = k * (k + 1) / 2;
+    double* L = sm;
+    double* vec = sm + npairs;      // k
+    const int sys = blockIdx.x;
+    if (sys >= nsys) return;
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    const double* q = Qp + (long)sys * ldq;
+    for (int idx = tid; idx < npairs; idx += T) L[idx] = q[idx];
+    __syncthreads();
+    if (dadd) {
+        for (int a = tid; a < k; a += T) L[a * (a + 1) / 2 + a] += dadd[(long)sys * dadd_sys_stride + (long)a * dadd_elem_stride];
+    }
+    __syncthreads();
+
+    // right-looking Cholesky on the packed lower triangle, rows dealt cyclically to threads
+    bool bad = false;
+    for (int j = 0; j < k; j++) {
+        const int jj = j * (j + 1) / 2 + j;
+        const double djj = L[jj];
+        if (!(djj > 0.0)) { bad = true; break; }     // uniform across the block (same smem value)
+        const double dinv = 1.0 / sqrt(djj);
+        __syncthreads();                              // everyone has read L[jj] before it is overwritten
+        if (tid == 0) L[jj] = sqrt(djj);
+        for (int i = j + 1 + tid; i < k; i += T) L[i * (i + 1) / 2 + j] *= dinv;
+        __syncthreads();
+        for (int i = j + 1 + tid; i < k; i += T) {
+            const double lij = L[i * (i + 1) / 2 + j];
+            double* row = L + i * (i + 1) / 2;
+            for (int l = j + 1; l <= i; l++) row[l] -= lij * L[l * (l + 1) / 2 + j];
+        }
+        __syncthreads();
+    }
+    if (bad) {
+        if (tid == 0) atomicMax(fail_flag, sys + 1);
+        return;
+    }
+    if (Lout) {
+        for (int idx = tid; idx < npairs; idx += T) Lout[(long)sys * npairs + idx] = L[idx];
+    }
+    if (!out) return;
+
+    // ---- solves, warp 0 only: lane owns entries i = lane + 32 t ----
+    if (tid >= 32) return;
+    const int lane = tid;
+    double x[KT];
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+        const int i = lane + 32 * t;
+        x[t] = (i < k) ? rhs[(long)sys * ldr + i] : 0.0;
+    }
+    // forward: v_i = (m_i - sum_{j<i} L[i][j] v_j) / L[i][i]   (row-oriented dot products)
+    for (int i = 0; i < k; i++) {
+        const double* row = L + i * (i + 1) / 2;
+        double part = 0.0;
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            const int j = lane + 32 * t;
+            if (j < i) part += row[j] * x[t];
+        }
+        part = warp_sum(part);
+        const int own = i & 31, ti = i >> 5;
+#pragma unroll
+        for (int t = 0; t < KT; t++)
+            if (t == ti && lane == own) x[t] = (x[t] - part) / row[i];
+    }
+    // w = v + z
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+        const int i = lane + 32 * t;
+        if (i < k) x[t] += var_normal(zsrc, i, sys);
+    }
+    // backward: x_j = w_j / L[j][j]; w_i -= L[j][i] x_j for i < j   (rows of L are contiguous)
+    for (int j = k - 1; j >= 0; j--) {
+        const double* row = L + j * (j + 1) / 2;
+        const int own = j & 31, tj = j >> 5;
+        double xj = 0.0;
+#pragma unroll
+        for (int t = 0; t < KT; t++)
+            if (t == tj) xj = x[t];
+        xj = __shfl_sync(0xffffffffu, xj, own) / row[j];
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            const int i = lane + 32 * t;
+            if (t == tj && lane == own) x[t] = xj;
+            else if (i < j) x[t] -= row[i] * xj;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+        const int i = lane + 32 * t;
+        if (i < k) out[(long)sys * ldo + i] = x[t];
+    }
+}
+
+// pack a full symmetric k x k (column-major, ld) into packed-lower order
+__global__ void pack_lower_kernel(const double* __restrict__ A, long ld, int k, double* __restrict__ out) {
+    const int npairs = k * (k + 1) / 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += gridDim.x * blockDim.x) {
+        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= idx) a++;
+        while (a * (a + 1) / 2 > idx) a--;
+        const int b = idx - a * (a + 1) / 2;
+        out[idx] = A[(long)b * ld + a];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// sample_factors_scores row solves (cpp:152-160): for each individual i (a row of rhs),
+//   F[i,:] = L'^-1 ( L^-1 rhs[i,:]' + z[i,:]' ),  L packed lower from the k x k Cholesky.
+// One warp per row; L staged in shared memory once per CTA.
+// rhs[i,h] = YL[i,h] + ZFa[i,h] * tau_e[h]  is formed on the fly.
+// ------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256)
+factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __restrict__ YL, long ldy,
+                   const double* __restrict__ ZFa, long ldz, const double* __restrict__ tau_e, VarSrc zsrc,
+                   double* __restrict__ Fout, long ldf) {
+    extern __shared__ double sm[];
+    const int npairs = k * (k + 1) / 2;
+    for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) sm[idx] = Lp[idx];
+    __syncthreads();
+    const double* L = sm;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int row_i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row_i < n; row_i += gridDim.x * warps_per_block) {
+        double x[KT];
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            const int h = lane + 32 * t;
+            x[t] = 0.0;
+            if (h < k) {
+                double v = YL[(long)h * ldy + row_i];
+                if (ZFa) v += ZFa[(long)h * ldz + row_i] * tau_e[h];
+                x[t] = v;
+            }
+        }
+        for (int i = 0; i < k; i++) {
+            const double* row = L + i * (i + 1) / 2;
+            double part = 0.0;
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                const int j = lane + 32 * t;
+                if (j < i) part += row[j] * x[t];
+            }
+            part = warp_sum(part);
+            const int own = i & 31, ti = i >> 5;
+#pragma unroll
+            for (int t = 0; t < KT; t++)
+                if (t == ti && lane == own) x[t] = (x[t] - part) / row[i];
+        }
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            const int h = lane + 32 * t;
+            if (h < k) x[t] += var_normal(zsrc, row_i, h);      // z is n x k: element (i, h)
+        }
+        for (int j = k - 1; j >= 0; j--) {
+            const double* row = L + j * (j + 1) / 2;
+            const int own = j & 31, tj = j >> 5;
+            double xj = 0.0;
+#pragma unroll
+            for (int t = 0; t < KT; t++)
+                if (t == tj) xj = x[t];
+            xj = __shfl_sync(0xffffffffu, xj, own) / row[j];
+#pragma unroll
+            for (int t = 0; t < KT; t++) {
+                const int i = lane + 32 * t;
+                if (t == tj && lane == own) x[t] = xj;
+                else if (i < j) x[t] -= row[i] * xj;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KT; t++) {
+            const int h = lane + 32 * t;
+            if (h < k) Fout[(long)h * ldf + row_i] = x[t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// sample_means element-wise step (cpp:75-78 without the U product):
+//   theta[i,j] = (DtYt[i,j] * rp_j) / d + z[i,j] / sqrt(d),  d = s1_i ep_j + s2_i rp_j
+// ------------------------------------------------------------------------------------
+__global__ void means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
+                                   const double* __restrict__ s1, const double* __restrict__ s2,
+                                   const double* __restrict__ rp, const double* __restrict__ ep, VarSrc zsrc,
+                                   double* __restrict__ theta, long ldt) {
+    const int j = blockIdx.y;
+    if (j >= p) return;
+    const double rpj = rp[j], epj = ep[j];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < br; i += gridDim.x * blockDim.x) {
+        const double d = s1[i] * epj + s2[i] * rpj;
+        const double mean = (DtYt[(long)j * ldd + i] * rpj) / d;
+        theta[(long)j * ldt + i] = mean + var_normal(zsrc, i, j) / sqrt(d);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// discrete h2 grid (cpp:196-238): three small kernels.
+// ------------------------------------------------------------------------------------
+// det[i] = sum_l log((s_l + (1-h2)/h2) * h2) / 2, h2 = i/H, i >= 1; det[0] = 0      (cpp:216)
+__global__ void h2_det_kernel(const double* __restrict__ s, int n, int H, double* __restrict__ det) {
+    __shared__ double red[32];
+    const int i = blockIdx.x;
+    if (i == 0) {
+        if (threadIdx.x == 0) det[0] = 0.0;
+        return;
+    }
+    const double h2 = (double)i / (double)H;
+    const double c = (1.0 - h2) / h2;
+    double acc = 0.0;
+    for (int l = threadIdx.x; l < n; l += blockDim.x) acc += log((s[l] + c) * h2) / 2.0;
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) det[i] = acc;
+}
+
+// ss[j,i] = sum_l dnorm_std_log(x_{j,i,l});  x = 1/sqrt(h2) * UtF[l,j] / sqrt(s_l + (1-h2)/h2)  (cpp:215)
+// i = 0 uses F itself (cpp:218).  One warp per (factor, grid point).
+__global__ void h2_loglik_kernel(const double* __restrict__ UtF, long ldu, const double* __restrict__ F, long ldf,
+                                 const double* __restrict__ s, int n, int k, int H,
+                                 double* __restrict__ ll /* k x H, ld k */) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= k * H) return;
+    const int j = warp_global % k, i = warp_global / k;
+    const double c0 = -0.91893853320467274178;     // log(1/sqrt(2 pi)), cpp:23
+    double acc = 0.0;
+    if (i == 0) {
+        const double* f = F + (long)j * ldf;
+        for (int l = lane; l < n; l += 32) { const double x = f[l]; acc += c0 - 0.5 * (x * x); }
+    } else {
+        const double h2 = (double)i / (double)H;
+        const double c = (1.0 - h2) / h2;
+        const double ih = 1.0 / sqrt(h2);
+        const double* f = UtF + (long)j * ldu;
+        for (int l = lane; l < n; l += 32) {
+            const double x = ih * (f[l] * (1.0 / sqrt(s[l] + c)));
+            acc += c0 - 0.5 * (x * x);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) ll[(long)i * k + j] = acc;
+}
+
+// log_ps[j,i] = ll[j,i] - det[i] (+ extra[j,i]) + log(prior[i]); LSE-normalise; cumsum; count (cpp:226-235)
+// One warp per row j; the 50-term normalise/cumsum runs sequentially on lane 0 in grid order,
+// like the reference, so an index can only differ when u is within rounding of a cumsum edge.
+__global__ void grid_draw_kernel(const double* __restrict__ ll, long ldl, const double* __restrict__ det, long det_ld,
+                                 int det_per_row, const double* __restrict__ prior, int rows, int H, VarSrc usrc,
+                                 double* __restrict__ out_h2, double* __restrict__ log_ps_out, long ldlp) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= rows) return;
+    extern __shared__ double smg[];
+    double* lp = smg + (threadIdx.x >> 5) * H;
+    double mx = -INFINITY;
+    for (int i = lane; i < H; i += 32) {
+        const double d = det_per_row ? det[(long)i * det_ld + j] : det[i];
+        const double v = ll[(long)i * ldl + j] - d + log(prior[i]);
+        lp[i] = v;
+        if (log_ps_out) log_ps_out[(long)i * ldlp + j] = v;
+        mx = fmax(mx, v);
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    if (lane == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < H; i++) sum += exp(lp[i] - mx);
+        const double norm = mx + log(sum);
+        const double u = var_uniform(usrc, j, 0);
+        double cum = 0.0;
+        int count = 0;
+        for (int i = 0; i < H; i++) {
+            cum += exp(lp[i] - norm);
+            if (u > cum) count++;
+        }
+        out_h2[j] = (double)count / (double)H;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// sample_prec_discrete_conditional_c (cpp:241-289) log-likelihood table.  One warp per
+// (trait, grid point).  ll[j,i] = sum_l dnorm_std_log(x);  det[j,i] per cpp:270-274.
+// ------------------------------------------------------------------------------------
+__global__ void prec_logdet_s_kernel(const double* __restrict__ s, int n, int H, double* __restrict__ slog) {
+    // slog[i] = sum_l log(s_l + (1-h2)/h2), i >= 1
+    __shared__ double red[32];
+    const int i = blockIdx.x;
+    if (i == 0) { if (threadIdx.x == 0) slog[0] = 0.0; return; }
+    const double h2 = (double)i / (double)H;
+    const double c = (1.0 - h2) / h2;
+    double acc = 0.0;
+    for (int l = threadIdx.x; l < n; l += blockDim.x) acc += log(s[l] + c);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) slog[i] = acc;
+}
+
+__global__ void prec_loglik_kernel(const double* __restrict__ UtY, long ldu, const double* __restrict__ Y, long ldy,
+                                   const double* __restrict__ s, const double* __restrict__ slog,
+                                   const double* __restrict__ res_prec, int n, int p, int H,
+                                   double* __restrict__ ll /* p x H ld p */, double* __restrict__ det /* p x H ld p */) {
+    const long warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= (long)p * H) return;
+    const int j = (int)(warp_global % p), i = (int)(warp_global / p);
+    const double c0 = -0.91893853320467274178;
+    const double rp = res_prec[j];
+    double acc = 0.0;
+    if (i == 0) {
+        const double sq = sqrt(rp);
+        const double* y = Y + (long)j * ldy;
+        for (int l = lane; l < n; l += 32) { const double x = y[l] * sq; acc += c0 - 0.5 * (x * x); }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            ll[(long)i * p + j] = acc;
+            det[(long)i * p + j] = (double)(n / 2) * log(1.0 / rp);      // integer n/2, cpp:274
+        }
+    } else {
+        const double h2 = (double)i / (double)H;
+        const double c = (1.0 - h2) / h2;
+        const double b2 = h2 / (rp * (1.0 - h2));
+        const double ib = 1.0 / sqrt(b2);
+        const double* y = UtY + (long)j * ldu;
+        for (int l = lane; l < n; l += 32) {
+            const double x = (y[l] * (1.0 / sqrt(s[l] + c))) * ib;
+            acc += c0 - 0.5 * (x * x);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            ll[(long)i * p + j] = acc;
+            // sum_l log((s_l + c) * b2)/2 = (slog_i + n log b2)/2     (cpp:270-271, factored)
+            det[(long)i * p + j] = 0.5 * (slog[i] + (double)n * log(b2));
+        }
+    }
+}
+
+__global__ void prec_from_h2_kernel(const double* __restrict__ res_prec, const double* __restrict__ h2, int p,
+                                    double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p) out[j] = (res_prec[j] * (1.0 - h2[j])) / h2[j];          // cpp:286 (h2 == 0 -> Inf, kept)
+}
+
+// ------------------------------------------------------------------------------------
+// sample_F_a element-wise step (cpp:320-333 before the U product):
+//   v[i,j] = b3[i,j]*tau_e_j / d + z[i,j]/sqrt(d),  d = s2_i tau_u_j + s1_i tau_e_j
+// (b3 = U3' Z_1' F; the column scaling by tau_e of cpp:311 commutes with the products)
+// columns with tau_e == 1 or tau_e > 10000 are zeroed here and patched by fa_fixup_kernel.
+// ------------------------------------------------------------------------------------
+__global__ void fa_v_kernel(const double* __restrict__ b3, long ldb, int r, int k, const double* __restrict__ F_h2,
+                            const double* __restrict__ s1, const double* __restrict__ s2, VarSrc zsrc,
+                            double* __restrict__ v, long ldv) {
+    const int j = blockIdx.y;
+    if (j >= k) return;
+    const double h2 = F_h2[j];
+    const double tau_e = 1.0 / (1.0 - h2), tau_u = 1.0 / h2;
+    const bool special = (tau_e == 1.0) || (tau_e > 10000.0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x) {
+        double out = 0.0;
+        if (!special) {
+            const double d = s2[i] * tau_u + s1[i] * tau_e;
+            out = (b3[(long)j * ldb + i] * tau_e) / d + var_normal(zsrc, i, j) / sqrt(d);
+        }
+        v[(long)j * ldv + i] = out;
+    }
+}
+__global__ void fa_fixup_kernel(const double* __restrict__ F, long ldf, int n, int r, int k,
+                                const double* __restrict__ F_h2, double* __restrict__ Fa, long lda) {
+    const int j = blockIdx.y;
+    if (j >= k) return;
+    const double tau_e = 1.0 / (1.0 - F_h2[j]);
+    if (tau_e == 1.0) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x) Fa[(long)j * lda + i] = 0.0;
+    } else if (tau_e > 10000.0) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x)
+            Fa[(long)j * lda + i] = (i < n) ? F[(long)j * ldf + i] : 0.0;
+    }
+}
+
+__global__ void tau_e_kernel(const double* __restrict__ F_h2, int k, double* __restrict__ tau_e) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) tau_e[j] = 1.0 / (1.0 - F_h2[j]);                          // cpp:147
+}
+
+// ------------------------------------------------------------------------------------
+// sample_delta (BSFG_functions.R:272-308)
+// ------------------------------------------------------------------------------------
+// colsum[h] = sum_j Lambda_prec[j,h] * Lambda2[j,h]   (one block per column)
+__global__ void delta_colsum_kernel(const double* __restrict__ LP, long ldp, const double* __restrict__ L2, long ldl,
+                                    int p, int k, int square_l2, double* __restrict__ colsum) {
+    __shared__ double red[32];
+    const int h = blockIdx.x;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+        double l = L2[(long)h * ldl + j];
+        if (square_l2) l = l * l;
+        acc += LP[(long)h * ldp + j] * l;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) colsum[h] = acc;
+}
+// the scalar recursion; one thread.  Loop order = R's 2:(k-1) (counts down when k == 2).
+__global__ void delta_recursion_kernel(double* __restrict__ delta, int k, const double* __restrict__ colsum,
+                                       double n_genes, double d1s, double d1r, double d2s, double d2r,
+                                       VarSrc gsrc, double* __restrict__ tauh_out, double* __restrict__ shapes,
+                                       double* __restrict__ rates, int* __restrict__ ndraws) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    extern __shared__ double tauh[];
+    double cp = 1.0;
+    for (int h = 0; h < k; h++) { cp *= delta[h]; tauh[h] = cp; }
+    int draw = 0;
+    {
+        const double shape = d1s + 0.5 * n_genes * k;
+        double acc = 0.0;
+        for (int h = 0; h < k; h++) acc += tauh[h] * colsum[h];
+        const double rate = d1r + 0.5 * (1.0 / delta[0]) * acc;
+        if (shapes) shapes[draw] = shape;
+        if (rates) rates[draw] = rate;
+        delta[0] = var_gamma(gsrc, draw, 0, shape) / rate;
+        draw++;
+        cp = 1.0;
+        for (int h = 0; h < k; h++) { cp *= delta[h]; tauh[h] = cp; }
+    }
+    const int hi = k - 1;
+    const int step = (hi >= 2) ? 1 : -1;
+    for (int h = 2; (step > 0) ? (h <= hi) : (h >= hi); h += step) {   // 1-based h
+        const double shape = d2s + 0.5 * n_genes * (k - h + 1);
+        double acc = 0.0;
+        for (int l = h - 1; l < k; l++) acc += tauh[l] * colsum[l];
+        const double rate = d2r + 0.5 * (1.0 / delta[h - 1]) * acc;
+        if (shapes) shapes[draw] = shape;
+        if (rates) rates[draw] = rate;
+        delta[h - 1] = var_gamma(gsrc, draw, 0, shape) / rate;
+        draw++;
+        cp = 1.0;
+        for (int l = 0; l < k; l++) { cp *= delta[l]; tauh[l] = cp; }
+    }
+    if (tauh_out) for (int h = 0; h < k; h++) tauh_out[h] = tauh[h];
+    if (ndraws) *ndraws = draw;
+}
+
+}  // namespace bsfg

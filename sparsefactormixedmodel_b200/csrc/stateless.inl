@@ -1,0 +1,496 @@
+// Stateless drop-ins: one C-ABI entry per Rcpp export (BSFG_functions_c.cpp) + sample_delta_c.
+// Copy in -> kernels -> copy out.  Included by bsfg.cu.
+
+namespace bsfg {
+
+struct Device {
+    cudaStream_t st = nullptr;
+    int sms = 0;
+    DVec ws;          // split-K workspace
+    int* d_flag = nullptr;
+    static constexpr size_t WS_DOUBLES = (size_t)160 * 128 * 128;
+    void init() {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail(BSFG_ECUDA, "no CUDA device: libbsfg_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+        int dev = 0;
+        BSFG_CUDA(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        BSFG_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10) fail(BSFG_ECUDA, "libbsfg_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+        sms = prop.multiProcessorCount;
+        BSFG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ws.alloc(WS_DOUBLES);
+        BSFG_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+        BSFG_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
+    }
+    void sync() { BSFG_CUDA(cudaStreamSynchronize(st)); }
+    // C = alpha * At' * B + beta * C
+    void gemm(int M, int N, int K, double alpha, const double* At, long lda, const double* B, long ldb,
+              double beta, double* C, long ldc) {
+        dgemm_tn(st, sms, M, N, K, alpha, At, lda, B, ldb, beta, C, ldc, C, ldc, ws.p, WS_DOUBLES);
+    }
+    void gemm(double alpha, const DMat& At, const DMat& B, double beta, DMat& C) {
+        if (At.rows != B.rows || C.rows != At.cols || C.cols != B.cols)
+            fail(BSFG_ESHAPE, "gemm shape mismatch: At %ldx%ld B %ldx%ld C %ldx%ld", At.rows, At.cols, B.rows, B.cols, C.rows, C.cols);
+        gemm((int)At.cols, (int)B.cols, (int)At.rows, alpha, At.p, At.ld, B.p, B.ld, beta, C.p, C.ld);
+    }
+    void transpose(const DMat& in, DMat& out) {
+        if (out.rows != in.cols || out.cols != in.rows) fail(BSFG_ESHAPE, "transpose shape mismatch");
+        if (in.rows == 0 || in.cols == 0) return;
+        dim3 grid(ceil_div(in.rows, 32), ceil_div(in.cols, 32)), block(32, 8);
+        transpose_kernel<<<grid, block, 0, st>>>(in.p, in.ld, in.rows, in.cols, out.p, out.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    void scale(const DMat& in, const double* rowscale, const double* colscale, DMat& out) {
+        const long total = in.rows * in.cols;
+        if (!total) return;
+        int blocks = (int)std::min<long>((total + 255) / 256, (long)sms * 16);
+        scale_kernel<<<blocks, 256, 0, st>>>(in.p, in.ld, in.rows, in.cols, rowscale, colscale, out.p, out.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    int read_flag_and_clear() {
+        int h = 0;
+        BSFG_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        sync();
+        if (h) BSFG_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        return h;
+    }
+};
+
+static Device& default_device() {
+    static thread_local Device* dev = nullptr;
+    if (!dev) {
+        Device* d = new Device();
+        d->init();
+        dev = d;
+    }
+    return *dev;
+}
+
+static VarSrc make_var(const DMat* injected, uint64_t seed, uint32_t site, uint32_t iter, long col_offset, long rows_total) {
+    VarSrc v;
+    v.ptr = injected ? injected->p : nullptr;
+    v.ld = injected ? injected->ld : 0;
+    v.rs.seed = seed; v.rs.site = site; v.rs.iter = iter;
+    v.col_offset = col_offset; v.rows_total = rows_total;
+    return v;
+}
+
+// ---- reusable device-level pieces (also used by the sweep) -----------------------------------
+static int kt_for(int k) {
+    if (k <= 32) return 1;
+    if (k <= 64) return 2;
+    if (k <= 128) return 4;
+    if (k <= 256) return 8;
+    fail(BSFG_ESHAPE, "k = %d exceeds the supported maximum of 256 factors", k);
+}
+
+static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int nsys, const double* dadd,
+                              long dadd_sys_stride, long dadd_elem_stride, const double* rhs, long ldr,
+                              const VarSrc& z, double* out, long ldo, double* Lout) {
+    if (nsys <= 0) return;
+    const size_t smem = sizeof(double) * ((size_t)k * (k + 1) / 2 + 2 * (size_t)k);
+    if (smem > 227 * 1024) fail(BSFG_ESHAPE, "k = %d: packed Cholesky tile (%zu B) exceeds shared memory", k, smem);
+#define BSFG_LAUNCH_CHOL(KT)                                                                                   \
+    do {                                                                                                       \
+        BSFG_CUDA(cudaFuncSetAttribute(chol_solve_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        chol_solve_kernel<KT><<<nsys, 128, smem, d.st>>>(Qp, ldq, k, nsys, dadd, dadd_sys_stride, dadd_elem_stride, \
+                                                         rhs, ldr, z, out, ldo, Lout, d.d_flag);            \
+    } while (0)
+    switch (kt_for(k)) {
+        case 1: BSFG_LAUNCH_CHOL(1); break;
+        case 2: BSFG_LAUNCH_CHOL(2); break;
+        case 4: BSFG_LAUNCH_CHOL(4); break;
+        default: BSFG_LAUNCH_CHOL(8); break;
+    }
+#undef BSFG_LAUNCH_CHOL
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+}
+
+static void launch_factor_rows(Device& d, const double* Lp, int k, int n, const double* YL, long ldy,
+                               const double* ZFa, long ldz, const double* tau_e, const VarSrc& z, double* F, long ldf) {
+    const size_t smem = sizeof(double) * ((size_t)k * (k + 1) / 2);
+    const int wpb = 8;
+    int blocks = std::min(ceil_div(n, wpb), d.sms * 4);
+#define BSFG_LAUNCH_FR(KT)                                                                                     \
+    do {                                                                                                       \
+        BSFG_CUDA(cudaFuncSetAttribute(factor_rows_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        factor_rows_kernel<KT><<<blocks, wpb * 32, smem, d.st>>>(Lp, k, n, YL, ldy, ZFa, ldz, tau_e, z, F, ldf); \
+    } while (0)
+    switch (kt_for(k)) {
+        case 1: BSFG_LAUNCH_FR(1); break;
+        case 2: BSFG_LAUNCH_FR(2); break;
+        case 4: BSFG_LAUNCH_FR(4); break;
+        default: BSFG_LAUNCH_FR(8); break;
+    }
+#undef BSFG_LAUNCH_FR
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+}
+
+// Lambda draw given rotated inputs.  UtF n x k, UtY n x p (rotated data), optional UtX (n x b), B (b x p).
+// Writes Lt (k x p).  Scratch: Gt (n x npairs), W, WY (n x p), Q (npairs x p), Mn (k x p).
+struct LambdaScratch {
+    DMat Gt, W, WY, Q, Mn;
+    void ensure(long n, long p, long k) {
+        const long np = k * (k + 1) / 2;
+        if (Gt.rows != n || Gt.cols != np) Gt.alloc(n, np);
+        if (W.rows != n || W.cols != p) { W.alloc(n, p); WY.alloc(n, p); }
+        if (Q.rows != np || Q.cols != p) Q.alloc(np, p);
+        if (Mn.rows != k || Mn.cols != p) Mn.alloc(k, p);
+    }
+};
+
+static void lambda_core(Device& d, LambdaScratch& sc, const DMat& UtF, const DMat& UtY, const double* s,
+                        const double* rp, const double* ep, const DMat* UtX, const DMat* B,
+                        const double* plam, long plam_sys_stride, long plam_elem_stride, const VarSrc& z,
+                        DMat& Lt) {
+    const int n = (int)UtF.rows, k = (int)UtF.cols, p = (int)UtY.cols;
+    const int np = k * (k + 1) / 2;
+    sc.ensure(n, p, k);
+    {
+        dim3 grid(std::min(ceil_div(n, 256), 64), np);
+        gram_features_kernel<<<grid, 256, 0, d.st>>>(UtF.p, UtF.ld, n, k, sc.Gt.p, sc.Gt.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    {
+        dim3 grid(std::min(ceil_div(n, 256), 64), p);
+        const int b = UtX ? (int)UtX->cols : 0;
+        lambda_weights_kernel<<<grid, 256, 0, d.st>>>(UtY.p, UtY.ld, n, p, s, rp, ep, UtX ? UtX->p : nullptr,
+                                                      UtX ? UtX->ld : 0, B ? B->p : nullptr, B ? B->ld : 0, b,
+                                                      sc.W.p, sc.W.ld, sc.WY.p, sc.WY.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    d.gemm(1.0, sc.Gt, sc.W, 0.0, sc.Q);       // Q[pair, j] = sum_i f_ia f_ib w_ij
+    d.gemm(1.0, UtF, sc.WY, 0.0, sc.Mn);       // m[a, j]    = sum_i f_ia w_ij y_ij
+    launch_chol_solve(d, sc.Q.p, sc.Q.ld, k, p, plam, plam_sys_stride, plam_elem_stride, sc.Mn.p, sc.Mn.ld, z,
+                      Lt.p, Lt.ld, nullptr);
+}
+
+static void check_notpd(Device& d, const char* what) {
+    int f = d.read_flag_and_clear();
+    if (f) fail(BSFG_ENOTPD, "chol(): decomposition failed in %s (system %d)", what, f - 1);
+}
+
+}  // namespace bsfg
+
+using namespace bsfg;
+
+#define BSFG_API_BEGIN try {
+#define BSFG_API_END                                   \
+    return BSFG_OK;                                    \
+    }                                                  \
+    catch (const bsfg::Error& e) {                     \
+        bsfg::set_last_error("%s", e.what());          \
+        return e.code;                                 \
+    }                                                  \
+    catch (const std::exception& e) {                  \
+        bsfg::set_last_error("%s", e.what());          \
+        return BSFG_ECUDA;                             \
+    }
+
+#define REQUIRE_PTR(p) do { if (!(p)) bsfg::fail(BSFG_EARG, "argument %s is NULL", #p); } while (0)
+
+extern "C" int bsfg_dgemm_tn_host(int M, int N, int K, double alpha, const double* At, int lda, const double* B,
+                                  int ldb, double beta, double* C, int ldc) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(At); REQUIRE_PTR(B); REQUIRE_PTR(C);
+    if (lda < K || ldb < K || ldc < M) fail(BSFG_ESHAPE, "bsfg_dgemm_tn_host: leading dimension too small");
+    Device& d = default_device();
+    DMat dA(K, M), dB(K, N), dC(M, N);
+    BSFG_CUDA(cudaMemcpy2DAsync(dA.p, dA.ld * 8, At, (size_t)lda * 8, (size_t)K * 8, M, cudaMemcpyHostToDevice, d.st));
+    BSFG_CUDA(cudaMemcpy2DAsync(dB.p, dB.ld * 8, B, (size_t)ldb * 8, (size_t)K * 8, N, cudaMemcpyHostToDevice, d.st));
+    if (beta != 0.0)
+        BSFG_CUDA(cudaMemcpy2DAsync(dC.p, dC.ld * 8, C, (size_t)ldc * 8, (size_t)M * 8, N, cudaMemcpyHostToDevice, d.st));
+    d.gemm(alpha, dA, dB, beta, dC);
+    BSFG_CUDA(cudaMemcpy2DAsync(C, (size_t)ldc * 8, dC.p, dC.ld * 8, (size_t)M * 8, N, cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    BSFG_API_END
+}
+
+// ---- sample_Lambda_c (cpp:86-135) -------------------------------------------------------------
+extern "C" int bsfg_sample_Lambda_c(const double* Y_tilde, int n, int p, const double* F, int k,
+                                    const double* resid_Y_prec, const double* E_a_prec, const double* Plam,
+                                    const double* U, const double* s, const double* z, unsigned long long seed,
+                                    double* Lambda_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(Y_tilde); REQUIRE_PTR(F); REQUIRE_PTR(resid_Y_prec); REQUIRE_PTR(E_a_prec); REQUIRE_PTR(Plam);
+    REQUIRE_PTR(U); REQUIRE_PTR(s); REQUIRE_PTR(Lambda_out);
+    if (n <= 0 || p <= 0 || k <= 0) fail(BSFG_ESHAPE, "sample_Lambda_c: n, p, k must be positive");
+    Device& d = default_device();
+    DMat dY(n, p), dF(n, k), dU(n, n), dPlam(p, k), dZ, UtF(n, k), UtY(n, p), Lt(k, p), Lam(p, k);
+    DVec ds(n), drp(p), dep(p);
+    dY.upload(Y_tilde, d.st); dF.upload(F, d.st); dU.upload(U, d.st); dPlam.upload(Plam, d.st);
+    ds.upload(s, d.st); drp.upload(resid_Y_prec, d.st); dep.upload(E_a_prec, d.st);
+    if (z) { dZ.alloc(k, p); dZ.upload(z, d.st); }
+    d.gemm(1.0, dU, dF, 0.0, UtF);       // U'F  = t(FtU), cpp:107
+    d.gemm(1.0, dU, dY, 0.0, UtY);       // U'Y_tilde, cpp:108
+    LambdaScratch sc;
+    VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_LAMBDA, 0, 0, k);
+    lambda_core(d, sc, UtF, UtY, ds.p, drp.p, dep.p, nullptr, nullptr, dPlam.p, 1, dPlam.ld, zs, Lt);
+    d.transpose(Lt, Lam);
+    Lam.download(Lambda_out, d.st);
+    check_notpd(d, "sample_Lambda_c");
+    BSFG_API_END
+}
+extern "C" int bsfg_sample_lambda_c(const double* Y_tilde, int n, int p, const double* F, int k,
+                                    const double* resid_Y_prec, const double* E_a_prec, const double* Plam,
+                                    const double* U, const double* s, const double* z, unsigned long long seed,
+                                    double* Lambda_out) {
+    return bsfg_sample_Lambda_c(Y_tilde, n, p, F, k, resid_Y_prec, E_a_prec, Plam, U, s, z, seed, Lambda_out);
+}
+
+// ---- sample_means_c (cpp:43-82) ---------------------------------------------------------------
+extern "C" int bsfg_sample_means_c(const double* Y_tilde, int n, int p, const double* resid_Y_prec,
+                                   const double* E_a_prec, const double* U, const double* s1, const double* s2,
+                                   const double* Design_U, int br, const double* z, unsigned long long seed,
+                                   double* location_sample_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(Y_tilde); REQUIRE_PTR(resid_Y_prec); REQUIRE_PTR(E_a_prec); REQUIRE_PTR(U); REQUIRE_PTR(s1);
+    REQUIRE_PTR(s2); REQUIRE_PTR(Design_U); REQUIRE_PTR(location_sample_out);
+    if (n <= 0 || p <= 0 || br <= 0) fail(BSFG_ESHAPE, "sample_means_c: n, p, br must be positive");
+    Device& d = default_device();
+    DMat dY(n, p), dU(br, br), dUt(br, br), dD(n, br), dZ, DtY(br, p), theta(br, p), out(br, p);
+    DVec ds1(br), ds2(br), drp(p), dep(p);
+    dY.upload(Y_tilde, d.st); dU.upload(U, d.st); dD.upload(Design_U, d.st);
+    ds1.upload(s1, d.st); ds2.upload(s2, d.st); drp.upload(resid_Y_prec, d.st); dep.upload(E_a_prec, d.st);
+    if (z) { dZ.alloc(br, p); dZ.upload(z, d.st); }
+    d.gemm(1.0, dD, dY, 0.0, DtY);                       // Design_U' Y_tilde, cpp:65
+    VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_MEANS, 0, 0, br);
+    {
+        dim3 grid(std::min(ceil_div(br, 256), 64), p);
+        means_theta_kernel<<<grid, 256, 0, d.st>>>(DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p, theta.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    d.transpose(dU, dUt);
+    d.gemm(1.0, dUt, theta, 0.0, out);                   // U * (mlam + z/sqrt(d)), cpp:78
+    out.download(location_sample_out, d.st);
+    d.sync();
+    BSFG_API_END
+}
+
+// ---- sample_factors_scores_c / px (cpp:138-193) -----------------------------------------------
+static void factor_scores_impl(const double* Y_tilde, int n, int p, const double* Z_1, int r, const double* Lambda,
+                               int k, const double* resid_Y_prec, const double* F_a, const double* F_h2,
+                               const double* tau_e_host, const double* z, unsigned long long seed, double* F_out) {
+    REQUIRE_PTR(Y_tilde); REQUIRE_PTR(Lambda); REQUIRE_PTR(resid_Y_prec); REQUIRE_PTR(F_a); REQUIRE_PTR(F_out);
+    if (!F_h2 && !tau_e_host) fail(BSFG_EARG, "F_h2 / tau_e is NULL");
+    if (n <= 0 || p <= 0 || k <= 0 || r < 0) fail(BSFG_ESHAPE, "sample_factors_scores_c: bad sizes");
+    Device& d = default_device();
+    DMat dY(n, p), dYt(p, n), dL(p, k), Lmsg(p, k), dFa(std::max(r, 1), k), LtL(k, k), YL(n, k), ZFa, dZ, Fo(n, k);
+    DVec drp(p), dtau(k), dh2(k), Lp((long)k * (k + 1) / 2);
+    dY.upload(Y_tilde, d.st); dL.upload(Lambda, d.st); drp.upload(resid_Y_prec, d.st);
+    if (z) { dZ.alloc(n, k); dZ.upload(z, d.st); }
+    if (tau_e_host) dtau.upload(tau_e_host, d.st);
+    else {
+        dh2.upload(F_h2, d.st);
+        tau_e_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(dh2.p, k, dtau.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    d.scale(dL, drp.p, nullptr, Lmsg);                   // Lmsg = Lambda * resid_Y_prec (rows), cpp:146
+    d.gemm(1.0, dL, Lmsg, 0.0, LtL);                     // Lambda' Lmsg, cpp:149
+    d.transpose(dY, dYt);
+    d.gemm(1.0, dYt, Lmsg, 0.0, YL);                     // Y_tilde * Lmsg, cpp:152
+    if (r > 0) {
+        REQUIRE_PTR(Z_1);
+        DMat dZ1(n, r), dZ1t(r, n);
+        dZ1.upload(Z_1, d.st);
+        dFa.upload(F_a, d.st);
+        ZFa.alloc(n, k);
+        d.transpose(dZ1, dZ1t);
+        d.gemm(1.0, dZ1t, dFa, 0.0, ZFa);                // Z_1 * F_a, cpp:152
+        d.sync();                                        // dZ1/dZ1t go out of scope
+    }
+    pack_lower_kernel<<<ceil_div((long)k * (k + 1) / 2, 256), 256, 0, d.st>>>(LtL.p, LtL.ld, k, Lp.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    DVec Lfac((long)k * (k + 1) / 2);
+    VarSrc none = make_var(nullptr, 0, 0, 0, 0, 1);
+    launch_chol_solve(d, Lp.p, 0, k, 1, dtau.p, 0, 1, nullptr, 0, none, nullptr, 0, Lfac.p);   // chol(.. + diag(tau_e))
+    VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_F, 0, 0, n);
+    launch_factor_rows(d, Lfac.p, k, n, YL.p, YL.ld, r > 0 ? ZFa.p : nullptr, r > 0 ? ZFa.ld : 0, dtau.p, zs, Fo.p, Fo.ld);
+    Fo.download(F_out, d.st);
+    check_notpd(d, "sample_factors_scores_c");
+}
+
+extern "C" int bsfg_sample_factors_scores_c(const double* Y_tilde, int n, int p, const double* Z_1, int r,
+                                            const double* Lambda, int k, const double* resid_Y_prec,
+                                            const double* F_a, const double* F_h2, const double* z,
+                                            unsigned long long seed, double* F_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(F_h2);
+    factor_scores_impl(Y_tilde, n, p, Z_1, r, Lambda, k, resid_Y_prec, F_a, F_h2, nullptr, z, seed, F_out);
+    BSFG_API_END
+}
+extern "C" int bsfg_sample_px_factors_scores_c(const double* Y_tilde, int n, int p, const double* Z_1, int r,
+                                               const double* Lambda_px, int k, const double* resid_Y_prec,
+                                               const double* F_a_px, const double* tau_e, const double* px_factor,
+                                               const double* z, unsigned long long seed, double* F_px_out) {
+    BSFG_API_BEGIN
+    (void)px_factor;   // unused in the reference too (cpp:172-176)
+    REQUIRE_PTR(tau_e);
+    factor_scores_impl(Y_tilde, n, p, Z_1, r, Lambda_px, k, resid_Y_prec, F_a_px, nullptr, tau_e, z, seed, F_px_out);
+    BSFG_API_END
+}
+
+// ---- sample_h2s_discrete_c (cpp:196-238) ------------------------------------------------------
+namespace bsfg {
+static void h2s_core(Device& d, const DMat& UtF, const DMat& F, const double* s, int H, const double* prior,
+                     const VarSrc& u, double* F_h2, double* log_ps /* k x H ld k or null */, DVec& det, DVec& ll) {
+    const int n = (int)F.rows, k = (int)F.cols;
+    h2_det_kernel<<<H, 256, 0, d.st>>>(s, n, H, det.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    {
+        const long warps = (long)k * H;
+        h2_loglik_kernel<<<ceil_div(warps * 32, 256), 256, 0, d.st>>>(UtF.p, UtF.ld, F.p, F.ld, s, n, k, H, ll.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    {
+        const int wpb = 4;
+        grid_draw_kernel<<<ceil_div(k, wpb), wpb * 32, sizeof(double) * wpb * H, d.st>>>(
+            ll.p, k, det.p, 0, 0, prior, k, H, u, F_h2, log_ps, k);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+}
+}  // namespace bsfg
+
+extern "C" int bsfg_sample_h2s_discrete_c(const double* F, int n, int k, int h2_divisions, const double* h2_priors,
+                                          const double* U, const double* s, const double* u,
+                                          unsigned long long seed, double* F_h2_out, double* log_ps_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(F); REQUIRE_PTR(h2_priors); REQUIRE_PTR(U); REQUIRE_PTR(s); REQUIRE_PTR(F_h2_out);
+    const int H = h2_divisions;
+    if (n <= 0 || k <= 0 || H <= 0) fail(BSFG_ESHAPE, "sample_h2s_discrete_c: bad sizes");
+    Device& d = default_device();
+    DMat dF(n, k), dU(n, n), UtF(n, k), dUin;
+    DVec ds(n), dprior(H), det(H), dh2(k), dlp((long)k * H), ll((long)k * H);
+    dF.upload(F, d.st); dU.upload(U, d.st); ds.upload(s, d.st); dprior.upload(h2_priors, d.st);
+    if (u) { dUin.alloc(k, 1); dUin.upload(u, d.st); }
+    d.gemm(1.0, dU, dF, 0.0, UtF);                        // t(F.t() * U), cpp:209
+    VarSrc us = make_var(u ? &dUin : nullptr, seed, SITE_U_H2, 0, 0, k);
+    h2s_core(d, UtF, dF, ds.p, H, dprior.p, us, dh2.p, log_ps_out ? dlp.p : nullptr, det, ll);
+    dh2.download(F_h2_out, d.st);
+    if (log_ps_out) dlp.download(log_ps_out, d.st);
+    d.sync();
+    BSFG_API_END
+}
+
+// ---- sample_prec_discrete_conditional_c (cpp:241-289) -----------------------------------------
+extern "C" int bsfg_sample_prec_discrete_conditional_c(const double* Y, int n, int p, int h2_divisions,
+                                                       const double* h2_priors, const double* U, const double* s,
+                                                       const double* res_prec, const double* u,
+                                                       unsigned long long seed, double* Prec_out, double* log_ps_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(Y); REQUIRE_PTR(h2_priors); REQUIRE_PTR(U); REQUIRE_PTR(s); REQUIRE_PTR(res_prec); REQUIRE_PTR(Prec_out);
+    const int H = h2_divisions;
+    if (n <= 0 || p <= 0 || H <= 0) fail(BSFG_ESHAPE, "sample_prec_discrete_conditional_c: bad sizes");
+    Device& d = default_device();
+    DMat dY(n, p), dU(n, n), UtY(n, p), dUin;
+    DVec ds(n), dprior(H), slog(H), drp(p), ll((long)p * H), det((long)p * H), dh2(p), dlp((long)p * H), dout(p);
+    dY.upload(Y, d.st); dU.upload(U, d.st); ds.upload(s, d.st); dprior.upload(h2_priors, d.st); drp.upload(res_prec, d.st);
+    if (u) { dUin.alloc(p, 1); dUin.upload(u, d.st); }
+    d.gemm(1.0, dU, dY, 0.0, UtY);                        // t(Y.t() * U), cpp:258
+    prec_logdet_s_kernel<<<H, 256, 0, d.st>>>(ds.p, n, H, slog.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    {
+        const long warps = (long)p * H;
+        prec_loglik_kernel<<<ceil_div(warps * 32, 256), 256, 0, d.st>>>(UtY.p, UtY.ld, dY.p, dY.ld, ds.p, slog.p, drp.p,
+                                                                       n, p, H, ll.p, det.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    VarSrc us = make_var(u ? &dUin : nullptr, seed, SITE_U_PREC, 0, 0, p);
+    {
+        const int wpb = 4;
+        grid_draw_kernel<<<ceil_div(p, wpb), wpb * 32, sizeof(double) * wpb * H, d.st>>>(
+            ll.p, p, det.p, p, 1, dprior.p, p, H, us, dh2.p, log_ps_out ? dlp.p : nullptr, p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    prec_from_h2_kernel<<<ceil_div(p, 256), 256, 0, d.st>>>(drp.p, dh2.p, p, dout.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    dout.download(Prec_out, d.st);
+    if (log_ps_out) dlp.download(log_ps_out, d.st);
+    d.sync();
+    BSFG_API_END
+}
+
+// ---- sample_F_a_c (cpp:293-339) ---------------------------------------------------------------
+namespace bsfg {
+// b3 = U3' Z_1' F (r x k), v = elementwise, F_a = U3 v, then branch fix-ups.  Z1 may be null (identity).
+static void fa_core(Device& d, const DMat& F, const DMat* Z1, const DMat& U3, const DMat& U3t, const double* s1,
+                    const double* s2, const double* F_h2, const VarSrc& z, DMat& T1, DMat& b3, DMat& v, DMat& Fa) {
+    const int n = (int)F.rows, k = (int)F.cols, r = (int)U3.rows;
+    const DMat* t1 = &F;
+    if (Z1) { d.gemm(1.0, *Z1, F, 0.0, T1); t1 = &T1; }    // Z_1' F
+    else if (r != n) fail(BSFG_ESHAPE, "Z_1 omitted (identity) but r != n");
+    d.gemm(1.0, U3, *t1, 0.0, b3);                          // U' (Z_1' F), cpp:311
+    {
+        dim3 grid(std::min(ceil_div(r, 256), 64), k);
+        fa_v_kernel<<<grid, 256, 0, d.st>>>(b3.p, b3.ld, r, k, F_h2, s1, s2, z, v.p, v.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    d.gemm(1.0, U3t, v, 0.0, Fa);                           // U * (mlam + z/sqrt(d)), cpp:331
+    {
+        dim3 grid(std::min(ceil_div(r, 256), 64), k);
+        fa_fixup_kernel<<<grid, 256, 0, d.st>>>(F.p, F.ld, n, r, k, F_h2, Fa.p, Fa.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+}
+}  // namespace bsfg
+
+extern "C" int bsfg_sample_F_a_c(const double* F, int n, int k, const double* Z_1, int r, const double* F_h2,
+                                 const double* U, const double* s1, const double* s2, const double* z,
+                                 unsigned long long seed, double* F_a_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(F); REQUIRE_PTR(Z_1); REQUIRE_PTR(F_h2); REQUIRE_PTR(U); REQUIRE_PTR(s1); REQUIRE_PTR(s2); REQUIRE_PTR(F_a_out);
+    if (n <= 0 || k <= 0 || r <= 0) fail(BSFG_ESHAPE, "sample_F_a_c: bad sizes");
+    for (int j = 0; j < k; j++)
+        if (1.0 / (1.0 - F_h2[j]) > 10000.0 && r != n)
+            fail(BSFG_ESHAPE, "sample_F_a_c: tau_e > 10000 copies F[,j] into F_a[,j] (cpp:326-327) but r != n");
+    Device& d = default_device();
+    DMat dF(n, k), dZ1(n, r), dU(r, r), dUt(r, r), dZ, T1(r, k), b3(r, k), v(r, k), Fa(r, k);
+    DVec ds1(r), ds2(r), dh2(k);
+    dF.upload(F, d.st); dZ1.upload(Z_1, d.st); dU.upload(U, d.st); ds1.upload(s1, d.st); ds2.upload(s2, d.st); dh2.upload(F_h2, d.st);
+    if (z) { dZ.alloc(r, k); dZ.upload(z, d.st); }
+    d.transpose(dU, dUt);
+    VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_FA, 0, 0, r);
+    fa_core(d, dF, &dZ1, dU, dUt, ds1.p, ds2.p, dh2.p, zs, T1, b3, v, Fa);
+    Fa.download(F_a_out, d.st);
+    d.sync();
+    BSFG_API_END
+}
+
+// ---- sample_delta_c (BSFG_functions.R:272-308) ------------------------------------------------
+extern "C" int bsfg_sample_delta_c(const double* delta, const double* tauh, int k, const double* Lambda_prec, int p,
+                                   double delta_1_shape, double delta_1_rate, double delta_2_shape,
+                                   double delta_2_rate, const double* Lambda2, const double* g,
+                                   unsigned long long seed, double* delta_out, int* n_draws_out,
+                                   double* shapes_out, double* rates_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(delta); REQUIRE_PTR(Lambda_prec); REQUIRE_PTR(Lambda2); REQUIRE_PTR(delta_out);
+    (void)tauh;   // R recomputes tauh = cumprod(delta) after the first draw; the input tauh only enters
+                  // the first rate, where it equals cumprod(delta) by the sweep's invariant (R:253-254).
+    if (k < 2) fail(BSFG_ESHAPE, "sample_delta: k >= 2 required (R's 2:(k-1) runs off the vector otherwise)");
+    if (p <= 0) fail(BSFG_ESHAPE, "sample_delta: p must be positive");
+    Device& d = default_device();
+    DMat LP(p, k), L2(p, k), dG;
+    DVec dd(k), colsum(k), shapes(k + 2), rates(k + 2);
+    int* d_nd = nullptr;
+    BSFG_CUDA(cudaMalloc(&d_nd, sizeof(int)));
+    LP.upload(Lambda_prec, d.st); L2.upload(Lambda2, d.st); dd.upload(delta, d.st);
+    if (g) { dG.alloc(k + 2, 1); BSFG_CUDA(cudaMemcpyAsync(dG.p, g, sizeof(double) * (size_t)(k == 2 ? 3 : k - 1), cudaMemcpyHostToDevice, d.st)); }
+    delta_colsum_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, L2.p, L2.ld, p, k, 0, colsum.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    VarSrc gs = make_var(g ? &dG : nullptr, seed, SITE_G_DELTA, 0, 0, k);
+    delta_recursion_kernel<<<1, 32, sizeof(double) * k, d.st>>>(dd.p, k, colsum.p, (double)p, delta_1_shape, delta_1_rate,
+                                                               delta_2_shape, delta_2_rate, gs, nullptr, shapes.p, rates.p, d_nd);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    dd.download(delta_out, d.st);
+    int nd = 0;
+    BSFG_CUDA(cudaMemcpyAsync(&nd, d_nd, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    cudaFree(d_nd);
+    if (n_draws_out) *n_draws_out = nd;
+    if (shapes_out) BSFG_CUDA(cudaMemcpy(shapes_out, shapes.p, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+    if (rates_out) BSFG_CUDA(cudaMemcpy(rates_out, rates.p, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+    BSFG_API_END
+}
