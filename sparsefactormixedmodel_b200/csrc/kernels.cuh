@@ -581,3 +581,234 @@ __global__ void delta_recursion_kernel(double* __restrict__ delta, int k, const 
 }
 
 }  // namespace bsfg
+
+// ====================================================================================
+// kernels used only by the stateful sweep
+// ====================================================================================
+namespace bsfg {
+
+// Lt (k x p, ld) -> Lam (p x k) and Lmsg = Lam * rp (rows)  (cpp:146); 32x32 smem tiles
+__global__ void lt_to_lam_kernel(const double* __restrict__ Lt, long ldt, int k, int p, const double* __restrict__ rp,
+                                 double* __restrict__ Lam, long ldl, double* __restrict__ Lmsg, long ldm) {
+    __shared__ double tile[32][33];
+    const int h0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int h = h0 + threadIdx.x, j = j0 + jj;
+        if (h < k && j < p) tile[jj][threadIdx.x] = Lt[(long)j * ldt + h];
+    }
+    __syncthreads();
+    for (int hh = threadIdx.y; hh < 32; hh += blockDim.y) {
+        const int j = j0 + threadIdx.x, h = h0 + hh;
+        if (h < k && j < p) {
+            const double v = tile[threadIdx.x][hh];
+            Lam[(long)h * ldl + j] = v;
+            if (Lmsg) Lmsg[(long)h * ldm + j] = v * rp[j];
+        }
+    }
+}
+
+// Plamt[h,j] = LP[j,h] * tauh[h]   (fast_BSFG_sampler.R:257), transposing
+__global__ void plam_kernel(const double* __restrict__ LP, long ldp, int p, int k, const double* __restrict__ tauh,
+                            double* __restrict__ Plamt, long ldt) {
+    __shared__ double tile[32][33];
+    const int j0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int hh = threadIdx.y; hh < 32; hh += blockDim.y) {
+        const int j = j0 + threadIdx.x, h = h0 + hh;
+        if (j < p && h < k) tile[hh][threadIdx.x] = LP[(long)h * ldp + j] * tauh[h];
+    }
+    __syncthreads();
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int h = h0 + threadIdx.x, j = j0 + jj;
+        if (j < p && h < k) Plamt[(long)j * ldt + h] = tile[threadIdx.x][jj];
+    }
+}
+
+// Lambda_prec[j,h] ~ Gamma((df+1)/2, (df + Lambda[j,h]^2 tauh[h])/2)   (fast_BSFG_sampler.R:235-236)
+// g is laid out like the reference's rgamma(p*k) stream: element j + h*p_total.
+__global__ void lambda_prec_kernel(const double* __restrict__ Lam, long ldl, int p, int k, const double* __restrict__ tauh,
+                                   double df, VarSrc gsrc, double* __restrict__ LP, long ldp,
+                                   double* __restrict__ rate_out /* p x k dense or null */) {
+    const long total = (long)p * k;
+    const double shape = (df + 1.0) / 2.0;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % p), h = (int)(idx / p);
+        const double l = Lam[(long)h * ldl + j];
+        const double rate = (df + (l * l) * tauh[h]) / 2.0;
+        double g;
+        if (gsrc.ptr) g = gsrc.ptr[(long)h * gsrc.ld + j];
+        else g = philox_gamma(gsrc.rs, (uint64_t)((long)h * gsrc.rows_total + j + gsrc.col_offset), shape);
+        LP[(long)h * ldp + j] = g / rate;
+        if (rate_out) rate_out[(long)h * p + j] = rate;
+    }
+}
+
+// per-factor reductions for sample_delta and update_k:
+//   colsum[h] = sum_j LP[j,h] Lam[j,h]^2  (BSFG_functions.R:287-292), cnt[h] = #{j: |Lam[j,h]| < eps} (R:326)
+__global__ void factor_reduce_kernel(const double* __restrict__ LP, long ldp, const double* __restrict__ Lam, long ldl,
+                                     int p, int k, double eps, double* __restrict__ colsum, double* __restrict__ cnt) {
+    __shared__ double red[32];
+    const int h = blockIdx.x;
+    double acc = 0.0, c = 0.0;
+    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+        const double l = Lam[(long)h * ldl + j];
+        acc += LP[(long)h * ldp + j] * (l * l);
+        c += (fabs(l) < eps) ? 1.0 : 0.0;
+    }
+    acc = block_sum(acc, red);
+    c = block_sum(c, red);
+    if (threadIdx.x == 0) { colsum[h] = acc; cnt[h] = c; }
+}
+
+// per-trait reductions + the two Gamma precision draws (fast_BSFG_sampler.R:239-245), one warp per trait.
+//   SS_j = yy - 2 th.DtY - 2 l.FtY + q2 + 2 th.acc2 + l.G2          (expanded ||y - Design_U th - F l||^2)
+//   q2   = sum s2 th^2 (diag mode)  or  th.(M2 th) (direct mode);  q1 likewise with s1 / M1
+//   resid_Y_prec ~ Gamma(a_r + n/2, b_r + SS/2);  E_a_prec ~ Gamma(a_e + r/2, b_e + (q1 - bX sum B^2)/2)
+struct TraitReduceArgs {
+    const double* theta; long ldth;
+    const double* DtY; long lddy;
+    const double* acc2; long ldacc;
+    const double* M1th; const double* M2th; long ldm;     // null in diag mode
+    const double* s1; const double* s2;
+    const double* Lt; long ldlt;
+    const double* FtY; long ldfy;
+    const double* G2; long ldg2;
+    const double* Bfix; long ldb;
+    const double* yy;
+    int br, k, b, p;
+    double n_half, r_half;
+    double rr_shape, rr_rate, re_shape, re_rate, bX;
+    double* rp; double* ep;
+    double* rr_rate_out; double* re_rate_out;     // optional aux
+};
+__global__ void trait_reduce_kernel(TraitReduceArgs a, VarSrc g_resid, VarSrc g_ea) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= a.p) return;
+    const double* th = a.theta + (long)j * a.ldth;
+    const double* dy = a.DtY + (long)j * a.lddy;
+    const double* ac = a.acc2 + (long)j * a.ldacc;
+    double a1 = 0, a2 = 0, q1 = 0, q2 = 0;
+    if (a.M1th) {
+        const double* m1 = a.M1th + (long)j * a.ldm;
+        const double* m2 = a.M2th + (long)j * a.ldm;
+        for (int i = lane; i < a.br; i += 32) {
+            const double t = th[i];
+            a1 += t * dy[i]; a2 += t * ac[i]; q1 += t * m1[i]; q2 += t * m2[i];
+        }
+    } else {
+        for (int i = lane; i < a.br; i += 32) {
+            const double t = th[i];
+            a1 += t * dy[i]; a2 += t * ac[i]; q1 += a.s1[i] * (t * t); q2 += a.s2[i] * (t * t);
+        }
+    }
+    double l1 = 0, l2 = 0;
+    const double* lt = a.Lt + (long)j * a.ldlt;
+    const double* fy = a.FtY + (long)j * a.ldfy;
+    const double* g2 = a.G2 + (long)j * a.ldg2;
+    for (int h = lane; h < a.k; h += 32) { const double l = lt[h]; l1 += l * fy[h]; l2 += l * g2[h]; }
+    double bb = 0;
+    for (int c = lane; c < a.b; c += 32) { const double v = a.Bfix[(long)j * a.ldb + c]; bb += v * v; }
+    a1 = warp_sum(a1); a2 = warp_sum(a2); q1 = warp_sum(q1); q2 = warp_sum(q2);
+    l1 = warp_sum(l1); l2 = warp_sum(l2); bb = warp_sum(bb);
+    if (lane == 0) {
+        const double ss = a.yy[j] - 2.0 * a1 - 2.0 * l1 + q2 + 2.0 * a2 + l2;
+        const double rate_r = a.rr_rate + 0.5 * ss;
+        const double rate_e = a.re_rate + 0.5 * (q1 - a.bX * bb);
+        a.rp[j] = var_gamma(g_resid, j, 0, a.rr_shape + a.n_half) / rate_r;
+        a.ep[j] = var_gamma(g_ea, j, 0, a.re_shape + a.r_half) / rate_e;
+        if (a.rr_rate_out) a.rr_rate_out[j] = rate_r;
+        if (a.re_rate_out) a.re_rate_out[j] = rate_e;
+    }
+}
+
+// yy[j] = sum_i Y[i,j]^2, one warp per column
+__global__ void colsumsq_kernel(const double* __restrict__ Y, long ld, int n, int p, double* __restrict__ out) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= p) return;
+    double acc = 0;
+    for (int i = lane; i < n; i += 32) { const double v = Y[(long)j * ld + i]; acc += v * v; }
+    acc = warp_sum(acc);
+    if (lane == 0) out[j] = acc;
+}
+
+// max |M[i,j] - (i==j ? d[i] : 0)| over a square matrix -> out[0] (atomicMax on the bit pattern; values >= 0)
+__global__ void diag_residual_kernel(const double* __restrict__ M, long ld, int m, const double* __restrict__ d,
+                                     unsigned long long* __restrict__ out) {
+    double mx = 0.0;
+    const long total = (long)m * m;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % m), j = (int)(idx / m);
+        double v = M[(long)j * ld + i];
+        if (i == j) v -= d[i];
+        mx = fmax(mx, fabs(v));
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+
+// Pfull = blockdiag(bX * I_b, Ainv)  (fast_BSFG_sampler_init.R:289)
+__global__ void build_prior_prec_kernel(const double* __restrict__ Ainv, long lda, int r, int b, double bX,
+                                        double* __restrict__ P, long ldp) {
+    const int br = b + r;
+    const long total = (long)br * br;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % br), j = (int)(idx / br);
+        double v = 0.0;
+        if (i < b || j < b) v = (i == j) ? bX : 0.0;
+        else v = Ainv[(long)(j - b) * lda + (i - b)];
+        P[(long)j * ldp + i] = v;
+    }
+}
+
+// ---- update_k (BSFG_functions.R:311-372) ----------------------------------------------------
+// add arm, trait-indexed part: new column h = k (0-based) of Lambda_prec, Plam, Lambda
+__global__ void addk_traits_kernel(int p, int h, double df, double tauh_new, VarSrc g_lp, VarSrc z_lam,
+                                   double* __restrict__ LP, long ldp, double* __restrict__ Lam, long ldl,
+                                   double* __restrict__ Lt, long ldlt, double* __restrict__ Plamt, long ldpt) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
+        const double lp = var_gamma(g_lp, j, 0, df / 2.0) / (df / 2.0);     // R:334
+        const double plam = lp * tauh_new;                                 // R:337
+        const double l = var_normal(z_lam, j, 0) * sqrt(1.0 / plam);        // R:338
+        LP[(long)h * ldp + j] = lp;
+        Lam[(long)h * ldl + j] = l;
+        Lt[(long)j * ldlt + h] = l;
+        Plamt[(long)j * ldpt + h] = plam;
+    }
+}
+// add arm, individual-indexed part: F_a[,k] = z sqrt(h2); F[,k] = Z_1 F_a[,k] + z sqrt(1-h2)   (R:339-341)
+__global__ void addk_fa_kernel(int r, int h, double h2, VarSrc z_fa, double* __restrict__ Fa, long lda) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x)
+        Fa[(long)h * lda + i] = var_normal(z_fa, i, 0) * sqrt(h2);
+}
+__global__ void addk_f_kernel(int n, int r, int h, double h2, const double* __restrict__ Z1, long ldz,
+                              const double* __restrict__ Fa, long lda, VarSrc z_f, double* __restrict__ F, long ldf) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double m;
+        if (Z1) {
+            m = 0.0;
+            for (int c = 0; c < r; c++) m += Z1[(long)c * ldz + i] * Fa[(long)h * lda + c];
+        } else {
+            m = Fa[(long)h * lda + i];
+        }
+        F[(long)h * ldf + i] = m + var_normal(z_f, i, 0) * sqrt(1.0 - h2);
+    }
+}
+// drop arm: keep columns map[0..knew) (ascending) of a column-major matrix, in place
+__global__ void compact_cols_kernel(double* __restrict__ A, long ld, int rows, int knew, const int* __restrict__ map) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x)
+        for (int h = 0; h < knew; h++) {
+            const int src = map[h];
+            if (src != h) A[(long)h * ld + i] = A[(long)src * ld + i];
+        }
+}
+// same for the rows of a (k x p) column-major matrix
+__global__ void compact_rows_kernel(double* __restrict__ A, long ld, int p, int knew, const int* __restrict__ map) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x)
+        for (int h = 0; h < knew; h++) {
+            const int src = map[h];
+            if (src != h) A[(long)j * ld + h] = A[(long)j * ld + src];
+        }
+}
+
+}  // namespace bsfg

@@ -1,16 +1,799 @@
-// placeholder until the stateful sweep lands (next commit)
+// Stateful sweep: the loop body of fast_BSFG_sampler (R_BSFG/fast_BSFG_sampler.R:176-270) with the
+// state resident in HBM and the data pre-rotated once (U'Y, Design_U'Y), so none of the reference's
+// per-iteration n^2 p products remain.  Included by bsfg.cu.
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace bsfg {
+
+// ---- NCCL, resolved at run time so a single-GPU process never needs the library ---------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    void load() {
+        if (handle) return;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) fail(BSFG_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define BSFG_NCCL_SYM(field, name)                                             \
+        *(void**)(&field) = dlsym(handle, name);                               \
+        if (!field) fail(BSFG_ENCCL, "symbol %s missing from libnccl", name)
+        BSFG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+        BSFG_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+        BSFG_NCCL_SYM(AllReduce, "ncclAllReduce");
+        BSFG_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        BSFG_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef BSFG_NCCL_SYM
+    }
+};
+static NcclApi g_nccl;
+#define BSFG_NCCL(expr)                                                                         \
+    do {                                                                                        \
+        ncclResult_t r__ = (expr);                                                              \
+        if (r__ != ncclSuccess) fail(BSFG_ENCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+enum Phase { PH_LAMBDA_PREP = 0, PH_LAMBDA_GRAM, PH_LAMBDA_CHOL, PH_MEANS, PH_H2, PH_FA, PH_F_GEMM, PH_F_COMM,
+             PH_F_SOLVE, PH_PREC, PH_DELTA, PH_UPDATE_K };
+static_assert(PH_UPDATE_K + 1 == BSFG_N_PHASES, "phase count");
+
+}  // namespace bsfg
+
+struct bsfg_ctx {
+    bsfg::Device dev;
+    bsfg_config cfg{};
+    bsfg_priors pri{};
+    std::vector<double> h2_prior_host;
+    bool have_priors = false, have_consts = false, have_state = false;
+    int n = 0, pl = 0, p_total = 0, p_off = 0, k = 0, kmax = 0, r = 0, b = 0, br = 0, H = 0;
+    bool z1_identity = false;
+    int mode = 0;                 // 1 direct, 2 diag
+    double resid_s1 = -1, resid_s2 = -1;
+    long iter = 0;                // current_state$nrun
+    // constants
+    bsfg::DMat UtY, UtYt, DtY, U1, U1t, UtX, U2, U2t, DU, DUt, U3, U3t, Z1, Z1t, M1, M2;
+    bsfg::DVec yy, s, s1_2, s2_2, s1_3, s2_3, h2_prior;
+    // state (factor-indexed storage has kmax columns / rows)
+    bsfg::DMat Lt, Lam, Lmsg, LP, Plamt, F, Fa, Bfix, theta, thetat, Ea_in;
+    bsfg::DVec F_h2, delta, tauh, rp, ep;
+    bool theta_valid = false, derived_valid = false;
+    // derived from F
+    bsfg::DMat UtF, FtD;
+    // scratch
+    bsfg::LambdaScratch lsc;
+    bsfg::DMat tmp_brp, acc2, M1th, M2th, red1, YL, ZFa, T1, b3, vfa, FtF, FtY, G2;
+    bsfg::DVec tau_e, Lp, Lfac, det, ll, red2, colsum_cnt, delta_shapes, delta_rates;
+    int* d_ndraws = nullptr;
+    int* d_map = nullptr;
+    // injected-variate staging
+    bsfg::DMat v_zL, v_zM, v_uh2, v_zFa, v_zF, v_gLP, v_gR, v_gE, v_gD, v_kadd;
+    // aux
+    bsfg::DMat aux_lp_rate;
+    bsfg::DVec aux_rr, aux_re, aux_logps;
+    bool aux_on = false;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    // timing
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_phase;     // (N_PHASES + 1) per iteration slot, reused
+    double last_total_ms = 0;
+    long long last_launches = 0;
+    double phase_ms[BSFG_N_PHASES] = {0};
+    bool phase_timing = false;
+};
+
+namespace bsfg {
+
+static void ctx_alloc_factor_storage(bsfg_ctx* c) {
+    const int n = c->n, pl = c->pl, km = c->kmax, r = c->r, br = c->br;
+    c->Lt.alloc(km, pl); c->Lam.alloc(pl, km); c->Lmsg.alloc(pl, km); c->LP.alloc(pl, km); c->Plamt.alloc(km, pl);
+    c->F.alloc(n, km); c->Fa.alloc(r, km); c->UtF.alloc(n, km); c->FtD.alloc(km, br);
+    c->F_h2.alloc(km); c->delta.alloc(km); c->tauh.alloc(km); c->tau_e.alloc(km);
+    c->YL.alloc(n, km); c->ZFa.alloc(n, km); c->T1.alloc(r, km); c->b3.alloc(r, km); c->vfa.alloc(r, km);
+    c->FtF.alloc(km, km); c->FtY.alloc(km, pl); c->G2.alloc(km, pl);
+    c->Lp.alloc((long)km * (km + 1) / 2); c->Lfac.alloc((long)km * (km + 1) / 2);
+    c->det.alloc(c->H); c->ll.alloc((long)km * c->H);
+    // red1 = [LtL (km x km) | P1 (n x km) | P2 (br x km)] stacked by rows: one allreduce buffer
+    c->red1.alloc(round_up(km, 2) + round_up(n, 2) + round_up(br, 2), km);
+    c->colsum_cnt.alloc(2 * (long)km);
+    c->delta_shapes.alloc(km + 2); c->delta_rates.alloc(km + 2);
+    c->aux_logps.alloc((long)km * c->H);
+}
+
+// view helpers: a DMat header over existing storage restricted to the first `cols` columns / `rows` rows
+static DMat view(const DMat& m, long rows, long cols) {
+    DMat v;
+    v.p = m.p; v.rows = rows; v.cols = cols; v.ld = m.ld; v.owner = false;
+    return v;
+}
+static DMat view_at(double* p, long rows, long cols, long ld) {
+    DMat v;
+    v.p = p; v.rows = rows; v.cols = cols; v.ld = ld; v.owner = false;
+    return v;
+}
+
+static void refresh_derived(bsfg_ctx* c) {
+    // UtF = U'F (t(FtU), cpp:107) and FtD = F' Design_U: depend only on F
+    Device& d = c->dev;
+    DMat F = view(c->F, c->n, c->k), UtF = view(c->UtF, c->n, c->k), FtD = view(c->FtD, c->k, c->br);
+    d.gemm(1.0, c->U1, F, 0.0, UtF);
+    d.gemm(1.0, F, c->DU, 0.0, FtD);
+    c->derived_valid = true;
+}
+
+static void allreduce(bsfg_ctx* c, double* buf, size_t count) {
+    if (c->cfg.world <= 1) return;
+    if (!c->comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
+    BSFG_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->dev.st));
+}
+
+struct IterVariates {   // device-side sources for one iteration
+    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD;
+};
+
+static void phase_mark(bsfg_ctx* c, int idx) {
+    if (c->phase_timing) BSFG_CUDA(cudaEventRecord(c->ev_phase[idx], c->dev.st));
+}
+
+// ---- one Gibbs iteration (everything but update_k), steps numbered as SURVEY.md section 3.1 ----
+static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, k = c->k, r = c->r, b = c->b, br = c->br, H = c->H;
+    if (!c->derived_valid) refresh_derived(c);
+    DMat F = view(c->F, n, k), Fa = view(c->Fa, r, k), UtF = view(c->UtF, n, k), FtD = view(c->FtD, k, br);
+    DMat Lt = view(c->Lt, k, pl), Lam = view(c->Lam, pl, k), Lmsg = view(c->Lmsg, pl, k), LP = view(c->LP, pl, k);
+    DMat Plamt = view(c->Plamt, k, pl);
+
+    // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
+    phase_mark(c, 0);
+    lambda_core(d, c->lsc, UtF, c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
+                Plamt.p, Plamt.ld, 1, v.zL, Lt);
+    phase_mark(c, 3);
+    {
+        dim3 grid(ceil_div(k, 32), ceil_div(pl, 32)), block(32, 8);
+        lt_to_lam_kernel<<<grid, block, 0, d.st>>>(Lt.p, Lt.ld, k, pl, c->rp.p, Lam.p, Lam.ld, Lmsg.p, Lmsg.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    // 2. [B; E_a] | F, Lambda in rotated coordinates theta      R:203-207 -> cpp:43-82
+    //    Design_U'(Y - F Lambda') = DtY - (Design_U'F) Lambda'
+    dgemm_tn(d.st, d.sms, br, pl, k, -1.0, FtD.p, FtD.ld, Lt.p, Lt.ld, 1.0, c->DtY.p, c->DtY.ld, c->tmp_brp.p,
+             c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
+    {
+        dim3 grid(std::min(ceil_div(br, 256), 64), pl);
+        means_theta_kernel<<<grid, 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
+                                                   c->ep.p, v.zM, c->theta.p, c->theta.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    d.transpose(c->theta, c->thetat);
+    if (b > 0) {
+        DMat U2Bt = view(c->U2t, br, b);                   // first b columns of U2' = rows 0..b-1 of U2
+        d.gemm(1.0, U2Bt, c->theta, 0.0, c->Bfix);         // B = location_sample[1:b,], R:206
+    }
+    c->theta_valid = true;
+    phase_mark(c, 4);
+
+    // 4. F_h2 | F (marginal over F_a)                         R:221 -> cpp:196-238
+    h2s_core(d, UtF, F, c->s.p, H, c->h2_prior.p, v.uh2, c->F_h2.p, c->aux_on ? c->aux_logps.p : nullptr, c->det, c->ll);
+    phase_mark(c, 5);
+    // 5. F_a | F, F_h2                                        R:226 -> cpp:293-339
+    {
+        DMat T1 = view(c->T1, r, k), b3 = view(c->b3, r, k), vfa = view(c->vfa, r, k);
+        fa_core(d, F, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa);
+    }
+    phase_mark(c, 6);
+
+    // 6. F | Lambda, B, E_a, F_a, F_h2                        R:230-232 -> cpp:138-163
+    //    Y_tilde Lmsg = U (U'Y Lmsg) - Design_U (theta Lmsg);  the three partial products are the only
+    //    cross-GPU traffic of the sweep (one allreduce of [Lambda'Lmsg | U'Y Lmsg | theta Lmsg]).
+    const long o1 = round_up(c->kmax, 2), o2 = o1 + round_up(n, 2);
+    DMat LtL = view_at(c->red1.p, k, k, c->red1.ld);
+    DMat P1 = view_at(c->red1.p + o1, n, k, c->red1.ld);
+    DMat P2 = view_at(c->red1.p + o2, br, k, c->red1.ld);
+    d.gemm(1.0, Lam, Lmsg, 0.0, LtL);
+    d.gemm(1.0, c->UtYt, Lmsg, 0.0, P1);
+    d.gemm(1.0, c->thetat, Lmsg, 0.0, P2);
+    phase_mark(c, 7);
+    allreduce(c, c->red1.p, (size_t)c->red1.ld * (size_t)k);
+    phase_mark(c, 8);
+    {
+        DMat YL = view(c->YL, n, k);
+        d.gemm(1.0, c->U1t, P1, 0.0, YL);
+        d.gemm(-1.0, c->DUt, P2, 1.0, YL);
+        const double* zfa_p = nullptr; long zfa_ld = 0;
+        if (c->z1_identity) { zfa_p = Fa.p; zfa_ld = Fa.ld; }
+        else {
+            DMat ZFa = view(c->ZFa, n, k);
+            d.gemm(1.0, c->Z1t, Fa, 0.0, ZFa);
+            zfa_p = ZFa.p; zfa_ld = ZFa.ld;
+        }
+        tau_e_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, k, c->tau_e.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        pack_lower_kernel<<<ceil_div((long)k * (k + 1) / 2, 256), 256, 0, d.st>>>(LtL.p, LtL.ld, k, c->Lp.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        VarSrc none = make_var(nullptr, 0, 0, 0, 0, 1);
+        launch_chol_solve(d, c->Lp.p, 0, k, 1, c->tau_e.p, 0, 1, nullptr, 0, none, nullptr, 0, c->Lfac.p);
+        launch_factor_rows(d, c->Lfac.p, k, n, YL.p, YL.ld, zfa_p, zfa_ld, c->tau_e.p, v.zF, F.p, F.ld);
+    }
+    phase_mark(c, 9);
+
+    // 7. Lambda_prec | Lambda, tauh                           R:235-236
+    {
+        const long total = (long)pl * k;
+        int blocks = (int)std::min<long>((total + 255) / 256, (long)d.sms * 8);
+        lambda_prec_kernel<<<blocks, 256, 0, d.st>>>(Lam.p, Lam.ld, pl, k, c->tauh.p, c->pri.Lambda_df, v.gLP, LP.p, LP.ld,
+                                                     c->aux_on ? c->aux_lp_rate.p : nullptr);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    // 8-9. resid_Y_prec, E_a_prec from sufficient statistics of the NEW F   R:239-245
+    refresh_derived(c);
+    {
+        DMat FtF = view(c->FtF, k, k), FtY = view(c->FtY, k, pl), G2 = view(c->G2, k, pl);
+        d.gemm(1.0, F, F, 0.0, FtF);
+        d.gemm(1.0, UtF, c->UtY, 0.0, FtY);                // F'Y = (U'F)'(U'Y)
+        d.gemm(1.0, FtF, Lt, 0.0, G2);                     // F'F lambda_j
+        d.gemm(1.0, FtD, Lt, 0.0, c->acc2);                // Design_U' F lambda_j
+        if (c->mode == 1) {
+            d.gemm(1.0, c->M1, c->theta, 0.0, c->M1th);
+            d.gemm(1.0, c->M2, c->theta, 0.0, c->M2th);
+        }
+        TraitReduceArgs a;
+        a.theta = c->theta.p; a.ldth = c->theta.ld; a.DtY = c->DtY.p; a.lddy = c->DtY.ld;
+        a.acc2 = c->acc2.p; a.ldacc = c->acc2.ld;
+        a.M1th = c->mode == 1 ? c->M1th.p : nullptr; a.M2th = c->mode == 1 ? c->M2th.p : nullptr; a.ldm = c->M1th.ld;
+        a.s1 = c->s1_2.p; a.s2 = c->s2_2.p;
+        a.Lt = Lt.p; a.ldlt = Lt.ld; a.FtY = FtY.p; a.ldfy = FtY.ld; a.G2 = G2.p; a.ldg2 = G2.ld;
+        a.Bfix = c->Bfix.p; a.ldb = c->Bfix.ld; a.yy = c->yy.p;
+        a.br = br; a.k = k; a.b = b; a.p = pl;
+        a.n_half = n / 2.0; a.r_half = r / 2.0;
+        a.rr_shape = c->pri.resid_Y_prec_shape; a.rr_rate = c->pri.resid_Y_prec_rate;
+        a.re_shape = c->pri.E_a_prec_shape; a.re_rate = c->pri.E_a_prec_rate; a.bX = c->pri.b_X_prec;
+        a.rp = c->rp.p; a.ep = c->ep.p;
+        a.rr_rate_out = c->aux_on ? c->aux_rr.p : nullptr; a.re_rate_out = c->aux_on ? c->aux_re.p : nullptr;
+        trait_reduce_kernel<<<ceil_div((long)pl * 32, 256), 256, 0, d.st>>>(a, v.gR, v.gE);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    phase_mark(c, 10);
+
+    // 11-12. delta, tauh, Plam                                R:253-257 -> BSFG_functions.R:272-308
+    factor_reduce_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, Lam.p, Lam.ld, pl, k, c->pri.epsilon, c->colsum_cnt.p,
+                                              c->colsum_cnt.p + c->kmax);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    allreduce(c, c->colsum_cnt.p, (size_t)2 * c->kmax);
+    delta_recursion_kernel<<<1, 32, sizeof(double) * k, d.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
+                                                               c->pri.delta_1_shape, c->pri.delta_1_rate,
+                                                               c->pri.delta_2_shape, c->pri.delta_2_rate, v.gD, c->tauh.p,
+                                                               c->delta_shapes.p, c->delta_rates.p, c->d_ndraws);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    {
+        dim3 grid(ceil_div(pl, 32), ceil_div(k, 32)), block(32, 8);
+        plam_kernel<<<grid, block, 0, d.st>>>(LP.p, LP.ld, pl, k, c->tauh.p, Plamt.p, Plamt.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    phase_mark(c, 11);
+}
+
+// ---- update_k (BSFG_functions.R:311-372); host decides, device applies -----------------------
+struct KAddVariates { VarSrc g_lp, z_lam, z_fa, z_f; double g_delta, u_h2; bool have_scalars; };
+
+static void update_k_step(bsfg_ctx* c, long i, double uu, const KAddVariates* inj) {
+    Device& d = c->dev;
+    const double prob = 1.0 / exp(c->pri.b0 + c->pri.b1 * (double)i);       // R:324
+    if (!(uu < prob && i > 200)) return;                                    // R:331
+    const int k = c->k, pl = c->pl, n = c->n, r = c->r;
+    std::vector<double> cnt(k);
+    BSFG_CUDA(cudaMemcpyAsync(cnt.data(), c->colsum_cnt.p + c->kmax, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    std::vector<int> vec(k);
+    int num = 0;
+    bool all_below = true;
+    for (int h = 0; h < k; h++) {
+        const double lind = cnt[h] / (double)c->p_total;                    // colMeans(abs(Lambda) < epsilon), R:326
+        vec[h] = lind >= c->pri.prop;
+        num += vec[h];
+        if (!(lind < 0.995)) all_below = false;
+    }
+    if (i > 20 && num == 0 && all_below && k < 2 * c->p_total) {            // add a column, R:332-341
+        if (k + 1 > c->kmax) fail(BSFG_ESHAPE, "update_k wants factor %d but k_max = %d", k + 1, c->kmax);
+        const int h = k;
+        RngStream rs{c->cfg.seed, SITE_K_ADD, (uint32_t)i};
+        double g_delta, u_h2;
+        if (inj && inj->have_scalars) { g_delta = inj->g_delta; u_h2 = inj->u_h2; }
+        else {
+            g_delta = philox_gamma(rs, 0, c->pri.delta_2_shape);
+            u_h2 = philox_uniform(rs, 1);
+        }
+        std::vector<double> delta(k + 1);
+        BSFG_CUDA(cudaMemcpyAsync(delta.data(), c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+        d.sync();
+        delta[k] = g_delta / c->pri.delta_2_rate;                            // R:335
+        std::vector<double> tauh(k + 1);
+        double cp = 1.0;
+        for (int q = 0; q <= k; q++) { cp *= delta[q]; tauh[q] = cp; }
+        BSFG_CUDA(cudaMemcpyAsync(c->delta.p, delta.data(), sizeof(double) * (k + 1), cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, tauh.data(), sizeof(double) * (k + 1), cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->F_h2.p + k, &u_h2, sizeof(double), cudaMemcpyHostToDevice, d.st));
+        d.sync();   // host vectors go out of scope
+        VarSrc g_lp, z_lam, z_fa, z_f;
+        if (inj) { g_lp = inj->g_lp; z_lam = inj->z_lam; z_fa = inj->z_fa; z_f = inj->z_f; }
+        else {
+            // element ranges of the SITE_K_ADD stream: [2, 2+p) g_lp, [2+p, 2+2p) z_lambda, then z_Fa (r), z_F (n)
+            g_lp = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + c->p_off, 1);
+            z_lam = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + (long)c->p_total + c->p_off, 1);
+            z_fa = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * c->p_total, 1);
+            z_f = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * c->p_total + r, 1);
+        }
+        addk_traits_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(
+            pl, h, c->pri.Lambda_df, tauh[k], g_lp, z_lam, c->LP.p, c->LP.ld, c->Lam.p, c->Lam.ld, c->Lt.p, c->Lt.ld,
+            c->Plamt.p, c->Plamt.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        addk_fa_kernel<<<std::min(ceil_div(r, 256), d.sms * 4), 256, 0, d.st>>>(r, h, u_h2, z_fa, c->Fa.p, c->Fa.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        addk_f_kernel<<<std::min(ceil_div(n, 256), d.sms * 4), 256, 0, d.st>>>(
+            n, r, h, u_h2, c->z1_identity ? nullptr : c->Z1.p, c->Z1.ld, c->Fa.p, c->Fa.ld, z_f, c->F.p, c->F.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        c->k = k + 1;
+        c->derived_valid = false;
+    } else if (num > 0) {                                                    // drop redundant columns, R:342-359
+        std::vector<int> nonred;
+        for (int h = 0; h < k; h++) if (!vec[h]) nonred.push_back(h);
+        const int knew = (int)nonred.size();
+        if (knew < 2) fail(BSFG_ESHAPE, "update_k would leave %d factors; sample_delta needs >= 2", knew);
+        std::vector<double> delta(k);
+        BSFG_CUDA(cudaMemcpyAsync(delta.data(), c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+        d.sync();
+        for (int red = 0; red < k; red++) {                                  // R:347-352
+            if (!vec[red]) continue;
+            if (red == k - 1) continue;
+            delta[red + 1] = delta[red + 1] * delta[red];
+        }
+        std::vector<double> dnew(knew), tnew(knew);
+        double cp = 1.0;
+        for (int q = 0; q < knew; q++) { dnew[q] = delta[nonred[q]]; cp *= dnew[q]; tnew[q] = cp; }
+        BSFG_CUDA(cudaMemcpyAsync(c->delta.p, dnew.data(), sizeof(double) * knew, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, tnew.data(), sizeof(double) * knew, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->d_map, nonred.data(), sizeof(int) * knew, cudaMemcpyHostToDevice, d.st));
+        d.sync();
+        auto cc = [&](DMat& A, int rows) {
+            compact_cols_kernel<<<std::min(ceil_div(std::max(rows, 1), 256), d.sms * 4), 256, 0, d.st>>>(A.p, A.ld, rows, knew, c->d_map);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        };
+        cc(c->Lam, pl); cc(c->LP, pl); cc(c->F, n); cc(c->Fa, r);
+        {
+            DMat h2v = view_at(c->F_h2.p, 1, k, 1);
+            compact_cols_kernel<<<1, 32, 0, d.st>>>(h2v.p, 1, 1, knew, c->d_map);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+        compact_rows_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(c->Lt.p, c->Lt.ld, pl, knew, c->d_map);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        c->k = knew;
+        {
+            dim3 grid(ceil_div(pl, 32), ceil_div(knew, 32)), block(32, 8);
+            plam_kernel<<<grid, block, 0, d.st>>>(c->LP.p, c->LP.ld, pl, knew, c->tauh.p, c->Plamt.p, c->Plamt.ld);   // R:356
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+        c->derived_valid = false;
+    }
+}
+
+static void require_ready(bsfg_ctx* c) {
+    if (!c) fail(BSFG_EARG, "ctx is NULL");
+    if (!c->have_priors) fail(BSFG_ESTATE, "bsfg_set_priors has not been called");
+    if (!c->have_consts) fail(BSFG_ESTATE, "bsfg_upload_constants has not been called");
+    if (!c->have_state) fail(BSFG_ESTATE, "bsfg_set_state has not been called");
+    if (c->k < 2) fail(BSFG_ESHAPE, "k >= 2 required");
+}
+
+static void finish_timing(bsfg_ctx* c, long long launches_before, int n_iter_timed_phases) {
+    Device& d = c->dev;
+    BSFG_CUDA(cudaEventRecord(c->ev_end, d.st));
+    BSFG_CUDA(cudaEventSynchronize(c->ev_end));
+    float ms = 0;
+    BSFG_CUDA(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+    c->last_total_ms = ms;
+    c->last_launches = g_launch_counter - launches_before;
+    if (c->phase_timing && n_iter_timed_phases > 0) {
+        // phase boundaries recorded: 0 start, 3 after Lambda, 4 means, 5 h2, 6 F_a, 7 F gemms, 8 comm, 9 F solve,
+        // 10 precisions, 11 delta/Plam.  (Lambda's own sub-phases are reported by bench.py's per-kernel timing.)
+        const int marks[] = {0, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+        const int phase_of[] = {PH_LAMBDA_GRAM, PH_MEANS, PH_H2, PH_FA, PH_F_GEMM, PH_F_COMM, PH_F_SOLVE, PH_PREC, PH_DELTA};
+        for (int q = 0; q + 1 < 10; q++) {
+            float t = 0;
+            BSFG_CUDA(cudaEventElapsedTime(&t, c->ev_phase[marks[q]], c->ev_phase[marks[q + 1]]));
+            c->phase_ms[phase_of[q]] = t;
+        }
+    }
+    check_notpd(d, "bsfg_sweep");
+}
+
+}  // namespace bsfg
+
 extern "C" long long bsfg_launch_count(void) { return bsfg::g_launch_counter; }
-#define BSFG_STUB(name, ...) extern "C" int name(__VA_ARGS__) { bsfg::set_last_error(#name ": not built yet"); return BSFG_ESTATE; }
-BSFG_STUB(bsfg_create, const bsfg_config*, bsfg_ctx**)
-BSFG_STUB(bsfg_destroy, bsfg_ctx*)
-BSFG_STUB(bsfg_set_priors, bsfg_ctx*, const bsfg_priors*)
-BSFG_STUB(bsfg_upload_constants, bsfg_ctx*, const bsfg_constants*)
-BSFG_STUB(bsfg_set_state, bsfg_ctx*, const bsfg_state*)
-BSFG_STUB(bsfg_get_state, bsfg_ctx*, bsfg_state*)
-BSFG_STUB(bsfg_get_aux, bsfg_ctx*, bsfg_aux*)
-BSFG_STUB(bsfg_sweep, bsfg_ctx*, int)
-BSFG_STUB(bsfg_sweep_injected, bsfg_ctx*, const bsfg_variates*)
-BSFG_STUB(bsfg_get_mode, bsfg_ctx*, int*, double*, double*)
-BSFG_STUB(bsfg_get_timing, bsfg_ctx*, double*, long long*, double*)
-BSFG_STUB(bsfg_nccl_unique_id, char*)
-BSFG_STUB(bsfg_comm_init, bsfg_ctx*, const char*)
+
+extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(cfg); REQUIRE_PTR(out);
+    if (cfg->n <= 0 || cfg->p_local <= 0 || cfg->p_total < cfg->p_local || cfg->k < 2 || cfg->k_max < cfg->k || cfg->r <= 0 ||
+        cfg->b < 0 || cfg->h2_divisions <= 0 || cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world ||
+        cfg->p_offset < 0 || cfg->p_offset + cfg->p_local > cfg->p_total)
+        fail(BSFG_ESHAPE, "bsfg_create: inconsistent sizes");
+    if (cfg->z1_is_identity && cfg->r != cfg->n) fail(BSFG_ESHAPE, "z1_is_identity requires r == n");
+    kt_for(cfg->k_max);
+    bsfg_ctx* c = new bsfg_ctx();
+    try {
+        c->dev.init();
+        c->cfg = *cfg;
+        c->n = cfg->n; c->pl = cfg->p_local; c->p_total = cfg->p_total; c->p_off = cfg->p_offset;
+        c->k = cfg->k; c->kmax = cfg->k_max; c->r = cfg->r; c->b = cfg->b; c->br = cfg->b + cfg->r; c->H = cfg->h2_divisions;
+        c->z1_identity = cfg->z1_is_identity != 0;
+        ctx_alloc_factor_storage(c);
+        const int n = c->n, pl = c->pl, br = c->br, b = c->b;
+        c->Bfix.alloc(std::max(b, 1), pl); c->theta.alloc(br, pl); c->thetat.alloc(pl, br);
+        c->tmp_brp.alloc(br, pl); c->acc2.alloc(br, pl);
+        c->rp.alloc(pl); c->ep.alloc(pl); c->yy.alloc(pl);
+        c->aux_lp_rate.alloc(pl, c->kmax); c->aux_rr.alloc(pl); c->aux_re.alloc(pl);
+        BSFG_CUDA(cudaMalloc(&c->d_ndraws, sizeof(int)));
+        BSFG_CUDA(cudaMalloc(&c->d_map, sizeof(int) * c->kmax));
+        BSFG_CUDA(cudaEventCreate(&c->ev_begin));
+        BSFG_CUDA(cudaEventCreate(&c->ev_end));
+        c->ev_phase.resize(BSFG_N_PHASES + 1);
+        for (auto& e : c->ev_phase) BSFG_CUDA(cudaEventCreate(&e));
+        (void)n;
+    } catch (...) {
+        delete c;
+        throw;
+    }
+    *out = c;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_destroy(bsfg_ctx* c) {
+    BSFG_API_BEGIN
+    if (!c) return BSFG_OK;
+    cudaStreamSynchronize(c->dev.st);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->d_ndraws) cudaFree(c->d_ndraws);
+    if (c->d_map) cudaFree(c->d_map);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    for (auto& e : c->ev_phase) cudaEventDestroy(e);
+    if (c->dev.d_flag) cudaFree(c->dev.d_flag);
+    if (c->dev.st) cudaStreamDestroy(c->dev.st);
+    delete c;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_set_priors(bsfg_ctx* c, const bsfg_priors* pr) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(pr); REQUIRE_PTR(pr->h2_priors_factors);
+    c->pri = *pr;
+    c->h2_prior_host.assign(pr->h2_priors_factors, pr->h2_priors_factors + c->H);
+    c->pri.h2_priors_factors = c->h2_prior_host.data();
+    c->h2_prior.alloc(c->H);
+    c->h2_prior.upload(c->h2_prior_host.data(), c->dev.st);
+    c->dev.sync();
+    c->have_priors = true;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(k);
+    if (!c->have_priors) fail(BSFG_ESTATE, "call bsfg_set_priors before bsfg_upload_constants (b_X_prec is needed)");
+    REQUIRE_PTR(k->Y); REQUIRE_PTR(k->U1); REQUIRE_PTR(k->s); REQUIRE_PTR(k->U2); REQUIRE_PTR(k->s1_2); REQUIRE_PTR(k->s2_2);
+    REQUIRE_PTR(k->Design_U); REQUIRE_PTR(k->U3); REQUIRE_PTR(k->s1_3); REQUIRE_PTR(k->s2_3);
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, r = c->r, b = c->b, br = c->br;
+    if (b > 0) REQUIRE_PTR(k->X);
+    if (!c->z1_identity) REQUIRE_PTR(k->Z_1);
+    c->U1.alloc(n, n); c->U1t.alloc(n, n); c->U2.alloc(br, br); c->U2t.alloc(br, br); c->DU.alloc(n, br); c->DUt.alloc(br, n);
+    c->U3.alloc(r, r); c->U3t.alloc(r, r);
+    c->s.alloc(n); c->s1_2.alloc(br); c->s2_2.alloc(br); c->s1_3.alloc(r); c->s2_3.alloc(r);
+    c->U1.upload(k->U1, d.st); c->U2.upload(k->U2, d.st); c->DU.upload(k->Design_U, d.st); c->U3.upload(k->U3, d.st);
+    c->s.upload(k->s, d.st); c->s1_2.upload(k->s1_2, d.st); c->s2_2.upload(k->s2_2, d.st);
+    c->s1_3.upload(k->s1_3, d.st); c->s2_3.upload(k->s2_3, d.st);
+    d.transpose(c->U1, c->U1t); d.transpose(c->U2, c->U2t); d.transpose(c->DU, c->DUt); d.transpose(c->U3, c->U3t);
+    if (!c->z1_identity) {
+        c->Z1.alloc(n, r); c->Z1t.alloc(r, n);
+        c->Z1.upload(k->Z_1, d.st);
+        d.transpose(c->Z1, c->Z1t);
+    }
+    {   // rotate the data once: U'Y, (U'Y)', Design_U'Y, colSums(Y^2), U'X
+        DMat Y(n, pl);
+        Y.upload(k->Y, d.st);
+        c->UtY.alloc(n, pl); c->UtYt.alloc(pl, n); c->DtY.alloc(br, pl);
+        d.gemm(1.0, c->U1, Y, 0.0, c->UtY);
+        d.transpose(c->UtY, c->UtYt);
+        d.gemm(1.0, c->DU, Y, 0.0, c->DtY);
+        colsumsq_kernel<<<ceil_div((long)pl * 32, 256), 256, 0, d.st>>>(Y.p, Y.ld, n, pl, c->yy.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (b > 0) {
+            DMat X(n, b);
+            X.upload(k->X, d.st);
+            c->UtX.alloc(n, b);
+            d.gemm(1.0, c->U1, X, 0.0, c->UtX);
+            d.sync();
+        }
+        d.sync();
+    }
+    // accuracy of the diagonalisation identities the "diag" forms rely on (SURVEY.md section 8d caveat)
+    c->M2.alloc(br, br);
+    d.gemm(1.0, c->DU, c->DU, 0.0, c->M2);                      // Design_U' Design_U  ~ diag(s2)
+    unsigned long long* d_mx = nullptr;
+    BSFG_CUDA(cudaMalloc(&d_mx, 2 * sizeof(unsigned long long)));
+    BSFG_CUDA(cudaMemsetAsync(d_mx, 0, 2 * sizeof(unsigned long long), d.st));
+    diag_residual_kernel<<<d.sms * 4, 256, 0, d.st>>>(c->M2.p, c->M2.ld, br, c->s2_2.p, d_mx + 1);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    bool have_m1 = false;
+    if (k->Ainv) {
+        DMat Ainv(r, r), P(br, br), PU(br, br);
+        Ainv.upload(k->Ainv, d.st);
+        build_prior_prec_kernel<<<d.sms * 4, 256, 0, d.st>>>(Ainv.p, Ainv.ld, r, b, c->pri.b_X_prec, P.p, P.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        c->M1.alloc(br, br);
+        d.gemm(1.0, P, c->U2, 0.0, PU);                         // P symmetric: P'U2 = P U2
+        d.gemm(1.0, c->U2, PU, 0.0, c->M1);                     // U2' P U2  ~ diag(s1)
+        diag_residual_kernel<<<d.sms * 4, 256, 0, d.st>>>(c->M1.p, c->M1.ld, br, c->s1_2.p, d_mx);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        d.sync();
+        have_m1 = true;
+    }
+    unsigned long long h_mx[2];
+    BSFG_CUDA(cudaMemcpyAsync(h_mx, d_mx, sizeof h_mx, cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    cudaFree(d_mx);
+    double r1, r2;
+    memcpy(&r1, &h_mx[0], 8); memcpy(&r2, &h_mx[1], 8);
+    c->resid_s1 = have_m1 ? r1 : -1.0;
+    c->resid_s2 = r2;
+    int mode = c->cfg.mode;
+    if (mode == 0) mode = (have_m1 && r1 <= 1e-11 && r2 <= 1e-11) ? 2 : (have_m1 ? 1 : 2);
+    if (mode == 1 && !have_m1) fail(BSFG_EARG, "mode 'direct' needs Ainv");
+    c->mode = mode;
+    if (mode == 1) { c->M1th.alloc(br, pl); c->M2th.alloc(br, pl); }
+    else { c->M1.release(); c->M2.release(); }
+    c->have_consts = true;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_get_mode(bsfg_ctx* c, int* mode, double* resid_s1, double* resid_s2) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c);
+    if (mode) *mode = c->mode;
+    if (resid_s1) *resid_s1 = c->resid_s1;
+    if (resid_s2) *resid_s2 = c->resid_s2;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(st);
+    REQUIRE_PTR(st->F); REQUIRE_PTR(st->resid_Y_prec); REQUIRE_PTR(st->E_a_prec); REQUIRE_PTR(st->Plam);
+    REQUIRE_PTR(st->delta); REQUIRE_PTR(st->tauh);
+    if (c->b > 0) REQUIRE_PTR(st->B);
+    const int k = st->k;
+    if (k < 2 || k > c->kmax) fail(BSFG_ESHAPE, "bsfg_set_state: k = %d outside [2, k_max = %d]", k, c->kmax);
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, r = c->r, b = c->b;
+    c->k = k;
+    c->iter = st->nrun;
+    DMat F = view(c->F, n, k); F.upload(st->F, d.st);
+    c->rp.upload(st->resid_Y_prec, d.st); c->ep.upload(st->E_a_prec, d.st);
+    BSFG_CUDA(cudaMemcpyAsync(c->delta.p, st->delta, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, st->tauh, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    if (b > 0) c->Bfix.upload(st->B, d.st);
+    {
+        DMat Plam(pl, k), Plamt = view(c->Plamt, k, pl);
+        Plam.upload(st->Plam, d.st);
+        d.transpose(Plam, Plamt);
+        d.sync();
+    }
+    if (st->Lambda) {
+        DMat Lam = view(c->Lam, pl, k), Lt = view(c->Lt, k, pl);
+        Lam.upload(st->Lambda, d.st);
+        d.transpose(Lam, Lt);
+    }
+    if (st->Lambda_prec) { DMat LP = view(c->LP, pl, k); LP.upload(st->Lambda_prec, d.st); }
+    if (st->F_a) { DMat Fa = view(c->Fa, r, k); Fa.upload(st->F_a, d.st); }
+    if (st->F_h2) BSFG_CUDA(cudaMemcpyAsync(c->F_h2.p, st->F_h2, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    if (st->E_a) {
+        if (c->Ea_in.rows != r) c->Ea_in.alloc(r, pl);
+        c->Ea_in.upload(st->E_a, d.st);
+    }
+    c->theta_valid = false;
+    c->derived_valid = false;
+    d.sync();
+    c->have_state = true;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_get_state(bsfg_ctx* c, bsfg_state* st) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(st);
+    if (!c->have_state) fail(BSFG_ESTATE, "no state on the device");
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, r = c->r, b = c->b, br = c->br, k = c->k;
+    st->k = k;
+    st->nrun = (int)c->iter;
+    if (st->Lambda) { DMat Lam = view(c->Lam, pl, k); Lam.download(st->Lambda, d.st); }
+    if (st->Lambda_prec) { DMat LP = view(c->LP, pl, k); LP.download(st->Lambda_prec, d.st); }
+    if (st->Plam) {
+        DMat Plam(pl, k), Plamt = view(c->Plamt, k, pl);
+        d.transpose(Plamt, Plam);
+        Plam.download(st->Plam, d.st);
+        d.sync();
+    }
+    if (st->F) { DMat F = view(c->F, n, k); F.download(st->F, d.st); }
+    if (st->F_a) { DMat Fa = view(c->Fa, r, k); Fa.download(st->F_a, d.st); }
+    if (st->F_h2) BSFG_CUDA(cudaMemcpyAsync(st->F_h2, c->F_h2.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+    if (st->B && b > 0) c->Bfix.download(st->B, d.st);
+    if (st->E_a) {
+        if (c->theta_valid) {
+            // E_a = location_sample[b+(1:r),] = U2[b.., :] theta   (fast_BSFG_sampler.R:207); U2t columns b.. = that block'
+            DMat Ea(r, pl);
+            DMat U2Et = view_at(c->U2t.p + (long)b * c->U2t.ld, br, r, c->U2t.ld);
+            d.gemm(1.0, U2Et, c->theta, 0.0, Ea);
+            Ea.download(st->E_a, d.st);
+            d.sync();
+        } else if (c->Ea_in.p) {
+            c->Ea_in.download(st->E_a, d.st);
+        } else {
+            fail(BSFG_ESTATE, "E_a requested but neither a sweep nor set_state provided it");
+        }
+    }
+    if (st->resid_Y_prec) c->rp.download(st->resid_Y_prec, d.st);
+    if (st->E_a_prec) c->ep.download(st->E_a_prec, d.st);
+    if (st->delta) BSFG_CUDA(cudaMemcpyAsync(st->delta, c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+    if (st->tauh) BSFG_CUDA(cudaMemcpyAsync(st->tauh, c->tauh.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    BSFG_API_END
+}
+
+extern "C" int bsfg_get_aux(bsfg_ctx* c, bsfg_aux* a) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(a);
+    Device& d = c->dev;
+    const int pl = c->pl, k = c->k;
+    if (a->Lambda_prec_rate) BSFG_CUDA(cudaMemcpyAsync(a->Lambda_prec_rate, c->aux_lp_rate.p, sizeof(double) * (size_t)pl * k, cudaMemcpyDeviceToHost, d.st));
+    if (a->resid_Y_prec_rate) c->aux_rr.download(a->resid_Y_prec_rate, d.st);
+    if (a->E_a_prec_rate) c->aux_re.download(a->E_a_prec_rate, d.st);
+    if (a->delta_rate) BSFG_CUDA(cudaMemcpyAsync(a->delta_rate, c->delta_rates.p, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, d.st));
+    if (a->h2_log_ps) BSFG_CUDA(cudaMemcpyAsync(a->h2_log_ps, c->aux_logps.p, sizeof(double) * (size_t)k * c->H, cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    BSFG_API_END
+}
+
+extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
+    BSFG_API_BEGIN
+    require_ready(c);
+    if (n_iter < 0) fail(BSFG_EARG, "n_iter < 0");
+    Device& d = c->dev;
+    c->aux_on = false;
+    const long long launches_before = g_launch_counter;
+    BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
+    for (int it = 0; it < n_iter; it++) {
+        const long i = c->iter + 1;                                         // for(i in start_i+(1:n_samples)), R:176
+        const uint64_t seed = c->cfg.seed;
+        const uint32_t ii = (uint32_t)i;
+        IterVariates v;
+        v.zL = make_var(nullptr, seed, SITE_Z_LAMBDA, ii, c->p_off, c->k);
+        v.zM = make_var(nullptr, seed, SITE_Z_MEANS, ii, c->p_off, c->br);
+        v.uh2 = make_var(nullptr, seed, SITE_U_H2, ii, 0, c->k);
+        v.zFa = make_var(nullptr, seed, SITE_Z_FA, ii, 0, c->r);
+        v.zF = make_var(nullptr, seed, SITE_Z_F, ii, 0, c->n);
+        v.gLP = make_var(nullptr, seed, SITE_G_LAMBDA_PREC, ii, c->p_off, c->p_total);
+        v.gR = make_var(nullptr, seed, SITE_G_RESID, ii, c->p_off, 1);
+        v.gE = make_var(nullptr, seed, SITE_G_EA, ii, c->p_off, 1);
+        v.gD = make_var(nullptr, seed, SITE_G_DELTA, ii, 0, 1);
+        c->phase_timing = (it == n_iter - 1);
+        gibbs_iteration(c, v);
+        RngStream rs{seed, SITE_U_K, ii};
+        update_k_step(c, i, philox_uniform(rs, 0), nullptr);               // uu = runif(1) every iteration, R:325
+        c->iter = i;
+    }
+    finish_timing(c, launches_before, n_iter);
+    BSFG_API_END
+}
+
+extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
+    BSFG_API_BEGIN
+    require_ready(c);
+    REQUIRE_PTR(hv);
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, k = c->k, r = c->r, br = c->br;
+    const long i = c->iter + 1;
+    const uint64_t seed = c->cfg.seed;
+    const uint32_t ii = (uint32_t)i;
+    auto stage = [&](DMat& buf, const double* host, long rows, long cols) -> const DMat* {
+        if (!host) return nullptr;
+        if (buf.rows != rows || buf.cols != cols) buf.alloc(rows, cols);
+        buf.upload(host, d.st);
+        return &buf;
+    };
+    IterVariates v;
+    v.zL = make_var(stage(c->v_zL, hv->z_Lambda, k, pl), seed, SITE_Z_LAMBDA, ii, c->p_off, k);
+    v.zM = make_var(stage(c->v_zM, hv->z_means, br, pl), seed, SITE_Z_MEANS, ii, c->p_off, br);
+    v.uh2 = make_var(stage(c->v_uh2, hv->u_h2, k, 1), seed, SITE_U_H2, ii, 0, k);
+    v.zFa = make_var(stage(c->v_zFa, hv->z_Fa, r, k), seed, SITE_Z_FA, ii, 0, r);
+    v.zF = make_var(stage(c->v_zF, hv->z_F, n, k), seed, SITE_Z_F, ii, 0, n);
+    v.gLP = make_var(stage(c->v_gLP, hv->g_Lambda_prec, pl, k), seed, SITE_G_LAMBDA_PREC, ii, c->p_off, c->p_total);
+    v.gR = make_var(stage(c->v_gR, hv->g_resid, pl, 1), seed, SITE_G_RESID, ii, c->p_off, 1);
+    v.gE = make_var(stage(c->v_gE, hv->g_Ea, pl, 1), seed, SITE_G_EA, ii, c->p_off, 1);
+    {
+        const DMat* gd = nullptr;
+        if (hv->g_delta) {       // only as many entries as sample_delta draws: 1 + |2:(k-1)|
+            if (c->v_gD.rows != c->kmax + 2) c->v_gD.alloc(c->kmax + 2, 1);
+            BSFG_CUDA(cudaMemcpyAsync(c->v_gD.p, hv->g_delta, sizeof(double) * (size_t)(k == 2 ? 3 : k - 1),
+                                      cudaMemcpyHostToDevice, d.st));
+            gd = &c->v_gD;
+        }
+        v.gD = make_var(gd, seed, SITE_G_DELTA, ii, 0, 1);
+    }
+    d.sync();
+    c->aux_on = true;
+    c->phase_timing = true;
+    const long long launches_before = g_launch_counter;
+    BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
+    gibbs_iteration(c, v);
+    double uu;
+    if (hv->u_k) uu = *hv->u_k;
+    else { RngStream rs{seed, SITE_U_K, ii}; uu = philox_uniform(rs, 0); }
+    KAddVariates ka;
+    bool have_add = hv->k_g_lp && hv->k_g_delta && hv->k_z_lambda && hv->k_u_h2 && hv->k_z_Fa && hv->k_z_F;
+    if (have_add) {
+        // staged as one buffer: [g_lp (pl) | z_lambda (pl) | z_Fa (r) | z_F (n)]
+        const long tot = 2L * pl + r + n;
+        if (c->v_kadd.rows != tot) c->v_kadd.alloc(tot, 1);
+        BSFG_CUDA(cudaMemcpyAsync(c->v_kadd.p, hv->k_g_lp, sizeof(double) * pl, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->v_kadd.p + pl, hv->k_z_lambda, sizeof(double) * pl, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->v_kadd.p + 2L * pl, hv->k_z_Fa, sizeof(double) * r, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->v_kadd.p + 2L * pl + r, hv->k_z_F, sizeof(double) * n, cudaMemcpyHostToDevice, d.st));
+        d.sync();
+        auto mk = [&](double* p) { VarSrc s = make_var(nullptr, 0, 0, 0, 0, 1); s.ptr = p; s.ld = 0; return s; };
+        ka.g_lp = mk(c->v_kadd.p); ka.z_lam = mk(c->v_kadd.p + pl); ka.z_fa = mk(c->v_kadd.p + 2L * pl);
+        ka.z_f = mk(c->v_kadd.p + 2L * pl + r);
+        ka.g_delta = *hv->k_g_delta; ka.u_h2 = *hv->k_u_h2; ka.have_scalars = true;
+    }
+    update_k_step(c, i, uu, have_add ? &ka : nullptr);
+    c->iter = i;
+    finish_timing(c, launches_before, 1);
+    BSFG_API_END
+}
+
+extern "C" int bsfg_get_timing(bsfg_ctx* c, double* total_ms, long long* launches, double* phase_ms) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c);
+    if (total_ms) *total_ms = c->last_total_ms;
+    if (launches) *launches = c->last_launches;
+    if (phase_ms) memcpy(phase_ms, c->phase_ms, sizeof(double) * BSFG_N_PHASES);
+    BSFG_API_END
+}
+
+extern "C" int bsfg_nccl_unique_id(char id_out[128]) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(id_out);
+    g_nccl.load();
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    BSFG_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, 128);
+    BSFG_API_END
+}
+
+extern "C" int bsfg_comm_init(bsfg_ctx* c, const char id_in[128]) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(id_in);
+    if (c->cfg.world <= 1) return BSFG_OK;
+    g_nccl.load();
+    ncclUniqueId id;
+    memcpy(&id, id_in, 128);
+    BSFG_NCCL(g_nccl.CommInitRank(&c->comm, c->cfg.world, id, c->cfg.rank));
+    BSFG_API_END
+}

@@ -1,9 +1,300 @@
-"""Host-side mirror of the reference's R driver contract (placeholder; filled in with the sweep)."""
+"""Host-side mirror of the reference's R driver contract.
+
+`fast_BSFG_sampler(BSFG_state, n_samples)` keeps the contract of `R_BSFG/fast_BSFG_sampler.R:1`:
+it takes the `BSFG_state` list (here a dict of dicts with the same field names, see
+fast_BSFG_sampler_init.R:352-362), runs `n_samples` Gibbs iterations starting at
+`current_state$nrun + 1`, records posterior samples on the reference's burn/thin schedule
+(`fast_BSFG_sampler.R:272-279` -> `save_posterior_samples`, BSFG_functions.R:375-408) and returns the
+updated `BSFG_state`.  The loop body (`:176-270`) runs on the GPU through `BSFGSweep`, a thin wrapper
+of the stateful C ABI (include/bsfg_b200.h); the state stays resident in HBM between iterations and is
+only read back at thinning boundaries.  Plotting / .RData side effects of the R driver are not part
+of the contract reproduced here.
+
+Trait sharding (one process per GPU): every rank constructs `BSFGSweep(..., rank=, world=)` over its
+slice of trait columns (`shard_bounds`), and the ranks share a NCCL communicator created from a
+unique id that the caller broadcasts (bench.py uses torch.distributed for that plumbing).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_f, check, ptr
+
+_STATE_FIELDS = ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
+                 "E_a_prec", "delta", "tauh")
+_VARIATE_FIELDS = ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
+                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F")
 
 
-class BSFGSweep:  # pragma: no cover - replaced in the next commit
-    pass
+def shard_bounds(p, rank, world):
+    """Contiguous, balanced split of the p trait columns: rank g owns [lo, hi)."""
+    base, rem = divmod(p, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
 
 
-def fast_BSFG_sampler(BSFG_state, n_samples):  # pragma: no cover
-    raise NotImplementedError
+def _is_identity(Z):
+    Z = np.asarray(Z)
+    return Z.shape[0] == Z.shape[1] and np.array_equal(Z, np.eye(Z.shape[0]))
+
+
+class BSFGSweep:
+    """Device-resident Gibbs sweep for one chain (one rank's trait shard)."""
+
+    def __init__(self, data_matrices, run_variables, priors, run_parameters, *, k_max=None, k_init=None,
+                 seed=0, rank=0, world=1, mode="auto", nccl_id=None):
+        self.lib = _lib.load()
+        Y = np.asarray(data_matrices["Y"], dtype=np.float64)
+        if np.isnan(Y).any():
+            raise ValueError("missing phenotypes (NaN in Y) are not supported by the device sweep yet")
+        X = np.asarray(data_matrices["X"], dtype=np.float64)
+        Z_1 = np.asarray(data_matrices["Z_1"], dtype=np.float64)
+        Z_2 = data_matrices.get("Z_2")
+        if Z_2 is not None and np.asarray(Z_2).shape[1] > 0:
+            raise ValueError("a second random effect (Z_2) is not supported by the device sweep yet")
+        n, p = Y.shape
+        r = Z_1.shape[1]
+        b = X.shape[1]
+        self.n, self.p_total, self.r, self.b, self.br = n, p, r, b, b + r
+        self.rank, self.world = rank, world
+        self.lo, self.hi = shard_bounds(p, rank, world)
+        self.pl = self.hi - self.lo
+        self.H = int(run_parameters["h2_divisions"])
+        k0 = int(k_init if k_init is not None else priors["k_init"])
+        self.k_max = int(k_max if k_max is not None else max(2 * k0, k0 + 8))
+        ident = _is_identity(Z_1)
+        cfg = _lib.bsfg_config(n=n, p_total=p, p_offset=self.lo, p_local=self.pl, k=k0, k_max=self.k_max,
+                               r=r, b=b, h2_divisions=self.H, rank=rank, world=world, seed=seed,
+                               z1_is_identity=int(ident), mode={"auto": 0, "direct": 1, "diag": 2}[mode])
+        self._ctx = C.c_void_p()
+        check(self.lib.bsfg_create(C.byref(cfg), C.byref(self._ctx)))
+        # priors / run parameters
+        self._h2p = np.ascontiguousarray(np.asarray(priors["h2_priors_factors"], dtype=np.float64).ravel())
+        if self._h2p.shape[0] != self.H:
+            raise ValueError("h2_priors_factors must have h2_divisions entries")
+        bx = priors.get("b_X_prec", 1e-10)
+        bx = float(np.asarray(bx).ravel()[0]) if np.size(bx) else 1e-10
+        pr = _lib.bsfg_priors(priors["resid_Y_prec_shape"], priors["resid_Y_prec_rate"], priors["E_a_prec_shape"],
+                              priors["E_a_prec_rate"], priors["Lambda_df"], priors["delta_1_shape"],
+                              priors["delta_1_rate"], priors["delta_2_shape"], priors["delta_2_rate"], bx,
+                              ptr(self._h2p), run_parameters["b0"], run_parameters["b1"],
+                              run_parameters["epsilon"], run_parameters["prop"])
+        check(self.lib.bsfg_set_priors(self._ctx, C.byref(pr)))
+        # constants (this rank's trait columns of Y)
+        l1 = run_variables["invert_aI_bZAZ"]; l2 = run_variables["invert_aPXA_bDesignDesignT"]
+        l3 = run_variables["invert_aZZt_Ainv"]
+        keep = [as_f(Y[:, self.lo:self.hi]), as_f(X), None if ident else as_f(Z_1),
+                as_f(l1["U"], (n, n)), np.ascontiguousarray(np.asarray(l1["s"], dtype=np.float64).ravel()),
+                as_f(l2["U"], (self.br, self.br)), np.ascontiguousarray(np.asarray(l2["s1"], dtype=np.float64).ravel()),
+                np.ascontiguousarray(np.asarray(l2["s2"], dtype=np.float64).ravel()), as_f(l2["Design_U"], (n, self.br)),
+                as_f(l3["U"], (r, r)), np.ascontiguousarray(np.asarray(l3["s1"], dtype=np.float64).ravel()),
+                np.ascontiguousarray(np.asarray(l3["s2"], dtype=np.float64).ravel()),
+                as_f(run_variables["Ainv"], (r, r)) if run_variables.get("Ainv") is not None else None]
+        consts = _lib.bsfg_constants(*[ptr(a) for a in keep])
+        check(self.lib.bsfg_upload_constants(self._ctx, C.byref(consts)))
+        if world > 1:
+            if nccl_id is None:
+                raise ValueError("world > 1 needs the 128-byte NCCL unique id (see nccl_unique_id())")
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            check(self.lib.bsfg_comm_init(self._ctx, buf))
+
+    # -- multi-GPU plumbing ----------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        check(_lib.load().bsfg_nccl_unique_id(buf))
+        return buf.raw
+
+    # -- state -----------------------------------------------------------------------------
+    def set_state(self, current_state):
+        """Upload `current_state` (fast_BSFG_sampler_init.R:238-254 field names); trait-indexed members
+        are given for ALL traits and sliced to this rank's shard here."""
+        cs = current_state
+        k = int(np.asarray(cs["F"]).shape[1])
+        sl = slice(self.lo, self.hi)
+        arrs = {}
+
+        def put(name, a):
+            arrs[name] = a
+            return ptr(a)
+
+        st = _lib.bsfg_state()
+        st.Lambda = put("Lambda", as_f(np.asarray(cs["Lambda"])[sl, :])) if cs.get("Lambda") is not None else None
+        st.Lambda_prec = put("Lambda_prec", as_f(np.asarray(cs["Lambda_prec"])[sl, :])) if cs.get("Lambda_prec") is not None else None
+        st.Plam = put("Plam", as_f(np.asarray(cs["Plam"])[sl, :]))
+        st.F = put("F", as_f(cs["F"]))
+        st.F_a = put("F_a", as_f(cs["F_a"])) if cs.get("F_a") is not None else None
+        st.F_h2 = put("F_h2", np.ascontiguousarray(np.asarray(cs["F_h2"], dtype=np.float64).ravel())) if cs.get("F_h2") is not None else None
+        st.B = put("B", as_f(np.asarray(cs["B"]).reshape(self.b, self.p_total)[:, sl])) if self.b > 0 else None
+        st.E_a = put("E_a", as_f(np.asarray(cs["E_a"])[:, sl])) if cs.get("E_a") is not None else None
+        st.resid_Y_prec = put("rp", np.ascontiguousarray(np.asarray(cs["resid_Y_prec"], dtype=np.float64).ravel()[sl]))
+        st.E_a_prec = put("ep", np.ascontiguousarray(np.asarray(cs["E_a_prec"], dtype=np.float64).ravel()[sl]))
+        st.delta = put("delta", np.ascontiguousarray(np.asarray(cs["delta"], dtype=np.float64).ravel()))
+        st.tauh = put("tauh", np.ascontiguousarray(np.asarray(cs["tauh"], dtype=np.float64).ravel()))
+        st.k = k
+        st.nrun = int(cs.get("nrun", 0))
+        check(self.lib.bsfg_set_state(self._ctx, C.byref(st)))
+
+    def get_state(self, with_E_a=True):
+        """Download this rank's shard of `current_state` (same field names; trait-indexed members cover
+        columns [lo, hi) only)."""
+        probe = _lib.bsfg_state()
+        check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))     # all-NULL call: just k and nrun
+        k = probe.k
+        out = dict(Lambda=np.zeros((self.pl, k), order="F"), Lambda_prec=np.zeros((self.pl, k), order="F"),
+                   Plam=np.zeros((self.pl, k), order="F"), F=np.zeros((self.n, k), order="F"),
+                   F_a=np.zeros((self.r, k), order="F"), F_h2=np.zeros(k), B=np.zeros((self.b, self.pl), order="F"),
+                   resid_Y_prec=np.zeros(self.pl), E_a_prec=np.zeros(self.pl), delta=np.zeros(k), tauh=np.zeros(k))
+        if with_E_a:
+            out["E_a"] = np.zeros((self.r, self.pl), order="F")
+        st = _lib.bsfg_state()
+        for name in _STATE_FIELDS:
+            if name in out and out[name].size:
+                setattr(st, name, ptr(out[name]))
+        check(self.lib.bsfg_get_state(self._ctx, C.byref(st)))
+        out["nrun"] = st.nrun
+        out["W"] = np.zeros((0, self.pl)); out["W_prec"] = np.zeros(self.pl)
+        return out
+
+    # -- sweeping --------------------------------------------------------------------------
+    def sweep(self, n_iter):
+        """`n_iter` Gibbs iterations with device Philox draws."""
+        check(self.lib.bsfg_sweep(self._ctx, int(n_iter)))
+
+    def sweep_injected(self, variates):
+        """One iteration with injected variates (dict in the layout of oracle gibbs_iteration; trait-indexed
+        blocks are given for ALL traits and sliced here)."""
+        sl = slice(self.lo, self.hi)
+        hold = []
+        v = _lib.bsfg_variates()
+
+        def conv(name, a):
+            a = np.asarray(a, dtype=np.float64)
+            if name in ("z_Lambda", "z_means"):
+                a = a[:, sl]
+            elif name in ("g_Lambda_prec",):
+                a = a[sl, :]
+            elif name in ("g_resid", "g_Ea", "k_g_lp", "k_z_lambda"):
+                a = a.ravel()[sl]
+            a = np.asfortranarray(a) if a.ndim == 2 else np.ascontiguousarray(a.ravel())
+            hold.append(a)
+            return ptr(a)
+
+        for name in _VARIATE_FIELDS:
+            if variates.get(name) is not None:
+                setattr(v, name, conv(name, variates[name]))
+        check(self.lib.bsfg_sweep_injected(self._ctx, C.byref(v)))
+
+    def aux(self):
+        probe = _lib.bsfg_state()
+        check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))
+        k = probe.k
+        out = dict(Lambda_prec_rate=np.zeros((self.pl, k), order="F"), resid_Y_prec_rate=np.zeros(self.pl),
+                   E_a_prec_rate=np.zeros(self.pl), delta_rate=np.zeros(k + 2), h2_log_ps=np.zeros((k, self.H), order="F"))
+        a = _lib.bsfg_aux(*[ptr(out[nm]) for nm in ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate",
+                                                     "delta_rate", "h2_log_ps")])
+        check(self.lib.bsfg_get_aux(self._ctx, C.byref(a)))
+        return out
+
+    def mode(self):
+        m = C.c_int(0); r1 = C.c_double(0); r2 = C.c_double(0)
+        check(self.lib.bsfg_get_mode(self._ctx, C.byref(m), C.byref(r1), C.byref(r2)))
+        return {1: "direct", 2: "diag"}.get(m.value, "?"), r1.value, r2.value
+
+    def timing(self):
+        t = C.c_double(0); n = C.c_longlong(0)
+        ph = (C.c_double * _lib.BSFG_N_PHASES)()
+        check(self.lib.bsfg_get_timing(self._ctx, C.byref(t), C.byref(n), ph))
+        names = ("lambda_prep", "lambda", "lambda_chol", "means", "h2", "F_a", "F_gemm", "F_comm", "F_solve",
+                 "precisions", "delta", "update_k")
+        return t.value, n.value, dict(zip(names, list(ph)))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.bsfg_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------
+# fast_BSFG_sampler (R_BSFG/fast_BSFG_sampler.R) -- same entry point, state dict in, state dict out
+# ------------------------------------------------------------------------------------------
+def _save_posterior_samples(sp_num, Posterior, cs):
+    """BSFG_functions.R:375-408: full traces for Lambda, F, F_a, delta, F_h2 and the precisions (rows grow
+    when update_k adds factors), running means for B and E_a."""
+    def put(name, vec):
+        vec = np.asarray(vec, dtype=np.float64).ravel(order="F")
+        M = Posterior.get(name)
+        if M is None or M.size == 0:
+            M = np.zeros((vec.shape[0], sp_num))
+        if M.shape[1] < sp_num:
+            M = np.column_stack([M, np.zeros((M.shape[0], sp_num - M.shape[1]))])
+        if vec.shape[0] > M.shape[0]:
+            M = np.vstack([M, np.zeros((vec.shape[0] - M.shape[0], M.shape[1]))])
+        M[:vec.shape[0], sp_num - 1] = vec
+        Posterior[name] = M
+    for name in ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec"):
+        put(name, cs[name])
+    for name in ("B", "E_a"):
+        prev = Posterior.get(name)
+        cur = np.asarray(cs[name], dtype=np.float64)
+        if prev is None or np.shape(prev) != cur.shape:
+            prev = np.zeros_like(cur)
+        Posterior[name] = (prev * (sp_num - 1) + cur) / sp_num
+    return Posterior
+
+
+def fast_BSFG_sampler(BSFG_state, n_samples, *, seed=None, sweep=None):
+    """Run `n_samples` iterations of the BSFG Gibbs sampler on the GPU (fast_BSFG_sampler.R:1).
+
+    BSFG_state: dict with data_matrices, run_parameters, run_variables, priors, current_state and
+    (optional) Posterior, as produced by the init (fast_BSFG_sampler_init.R:352-362).
+    `sweep`: an existing BSFGSweep to reuse (keeps the rotated data resident across calls); otherwise
+    one is created and closed here.  Returns the updated BSFG_state (new dict; inputs are not mutated).
+    """
+    rp = BSFG_state["run_parameters"]
+    cs = dict(BSFG_state["current_state"])
+    Posterior = dict(BSFG_state.get("Posterior") or {})
+    burn, thin = int(rp.get("burn", 0)), int(rp.get("thin", 1))
+    start_i = int(cs.get("nrun", 0))
+    own = sweep is None
+    if own:
+        if seed is None:
+            seed = int(BSFG_state.get("RNG", {}).get("seed", 0)) if isinstance(BSFG_state.get("RNG"), dict) else 0
+        sweep = BSFGSweep(BSFG_state["data_matrices"], BSFG_state["run_variables"], BSFG_state["priors"], rp,
+                          k_init=np.asarray(cs["F"]).shape[1], seed=seed)
+    try:
+        sweep.set_state(cs)
+        i = start_i
+        end = start_i + int(n_samples)
+        while i < end:
+            # run up to the next thinning boundary (fast_BSFG_sampler.R:272)
+            nxt = end
+            if thin > 0:
+                j = max(i + 1, burn + 1)
+                while (j - burn) % thin != 0:
+                    j += 1
+                if j <= end:
+                    nxt = j
+            sweep.sweep(nxt - i)
+            i = nxt
+            if (i - burn) % thin == 0 and i > burn:
+                sp_num = (i - burn) // thin
+                Posterior = _save_posterior_samples(sp_num, Posterior, sweep.get_state(with_E_a=True))
+        new_cs = sweep.get_state(with_E_a=True)
+    finally:
+        if own:
+            sweep.close()
+    out = dict(BSFG_state)
+    out["current_state"] = new_cs
+    out["Posterior"] = Posterior
+    return out

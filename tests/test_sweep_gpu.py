@@ -1,0 +1,198 @@
+"""GPU parity of the fused, device-resident sweep (rotated-data formulation) against the oracle's
+reference-formulation Gibbs iteration (fast_BSFG_sampler.R:176-270) under injected variates."""
+import numpy as np
+import pytest
+
+from conftest import relerr, rowwise_relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _build(n, p, k, lists, pedigree="halfsib", seed=7, b=1):
+    from oracle import init_oracle as I
+    setup = I.make_synthetic(n, p, max(2, k // 2), pedigree=pedigree, seed=seed, b=b)
+    pri = I.default_priors(k_init=k)
+    rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=3, lists=lists)
+    return st
+
+
+def _compare_states(dev, ora, b, tol=TOL, h2_exact=True):
+    assert dev["F"].shape == ora["F"].shape
+    assert rowwise_relerr(dev["Lambda"], ora["Lambda"]) < tol
+    assert rowwise_relerr(dev["F"], ora["F"]) < tol
+    assert rowwise_relerr(dev["F_a"].T, ora["F_a"].T) < tol
+    if h2_exact:
+        assert np.array_equal(dev["F_h2"], np.asarray(ora["F_h2"]).ravel())
+    assert relerr(dev["B"], ora["B"].reshape(dev["B"].shape)) < tol
+    assert rowwise_relerr(dev["E_a"].T, ora["E_a"].T) < tol
+    assert relerr(dev["Lambda_prec"], ora["Lambda_prec"]) < tol
+    assert relerr(dev["resid_Y_prec"], ora["resid_Y_prec"]) < tol
+    assert relerr(dev["E_a_prec"], ora["E_a_prec"]) < tol
+    assert relerr(dev["delta"], ora["delta"]) < tol
+    assert relerr(dev["tauh"], ora["tauh"]) < tol
+    assert relerr(dev["Plam"], ora["Plam"]) < tol * 10
+
+
+@pytest.mark.parametrize("lists,mode,expect", [("stable", "auto", "diag"), ("reference", "auto", "direct"),
+                                               ("stable", "direct", "direct")])
+def test_sweep_injected_matches_oracle(lists, mode, expect):
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 60, 45, 6
+    st = _build(n, p, k, lists)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, mode=mode)
+    try:
+        got_mode, r1, r2 = sw.mode()
+        assert got_mode == expect, (got_mode, r1, r2)
+        rng = np.random.default_rng(21)
+        ora = cs
+        for it in range(1, 4):
+            v = I.draw_variates(rng, n, p, k, n, 1 + n, pri)
+            sw.set_state(ora)                      # re-synchronise, then compare one iteration
+            ora_next, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            assert dev["nrun"] == it
+            _compare_states(dev, ora_next, 1)
+            a = sw.aux()
+            assert relerr(a["resid_Y_prec_rate"], aux["resid_Y_prec_rate"]) < TOL
+            assert relerr(a["E_a_prec_rate"], aux["E_a_prec_rate"]) < TOL
+            assert relerr(a["Lambda_prec_rate"], aux["Lambda_prec_rate"]) < TOL
+            nd = len(aux["delta_rate"])
+            assert relerr(a["delta_rate"][:nd], aux["delta_rate"]) < TOL
+            ora = ora_next
+    finally:
+        sw.close()
+
+
+def test_sweep_free_running_three_iterations():
+    """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 50, 64, 5
+    st = _build(n, p, k, "stable", seed=11)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=10)
+    try:
+        sw.set_state(cs)
+        rng = np.random.default_rng(22)
+        ora = cs
+        for it in range(1, 4):
+            v = I.draw_variates(rng, n, p, k, n, 1 + n, pri)
+            ora, _ = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+        dev = sw.get_state()
+        _compare_states(dev, ora, 1, tol=1e-7)
+    finally:
+        sw.close()
+
+
+def test_sweep_random_pedigree_rectangular_design():
+    """n distinct eigenvalues (random pedigree), b = 2 fixed effects, odd sizes."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 53, 37, 7
+    st = _build(n, p, k, "stable", pedigree="random", seed=5, b=2)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=9)
+    try:
+        rng = np.random.default_rng(23)
+        v = I.draw_variates(rng, n, p, k, n, 2 + n, pri)
+        sw.set_state(cs)
+        ora, _ = O.gibbs_iteration(d, rv, pri, rp, cs, 1, v)
+        sw.sweep_injected(v)
+        _compare_states(sw.get_state(), ora, 2)
+    finally:
+        sw.close()
+
+
+def test_update_k_add_and_drop():
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 40, 30, 5
+    st = _build(n, p, k, "stable", seed=13)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    cs = dict(cs)
+    # moderate shrinkage everywhere -> no redundant column -> the add arm fires when uu < prob and i > 200
+    cs["delta"] = np.array([1.5, 1.2, 1.1, 1.3, 1.2]); cs["tauh"] = np.cumprod(cs["delta"])
+    cs["Plam"] = cs["Lambda_prec"] * cs["tauh"][None, :]
+    cs["nrun"] = 300
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8)
+    try:
+        rng = np.random.default_rng(24)
+        v = I.draw_variates(rng, n, p, k, n, 1 + n, pri, add_arm=True)
+        v["u_k"] = 1e-6
+        sw.set_state(cs)
+        ora, _ = O.gibbs_iteration(d, rv, pri, rp, cs, 301, v)
+        assert ora["F"].shape[1] == k + 1, "oracle did not take the add arm; test inputs need retuning"
+        sw.sweep_injected(v)
+        dev = sw.get_state()
+        assert dev["F"].shape[1] == k + 1
+        _compare_states(dev, ora, 1)
+        # next iteration runs with k+1 factors
+        v2 = I.draw_variates(rng, n, p, k + 1, n, 1 + n, pri)
+        v2["u_k"] = 0.99
+        ora2, _ = O.gibbs_iteration(d, rv, pri, rp, ora, 302, v2)
+        sw.set_state(ora)
+        sw.sweep_injected(v2)
+        _compare_states(sw.get_state(), ora2, 1)
+        # drop arm: crush columns 2 and 4 (0-based 1, 3) with enormous shrinkage -> all |Lambda| < eps
+        cs3 = dict(ora2)
+        kk = cs3["F"].shape[1]
+        delta = np.array([1.5, 1e14, 1e-14 * 1.2, 1e14, 1e-14 * 1.3, 1.1])[:kk]
+        cs3["delta"] = delta; cs3["tauh"] = np.cumprod(delta)
+        cs3["Plam"] = cs3["Lambda_prec"] * cs3["tauh"][None, :]
+        v3 = I.draw_variates(rng, n, p, kk, n, 1 + n, pri)
+        v3["u_k"] = 1e-6
+        ora3, _ = O.gibbs_iteration(d, rv, pri, rp, cs3, 303, v3)
+        assert ora3["F"].shape[1] < kk, "oracle did not take the drop arm; test inputs need retuning"
+        sw.set_state(cs3)
+        sw.sweep_injected(v3)
+        dev3 = sw.get_state()
+        assert dev3["F"].shape[1] == ora3["F"].shape[1]
+        _compare_states(dev3, ora3, 1, tol=1e-8)
+    finally:
+        sw.close()
+
+
+def test_philox_sweep_reproducible_and_finite():
+    """production path: device draws; same seed -> identical chain, different seed -> different."""
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 60, 45, 6
+    st = _build(n, p, k, "stable")
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    outs = []
+    for seed in (5, 5, 6):
+        sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, seed=seed)
+        try:
+            sw.set_state(cs)
+            sw.sweep(5)
+            outs.append(sw.get_state())
+            t, launches, _ = sw.timing()
+            assert t > 0 and launches > 100
+        finally:
+            sw.close()
+    for name in ("Lambda", "F", "F_a", "resid_Y_prec", "E_a_prec", "delta"):
+        assert np.all(np.isfinite(outs[0][name]))
+        assert np.array_equal(outs[0][name], outs[1][name])
+    assert not np.array_equal(outs[0]["F"], outs[2]["F"])
+    assert outs[0]["nrun"] == 5
+
+
+def test_fast_BSFG_sampler_contract():
+    """fast_BSFG_sampler(BSFG_state, n_samples) -> BSFG_state with Posterior filled on the burn/thin schedule."""
+    from sparsefactormixedmodel_b200 import fast_BSFG_sampler
+    n, p, k = 40, 30, 4
+    st = _build(n, p, k, "stable", seed=17)
+    st["run_parameters"].update(burn=4, thin=2)
+    out = fast_BSFG_sampler(st, 10, seed=3)
+    assert out["current_state"]["nrun"] == 10
+    assert st["current_state"]["nrun"] == 0                       # input not mutated
+    assert out["Posterior"]["Lambda"].shape == (p * k, 3)          # i = 6, 8, 10
+    assert out["Posterior"]["E_a"].shape == (n, p)
+    out2 = fast_BSFG_sampler(out, 4, seed=3)                       # continuation (README.md:33)
+    assert out2["current_state"]["nrun"] == 14
+    assert out2["Posterior"]["Lambda"].shape[1] == 5
