@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs iterations/second of the BSFG sweep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C4]
+
+A "step" is one Gibbs iteration (the loop body of fast_BSFG_sampler, R_BSFG/fast_BSFG_sampler.R:176-270)
+on synthetic data of the named shape.  Default workload: C4 = n 5000 individuals, p 20000 traits, k 100
+factors, X = 1_n, Z_1 = I_n, random three-generation pedigree; traits are sharded
+over the N ranks (total work fixed -> "strong" scaling).  One JSON line is printed by rank 0.
+
+  value        iterations/s with the chain state resident in HBM (K iterations inside ONE bsfg_sweep call,
+               timed with CUDA events on the library's stream; max over ranks)
+  e2e          the same metric through the public host API per iteration: pinned host state -> set_state
+               (H2D) -> one iteration -> get_state of the posterior-sample fields (D2H)
+  roofline     the weighted-Gram FP64 GEMM (dgemm_tn_kernel, DMMA + TMA): algorithmic k(k+1) n p_local
+               FLOP / its CUDA-event duration, vs the cuBLAS DGEMM rate measured on this pool
+  cpu_baseline the oracle (restatement of the reference formulation) timed on this box's host cores on a
+               bounded trait sample (rank 0, N = 1 only)
+
+Synthetic inputs and the three diagonalisations are generated here (torch on the GPU when present, for
+speed; not part of any timed region).  The oracle is only imported by the CPU-baseline legs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, p, k)            BASELINE.json configs
+    "C2": (1000, 1000, 20),
+    "C3": (200, 10000, 50),
+    "C4": (5000, 20000, 100),
+    "C5": (20000, 50000, 200),
+    "tiny": (96, 160, 8),
+}
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+NCU_SUMMARY_FILE = os.path.join(ROOT, "profiles", "ncu_gram_gemm.json")
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic problem (recipe: generate_simulations_halfSib.R:20-37,72-89)
+# --------------------------------------------------------------------------------------------
+def random_pedigree_A(n, rng, frac_founders=0.2, frac_gen1=0.3):
+    n0 = max(2, int(n * frac_founders)); n1 = max(2, int(n * frac_gen1)); n2 = n - n0 - n1
+    A = np.zeros((n, n))
+    A[:n0, :n0] = np.eye(n0)
+    lo, prev = n0, (0, n0)
+    for cnt in (n1, n2):
+        if cnt <= 0:
+            continue
+        hi = lo + cnt
+        sire = rng.integers(prev[0], prev[1], size=cnt)
+        dam = rng.integers(prev[0], prev[1], size=cnt)
+        same = sire == dam
+        dam[same] = prev[0] + (dam[same] - prev[0] + 1) % (prev[1] - prev[0])
+        A[lo:hi, :lo] = 0.5 * (A[sire, :lo] + A[dam, :lo])
+        A[:lo, lo:hi] = A[lo:hi, :lo].T
+        blk = 0.5 * (A[lo:hi, :lo][:, sire] + A[lo:hi, :lo][:, dam])
+        blk = 0.5 * (blk + blk.T)
+        np.fill_diagonal(blk, 1.0 + 0.5 * A[sire, dam])
+        A[lo:hi, lo:hi] = blk
+        prev, lo = (lo, hi), hi
+    return A
+
+
+def make_problem(n, p, k, seed=20131, device=None):
+    """Returns (data_matrices, run_variables, priors, run_parameters, current_state) as host NumPy."""
+    import torch
+    dev = torch.device(device if device is not None else ("cuda:0" if torch.cuda.is_available() else "cpu"))
+    f64 = torch.float64
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+    A_np = random_pedigree_A(n, rng)
+    A = torch.from_numpy(A_np).to(dev)
+    k_true = max(2, k // 2)
+    factor_h2s = np.linspace(1.0, 0.0, k_true + 1)[:k_true].copy()
+    factor_h2s[0::2] = 0.0
+    Lam_true = np.zeros((p, k_true))
+    lo, hi = max(1, p // 30), max(2, p // 4)
+    for h in range(k_true):
+        numeff = int(rng.integers(lo, hi + 1))
+        rows = rng.choice(p, size=numeff, replace=False)
+        Lam_true[rows, h] = rng.standard_normal(numeff)
+    Lt_ = torch.from_numpy(Lam_true).to(dev)
+    h2 = torch.from_numpy(factor_h2s).to(dev)
+    L_A = torch.linalg.cholesky(A)
+    rn = lambda *s: torch.randn(*s, dtype=f64, device=dev, generator=gen)
+    U_act = L_A @ (rn(n, k_true) @ (Lt_ * h2.sqrt()[None, :]).T + np.sqrt(0.2) * rn(n, p))
+    E_act = rn(n, k_true) @ (Lt_ * (1 - h2).sqrt()[None, :]).T + np.sqrt(0.2) * rn(n, p)
+    Y = U_act + E_act
+    del U_act, E_act
+    X = torch.ones(n, 1, dtype=f64, device=dev)
+    b = 1
+    # --- the three diagonalisations (same contract as fast_BSFG_sampler_init.R:263-325), eigen route
+    s, U = torch.linalg.eigh(A)
+    s = s.flip(0).clamp_min(0.0).contiguous(); U = U.flip(1).contiguous()
+    Ainv = torch.linalg.inv(A); Ainv = 0.5 * (Ainv + Ainv.T)
+    br = b + n
+    P = torch.zeros(br, br, dtype=f64, device=dev); P[0, 0] = 1e-10; P[b:, b:] = Ainv
+    D = torch.cat([X, torch.eye(n, dtype=f64, device=dev)], dim=1)
+    D2 = D.T @ D
+    Lc = torch.linalg.cholesky(P + D2)
+    Li = torch.linalg.solve_triangular(Lc, torch.eye(br, dtype=f64, device=dev), upper=False)
+    M = Li @ D2 @ Li.T; M = 0.5 * (M + M.T)
+    lam, V = torch.linalg.eigh(M)
+    lam = lam.clamp(0.0, 1.0)
+    U2 = Li.T @ V
+    s1_2, s2_2 = 1.0 - lam, lam
+    Design_U = D @ U2
+    del P, D, D2, Lc, Li, M, V
+    t2 = s / (1.0 + s)                      # Z_1 = I: U3 = U diag(t), U3'U3 = t^2 = s1, U3'Ainv U3 = t^2/s = s2
+    U3 = U * t2.sqrt()[None, :]
+    s1_3, s2_3 = t2, 1.0 - t2
+    H = 50
+    run_parameters = dict(b0=1.0, b1=0.0005, epsilon=1e-2, prop=1.00, h2_divisions=H, save_freq=100, burn=2000,
+                          thin=400, draw_iter=200, simulation=True)
+    priors = dict(k_init=k, resid_Y_prec_shape=2.0, resid_Y_prec_rate=0.1, E_a_prec_shape=2.0, E_a_prec_rate=0.1,
+                  W_prec_shape=2.0, W_prec_rate=0.1, Lambda_df=3.0, delta_1_shape=2.1, delta_1_rate=1 / 20,
+                  delta_2_shape=4.5, delta_2_rate=1.0, b_X_prec=1e-10 * np.eye(b),
+                  h2_priors_factors=np.concatenate([[H - 1.0], np.ones(H - 1)]) / (2.0 * (H - 1)))
+    # --- initial state from the priors (fast_BSFG_sampler_init.R:127-216)
+    g = lambda shape, rate, size: rng.gamma(shape, 1.0, size=size) / rate
+    resid_Y_prec = g(2.0, 0.1, p)
+    Lambda_prec = g(1.5, 1.5, (p, k))
+    delta = np.concatenate([g(2.1, 1 / 20, 1), g(4.5, 1.0, k - 1)])
+    tauh = np.cumprod(delta)
+    Plam = Lambda_prec * tauh[None, :]
+    Lambda = rng.standard_normal((p, k)) * np.sqrt(1.0 / Plam)
+    E_a_prec = g(2.0, 0.1, p)
+    F_h2 = rng.uniform(size=k)
+    F_a = rng.standard_normal((n, k)) * np.sqrt(F_h2)[None, :]
+    F = F_a + rng.standard_normal((n, k)) * np.sqrt(1 - F_h2)[None, :]
+    B = rng.standard_normal((b, p))
+    cpu = lambda t: np.asfortranarray(t.cpu().numpy())
+    data = dict(Y=cpu(Y), X=cpu(X), Z_1=np.eye(n), Z_2=np.zeros((n, 0)))
+    rv = dict(p=p, n=n, r=n, r2=0, b=b, Ainv=cpu(Ainv),
+              invert_aI_bZAZ=dict(U=cpu(U), s=s.cpu().numpy()),
+              invert_aPXA_bDesignDesignT=dict(U=cpu(U2), s1=s1_2.cpu().numpy(), s2=s2_2.cpu().numpy(),
+                                              Design_U=cpu(Design_U)),
+              invert_aZZt_Ainv=dict(U=cpu(U3), s1=s1_3.cpu().numpy(), s2=s2_3.cpu().numpy()))
+    cs = dict(resid_Y_prec=resid_Y_prec, Lambda_prec=Lambda_prec, delta=delta, tauh=tauh, Plam=Plam, Lambda=Lambda,
+              F_h2=F_h2, E_a_prec=E_a_prec, F_a=F_a, F=F, B=B, E_a=None, nrun=0)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+    return data, rv, priors, run_parameters, cs
+
+
+def algorithmic_flops(n, p, k, b=1):
+    """SURVEY.md section 8d W_flop without the fitted-value term (pre-rotation removes it)."""
+    return (k * (k + 1) * n * p + 2 * k * n * p + 2 * n * p * k + 2 * n * p * k + 2 * p * k * k
+            + p * (k ** 3 / 3 + 3 * k * k) + 2 * k * k * n)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline: the oracle on a bounded trait sample (the ONLY place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------
+def cpu_baseline(data, rv, priors, rp, cs, n, p, k, sample_traits, iters=1, seed=1):
+    """Times oracle.gibbs_iteration (reference formulation, incl. U'Y, per-trait k x n GEMMs + chol, dense
+    Z_1 E_a and the full t(E_a) Ainv E_a product) on the first `sample_traits` traits at full n and k, and
+    scales to p traits: per-trait work dominates and is linear in p, so iter/s(p) ~= iter/s(sample) * sample/p.
+    (The p^2 r term of fast_BSFG_sampler.R:245 is under-counted by the sample -- in the reference's favour.)"""
+    from oracle import bsfg_oracle as O, init_oracle as I   # test infrastructure, used here as the timed baseline
+    ps = min(sample_traits, p)
+    sl = slice(0, ps)
+    d = dict(Y=np.ascontiguousarray(data["Y"][:, sl]), X=data["X"], Z_1=data["Z_1"])
+    st = {kk: vv for kk, vv in cs.items() if vv is not None}
+    for nm in ("Lambda", "Lambda_prec", "Plam"):
+        st[nm] = np.asarray(st[nm])[sl, :]
+    for nm in ("resid_Y_prec", "E_a_prec"):
+        st[nm] = np.asarray(st[nm])[sl]
+    st["B"] = np.asarray(st["B"])[:, sl]
+    rng = np.random.default_rng(seed)
+    t_best = None
+    for it in range(iters):
+        v = I.draw_variates(rng, n, ps, k, n, rv["b"] + n, priors)
+        t0 = time.perf_counter()
+        st, _ = O.gibbs_iteration(d, rv, priors, rp, st, it + 1, v, with_update_k=False)
+        dt = time.perf_counter() - t0
+        t_best = dt if t_best is None else min(t_best, dt)
+    try:
+        import threadpoolctl
+        cores = max([x.get("num_threads", 1) for x in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    value = 1.0 / (t_best * (p / ps))
+    return {"value": value, "unit": "iter/s", "cores": int(cores), "kind": "port",
+            "sample": f"oracle.gibbs_iteration (NumPy/OpenBLAS restatement of the Rcpp path, reference formulation) on "
+                      f"{ps} of {p} traits at full n={n}, k={k}: {t_best:.2f} s/iter on the sample, scaled x{p / ps:.1f} "
+                      f"(per-trait work is linear in p); best of {iters}"}
+
+
+# --------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def bcast_obj(obj, src=0):
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the BSFG sweep has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    import sparsefactormixedmodel_b200 as pkg
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    lib = pkg.load()
+    n, p, k = WORKLOADS[args.workload]
+
+    t_setup = time.time()
+    if rank == 0:
+        prob = make_problem(n, p, k, device=f"cuda:{local}")
+    else:
+        prob = None
+    if world > 1:
+        prob = bcast_obj(prob)          # host pickle broadcast: setup only, outside every timed region
+    data, rv, priors, rp, cs = prob
+    nccl_id = None
+    if world > 1:
+        nccl_id = bcast_obj(BSFGSweep.nccl_unique_id() if rank == 0 else None)
+    sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k, seed=20131, rank=rank, world=world, nccl_id=nccl_id)
+    sw.set_state(cs)
+    mode, r1, r2 = sw.mode()
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------
+    sw.sweep(args.warmup)
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    launches0 = lib.bsfg_launch_count()
+    wall0 = time.perf_counter()
+    sw.sweep(args.steps)                      # K iterations, one call, CUDA events inside on the sweep stream
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib.bsfg_launch_count() - launches0
+    clk = clocks.stop()
+    dev_ms, _, phases = sw.timing()
+    dev_ms = max_over_ranks(dev_ms)
+    value = args.steps / (dev_ms * 1e-3)
+    gram_ms = phases["lambda"]               # exactly one dgemm_tn launch (weighted Gram), last timed iteration
+
+    # ---- end to end through the host API, per iteration -----------------------------------
+    def pinned(a):
+        a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+        t = torch.empty(a.shape[::-1], dtype=torch.float64).pin_memory()   # F-order view of a C-order pinned block
+        v = t.numpy().T
+        v[...] = a
+        return v
+    host = sw.get_state(with_E_a=False)
+    full = dict(cs)
+    # trait-indexed members of set_state are given for all p traits and sliced per rank; keep them pinned
+    for nm in ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "B"):
+        full[nm] = pinned(full[nm])
+    e2e_steps = max(2, min(args.steps, 5))
+    h2d = 8 * (3 * sw.pl * k + 2 * n * k + sw.b * sw.pl + 2 * sw.pl + 3 * k)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
+    d2h = 8 * (3 * sw.pl * k + n * k + n * k + k + sw.b * sw.pl + 2 * sw.pl + 2 * k)
+    sw.set_state(full); sw.sweep(1); sw.get_state(with_E_a=False)         # warm the path
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sw.set_state(full)
+        sw.sweep(1)
+        out = sw.get_state(with_E_a=False)
+        full.update({nm: out[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})   # replicated members carry over
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = e2e_steps / e2e_s
+
+    if rank != 0:
+        sw.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak_tf, peak_src = 35.4, "fallback constant (profiles/r01_fp64_peaks.md)"
+    if os.path.exists(FP64_PEAK_FILE):
+        pk = json.load(open(FP64_PEAK_FILE))
+        peak_tf = float(pk.get("dgemm_8192_sustained_tflops", peak_tf))
+        peak_src = "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json; MEASURED_PEAKS.json has no FP64 entry)"
+    gram_flop = k * (k + 1) * n * sw.pl
+    achieved = gram_flop / (gram_ms * 1e-3) * 1e-12 if gram_ms > 0 else None
+    traffic = None
+    if os.path.exists(NCU_SUMMARY_FILE):
+        try:
+            traffic = json.load(open(NCU_SUMMARY_FILE)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "Gibbs iter/sec at n=5000,p=20000,k=100 (1/2/4/8 B200) vs Rcpp host" if args.workload == "C4"
+                  else f"Gibbs iter/sec at n={n},p={p},k={k}",
+        "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: n={n} individuals, p={p} traits, k={k} factors, b=1, Z_1=I, r=n, H=50, "
+                               f"random 3-generation pedigree, traits sharded over {world} rank(s)",
+                   "parallelism": f"trait-shard x{world}", "l2": "inputs larger than L2 (rotated data 2.4 GB/rank-set, "
+                   "Gram operands 1 GB) -- no explicit flush", "formulation": mode,
+                   "diag_identity_residuals": [r1, r2], "update_k": "gated off by i<=200 (uu still drawn)",
+                   "rng": "device Philox4x32-10", "setup_s": round(t_setup, 1), "wall_s_timed_region": round(wall, 3)},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "what": f"{e2e_steps} x [set_state(pinned host current_state) -> bsfg_sweep(1) -> get_state(posterior-sample fields)]; "
+                        "E_a (r x p) is resampled before use and only read back on request"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                     "kernel": "dgemm_tn_kernel<128,128,6> (weighted Gram Q = G'W, M=k(k+1)/2, N=p_local, K=n)",
+                     "flop_per_launch": gram_flop, "ms_per_launch": gram_ms, "peak_source": peak_src,
+                     "dmma_issue_peak_tflops": 37.1},
+        "phases_ms_last_iter": phases,
+        "sweep_achieved_tflops": algorithmic_flops(n, p, k) / world / (dev_ms / args.steps * 1e-3) * 1e-12,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(data, rv, priors, rp, cs, n, p, k, args.cpu_sample_traits)
+    print(json.dumps(line), flush=True)
+    sw.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """--impl reference: the reference formulation on the host cores (the Rcpp path cannot be built here: no
+    R/Rcpp/Armadillo), same config/metric.  Rank 0 only."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    n, p, k = WORKLOADS[args.workload]
+    data, rv, priors, rp, cs = make_problem(n, p, k)
+    steps = max(1, min(args.steps, 3))
+    cb = cpu_baseline(data, rv, priors, rp, cs, n, p, k, args.cpu_sample_traits, iters=steps)
+    line = {"impl": "reference",
+            "metric": "Gibbs iter/sec at n=5000,p=20000,k=100 (1/2/4/8 B200) vs Rcpp host" if args.workload == "C4"
+                      else f"Gibbs iter/sec at n={n},p={p},k={k}",
+            "value": cb["value"], "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: n={n} individuals, p={p} traits, k={k} factors, b=1, Z_1=I, r=n, H=50"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-traits", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,7 +145,7 @@ struct LambdaScratch {
 static void lambda_core(Device& d, LambdaScratch& sc, const DMat& UtF, const DMat& UtY, const double* s,
                         const double* rp, const double* ep, const DMat* UtX, const DMat* B,
                         const double* plam, long plam_sys_stride, long plam_elem_stride, const VarSrc& z,
-                        DMat& Lt) {
+                        DMat& Lt, cudaEvent_t* ev = nullptr /* 3 marks: before Gram GEMM, after it, after chol */) {
     const int n = (int)UtF.rows, k = (int)UtF.cols, p = (int)UtY.cols;
     const int np = k * (k + 1) / 2;
     sc.ensure(n, p, k);
@@ -162,10 +162,13 @@ static void lambda_core(Device& d, LambdaScratch& sc, const DMat& UtF, const DMa
                                                       sc.W.p, sc.W.ld, sc.WY.p, sc.WY.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
+    if (ev) BSFG_CUDA(cudaEventRecord(ev[0], d.st));
     d.gemm(1.0, sc.Gt, sc.W, 0.0, sc.Q);       // Q[pair, j] = sum_i f_ia f_ib w_ij
+    if (ev) BSFG_CUDA(cudaEventRecord(ev[1], d.st));
     d.gemm(1.0, UtF, sc.WY, 0.0, sc.Mn);       // m[a, j]    = sum_i f_ia w_ij y_ij
     launch_chol_solve(d, sc.Q.p, sc.Q.ld, k, p, plam, plam_sys_stride, plam_elem_stride, sc.Mn.p, sc.Mn.ld, z,
                       Lt.p, Lt.ld, nullptr);
+    if (ev) BSFG_CUDA(cudaEventRecord(ev[2], d.st));
 }
 
 static void check_notpd(Device& d, const char* what) {

@@ -155,8 +155,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
     phase_mark(c, 0);
     lambda_core(d, c->lsc, UtF, c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
-                Plamt.p, Plamt.ld, 1, v.zL, Lt);
-    phase_mark(c, 3);
+                Plamt.p, Plamt.ld, 1, v.zL, Lt, c->phase_timing ? &c->ev_phase[1] : nullptr);
     {
         dim3 grid(ceil_div(k, 32), ceil_div(pl, 32)), block(32, 8);
         lt_to_lam_kernel<<<grid, block, 0, d.st>>>(Lt.p, Lt.ld, k, pl, c->rp.p, Lam.p, Lam.ld, Lmsg.p, Lmsg.ld);
@@ -400,14 +399,12 @@ static void finish_timing(bsfg_ctx* c, long long launches_before, int n_iter_tim
     c->last_total_ms = ms;
     c->last_launches = g_launch_counter - launches_before;
     if (c->phase_timing && n_iter_timed_phases > 0) {
-        // phase boundaries recorded: 0 start, 3 after Lambda, 4 means, 5 h2, 6 F_a, 7 F gemms, 8 comm, 9 F solve,
-        // 10 precisions, 11 delta/Plam.  (Lambda's own sub-phases are reported by bench.py's per-kernel timing.)
-        const int marks[] = {0, 3, 4, 5, 6, 7, 8, 9, 10, 11};
-        const int phase_of[] = {PH_LAMBDA_GRAM, PH_MEANS, PH_H2, PH_FA, PH_F_GEMM, PH_F_COMM, PH_F_SOLVE, PH_PREC, PH_DELTA};
-        for (int q = 0; q + 1 < 10; q++) {
+        // marks 0..11 bracket the 11 phases PH_LAMBDA_PREP .. PH_DELTA in order; PH_LAMBDA_GRAM is exactly the
+        // weighted-Gram dgemm_tn launch (the kernel bench.py reports the roofline for).
+        for (int q = 0; q < 11; q++) {
             float t = 0;
-            BSFG_CUDA(cudaEventElapsedTime(&t, c->ev_phase[marks[q]], c->ev_phase[marks[q + 1]]));
-            c->phase_ms[phase_of[q]] = t;
+            BSFG_CUDA(cudaEventElapsedTime(&t, c->ev_phase[q], c->ev_phase[q + 1]));
+            c->phase_ms[q] = t;
         }
     }
     check_notpd(d, "bsfg_sweep");
