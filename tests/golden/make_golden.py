@@ -1,0 +1,110 @@
+"""Generates tests/golden/*.npz -- run ONCE in the build container (it reads /root/reference, which does
+not exist on the GPU box; nothing in tests/, smoke() or bench.py reads /root/reference at run time).
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors, so these fixtures pin the next best thing:
+the reference's OWN INPUT FIXTURES (`R_BSFG/Sim_1/setup.mat`, `R_BSFG/Example_simulation/setup.mat`,
+`.../Ayroles_et_al_Competitive_fitness/setup.mat`) pushed through the init restatement
+(fast_BSFG_sampler_init.R:63-345, `lists="reference"` = the GSVD route the R code takes) and two Gibbs
+iterations of the oracle (`oracle/bsfg_oracle.py`, restating BSFG_functions_c.cpp) under seeded, stored
+variates.  Each file holds every input of the `_c` boundary (data, the three diagonalisation lists, priors
+literals, state, variates) and the outputs, so
+
+  * `-m "not gpu"` tests re-run the oracle from the stored inputs (pins it against drift: NumPy/LAPACK
+    version, later edits) and cross-check it against the R-twin transcription on the same inputs;
+  * `-m gpu` tests push the same stored inputs through the C ABI and compare with the stored outputs.
+
+Fixtures are sub-sampled to stay small (whole half-sib families / whole lines are kept so A stays a valid
+relationship matrix); the Ayroles panel has missing phenotypes, which the device sweep does not handle yet
+(SURVEY.md section 8f-3): its NaNs are replaced by the trait mean here and the case serves as the
+rectangular-Z_1 (n=200 individuals, r=40 lines, b=2) fixture.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.io as sio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import bsfg_oracle as O, init_oracle as I  # noqa: E402
+
+REF = "/root/reference/R_BSFG"
+CASES = {
+    # name: (path, individuals kept, traits kept, k)
+    "sim1": (f"{REF}/Sim_1/setup.mat", 60, 40, 6),
+    "example": (f"{REF}/Example_simulation/setup.mat", 64, 36, 5),
+    "ayroles": (f"{REF}/Runcie_Mukherjee_analyses/Ayroles_et_al_Competitive_fitness/setup.mat", 200, 48, 7),
+}
+
+
+def load_setup(name, path, n_keep, p_keep):
+    m = sio.loadmat(path)
+    Y = np.asarray(m["Y"], dtype=np.float64)
+    n = Y.shape[0]
+    Z_1 = np.asarray(m["Z_1"], dtype=np.float64)
+    if Z_1.shape[0] != n:
+        Z_1 = Z_1.T
+    X = np.asarray(m["X"], dtype=np.float64)
+    if X.shape[0] != n:
+        X = X.T
+    A = np.asarray(m["A"], dtype=np.float64)
+    if name == "ayroles":
+        mu = np.nanmean(Y, axis=0)
+        Y = np.where(np.isnan(Y), mu[None, :], Y)
+        # keep traits with the fewest imputed values first -> deterministic choice
+        keep = np.arange(p_keep)
+        return dict(Y=Y[:, keep], X=X, Z_1=Z_1, A=A, simulation=False)
+    # simulations: Z_1 = I, individuals are ordered by family -> the first n_keep are whole families
+    assert np.array_equal(Z_1, np.eye(n))
+    return dict(Y=Y[:n_keep, :p_keep], X=X[:n_keep], Z_1=np.eye(n_keep), A=A[:n_keep, :n_keep], simulation=True)
+
+
+def flatten(prefix, d, out):
+    for k, v in d.items():
+        if isinstance(v, dict):
+            flatten(f"{prefix}{k}.", v, out)
+        elif v is None:
+            continue
+        else:
+            out[f"{prefix}{k}"] = np.asarray(v)
+
+
+def main():
+    for name, (path, n_keep, p_keep, k) in CASES.items():
+        setup = load_setup(name, path, n_keep, p_keep)
+        pri = I.default_priors(k_init=k)
+        rp = I.default_run_parameters()
+        st = I.sampler_init(setup, pri, rp, seed=101, lists="reference")
+        d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+        n, p = d["Y"].shape
+        r, b = d["Z_1"].shape[1], d["X"].shape[1]
+        rng = np.random.default_rng(202)
+        out = {}
+        flatten("data.", {kk: d[kk] for kk in ("Y", "X", "Z_1")}, out)
+        flatten("rv.", {kk: rv[kk] for kk in ("Ainv", "invert_aI_bZAZ", "invert_aPXA_bDesignDesignT", "invert_aZZt_Ainv")}, out)
+        flatten("state0.", {kk: vv for kk, vv in cs.items() if kk not in ("W", "W_prec")}, out)
+        cur = cs
+        for it in (1, 2):
+            v = I.draw_variates(rng, n, p, k, r, b + r, pri)
+            nxt, aux = O.gibbs_iteration(d, rv, pri, rp, cur, it, v)
+            flatten(f"variates{it}.", v, out)
+            flatten(f"state{it}.", {kk: vv for kk, vv in nxt.items() if kk not in ("W", "W_prec")}, out)
+            flatten(f"aux{it}.", {kk: vv for kk, vv in aux.items() if kk.endswith("_rate")}, out)
+            cur = nxt
+        # the export that is off the active sweep (fast_BSFG_sampler.R:198-199): stored separately
+        u = rng.uniform(size=p)
+        prec = O.sample_prec_discrete_conditional_c(d["Y"], rp["h2_divisions"], pri["h2_priors_factors"],
+                                                    rv["invert_aI_bZAZ"], cs["resid_Y_prec"], u)
+        out["prec_cond.u"] = u
+        out["prec_cond.Prec"] = prec
+        out["meta.k"] = np.int64(k)
+        dst = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(dst, **out)
+        print(name, f"n={n} p={p} r={r} b={b} k={k}", f"{os.path.getsize(dst) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""Trait-sharded sweep check, one process per GPU.  Launched by
+tests/test_multi_gpu.py (and by hand under gpurun) as
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P tests/multi_gpu_check.py
+
+Checks, on every rank:
+  1. three injected-variate iterations: this rank's trait shard of the device state matches the oracle's
+     full-problem Gibbs iteration to 1e-9 (the oracle is the checker; it runs on every rank, sizes are small);
+  2. free-running Philox sweep: the replicated members (F, F_a, F_h2, delta, tauh) are BIT-identical on all
+     ranks, and the N-rank chain equals the 1-rank chain (run on rank 0) to 1e-10 -- the Philox element index
+     of every trait-indexed draw is the global trait index, so sharding must not change the chain beyond the
+     summation order of the allreduce.
+Prints "multi_gpu_check ok world=N" from rank 0 and exits 0; any mismatch raises.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from conftest import relerr, rowwise_relerr
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    def bcast(obj):
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    n, p, k = 96, 131, 8            # p not divisible by the world size: ragged shards
+    setup = I.make_synthetic(n, p, 4, pedigree="random", seed=17)
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=5, lists="stable")
+    d, rv, cs = st["data_matrices"], st["run_variables"], st["current_state"]
+
+    nccl_id = bcast(BSFGSweep.nccl_unique_id() if rank == 0 else None)
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, seed=99, rank=rank, world=world, nccl_id=nccl_id)
+    lo, hi = sw.lo, sw.hi
+    tol = 1e-9
+    rng = np.random.default_rng(31)
+    ora = cs
+    for it in range(1, 4):
+        v = I.draw_variates(rng, n, p, k, n, 1 + n, pri)
+        sw.set_state(ora)
+        ora, _ = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+        sw.sweep_injected(v)
+        dev = sw.get_state()
+        assert rowwise_relerr(dev["Lambda"], ora["Lambda"][lo:hi]) < tol
+        assert rowwise_relerr(dev["F"], ora["F"]) < tol
+        assert rowwise_relerr(dev["F_a"].T, ora["F_a"].T) < tol
+        assert np.array_equal(dev["F_h2"], np.asarray(ora["F_h2"]).ravel())
+        assert relerr(dev["B"], ora["B"].reshape(1, p)[:, lo:hi]) < tol
+        assert rowwise_relerr(dev["E_a"].T, ora["E_a"][:, lo:hi].T) < tol
+        assert relerr(dev["Lambda_prec"], ora["Lambda_prec"][lo:hi]) < tol
+        assert relerr(dev["resid_Y_prec"], ora["resid_Y_prec"][lo:hi]) < tol
+        assert relerr(dev["E_a_prec"], ora["E_a_prec"][lo:hi]) < tol
+        assert relerr(dev["delta"], ora["delta"]) < tol
+        assert relerr(dev["Plam"], ora["Plam"][lo:hi]) < tol * 10
+
+    # free-running Philox chain, N ranks vs 1 rank
+    sw.set_state(cs)
+    sw.sweep(6)
+    got = sw.get_state(with_E_a=False)
+    for name in ("F", "F_a", "F_h2", "delta", "tauh"):
+        t = torch.from_numpy(np.ascontiguousarray(got[name])).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(t, ref), f"replicated member {name} differs between rank {rank} and rank 0"
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {nm: got[nm] for nm in ("Lambda", "resid_Y_prec", "E_a_prec", "Lambda_prec")})
+    sw.close()
+    if rank == 0:
+        one = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, seed=99)
+        one.set_state(cs)
+        one.sweep(6)
+        ref = one.get_state(with_E_a=False)
+        one.close()
+        for nm in ("Lambda", "resid_Y_prec", "E_a_prec", "Lambda_prec"):
+            full = np.concatenate([g[nm] for g in gathered], axis=0)
+            assert relerr(full, ref[nm]) < 1e-10, (nm, relerr(full, ref[nm]))
+        for nm in ("F", "F_a", "delta"):
+            assert relerr(got[nm], ref[nm]) < 1e-10, (nm, relerr(got[nm], ref[nm]))
+        assert np.array_equal(got["F_h2"], ref["F_h2"])
+        print(f"multi_gpu_check ok world={world}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,339 @@
+"""CPU checks of the oracle itself (no GPU, no library compute calls).
+
+The reference has no tests and cannot be run here (no R/Rcpp/Armadillo), so the oracle is pinned by
+  (1) the reference author's twin convention (README.md:37-38): the restatement of the `_c` functions
+      (oracle/bsfg_oracle.py, following BSFG_functions_c.cpp) must agree with the independent restatement of
+      the R twins (oracle/bsfg_oracle_rtwin.py, following BSFG_functions.R:23-269) under shared variates;
+  (2) closed-form identities: every Gaussian conditional recomputed by dense n x n algebra from the model
+      statement, without the diagonalisation lists;
+  (3) the committed golden fixtures built from the reference's own setup.mat inputs
+      (tests/golden/make_golden.py): re-running the oracle on the stored inputs reproduces the stored outputs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr, rowwise_relerr
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ("sim1", "example", "ayroles")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLD, f"{name}.npz"))
+    out = {}
+    for key in z.files:
+        cur = out
+        parts = key.split(".")
+        for part in parts[:-1]:
+            cur = cur.setdefault(part, {})
+        val = z[key]
+        cur[parts[-1]] = val.item() if val.ndim == 0 else val
+    return out
+
+
+def golden_problem(name):
+    from oracle import init_oracle as I
+    g = load_golden(name)
+    k = int(g["meta"]["k"])
+    pri = I.default_priors(k_init=k)
+    b = g["data"]["X"].shape[1]
+    pri["b_X_prec"] = 1e-10 * np.eye(b)
+    rp = I.default_run_parameters()
+    rv = dict(g["rv"])
+    n, p = g["data"]["Y"].shape
+    rv.update(n=n, p=p, r=g["data"]["Z_1"].shape[1], b=b)
+    return g, g["data"], rv, pri, rp
+
+
+STATE_FIELDS = ("Lambda", "F", "F_a", "F_h2", "B", "E_a", "Lambda_prec", "resid_Y_prec", "E_a_prec", "delta",
+                "tauh", "Plam")
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) golden fixtures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden(name):
+    from oracle import bsfg_oracle as O
+    g, d, rv, pri, rp = golden_problem(name)
+    cur = g["state0"]
+    for it in (1, 2):
+        nxt, aux = O.gibbs_iteration(d, rv, pri, rp, cur, it, g[f"variates{it}"])
+        want = g[f"state{it}"]
+        for f in STATE_FIELDS:
+            assert relerr(np.asarray(nxt[f]).ravel(), np.asarray(want[f]).ravel()) < 1e-10, (name, it, f)
+        for f, val in g[f"aux{it}"].items():
+            assert relerr(aux[f], val) < 1e-10, (name, it, f)
+        cur = nxt
+    prec = O.sample_prec_discrete_conditional_c(d["Y"], rp["h2_divisions"], pri["h2_priors_factors"],
+                                                rv["invert_aI_bZAZ"], g["state0"]["resid_Y_prec"], g["prec_cond"]["u"])
+    fin = np.isfinite(g["prec_cond"]["Prec"])
+    assert np.array_equal(fin, np.isfinite(prec))
+    assert relerr(prec[fin], g["prec_cond"]["Prec"][fin]) < 1e-10
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_lists_satisfy_their_contract(name):
+    """inv(a P + b D'D) = U diag(1/(a s1 + b s2)) U' (BSFG_functions_c.cpp:52-54) and the aI+bZAZ' analogue
+    (cpp:98-99) on the lists the reference's init route produced for the reference's own fixtures."""
+    g, d, rv, pri, rp = golden_problem(name)
+    X, Z = d["X"], d["Z_1"]
+    b = X.shape[1]
+    r = Z.shape[1]
+    A = np.linalg.inv(rv["Ainv"])
+    l1, l2, l3 = rv["invert_aI_bZAZ"], rv["invert_aPXA_bDesignDesignT"], rv["invert_aZZt_Ainv"]
+    a_, b_ = 0.7, 1.9
+    n = Z.shape[0]
+    M = a_ * np.eye(n) + b_ * Z @ A @ Z.T
+    got = (l1["U"] / (l1["s"] + a_ / b_)[None, :]) @ l1["U"].T / b_
+    assert relerr(got, np.linalg.inv(M)) < 1e-8
+    D = np.column_stack([X, Z])
+    P = np.zeros((b + r, b + r)); P[:b, :b] = 1e-10 * np.eye(b); P[b:, b:] = rv["Ainv"]
+    got = (l2["U"] / (a_ * l2["s1"] + b_ * l2["s2"])[None, :]) @ l2["U"].T
+    assert relerr(got, np.linalg.inv(a_ * P + b_ * D.T @ D)) < 1e-6    # reference init is only ~1e-10/cond accurate
+    assert relerr(l2["Design_U"], D @ l2["U"]) < 1e-12
+    got = (l3["U"] / (a_ * l3["s1"] + b_ * l3["s2"])[None, :]) @ l3["U"].T
+    assert relerr(got, np.linalg.inv(a_ * Z.T @ Z + b_ * rv["Ainv"])) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) `_c` restatement == R-twin restatement
+# ------------------------------------------------------------------------------------------------
+def _twin_inputs(name):
+    g, d, rv, pri, rp = golden_problem(name)
+    return g, d, rv, pri, rp, g["state0"], g["variates1"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_twins_agree_on_reference_fixtures(name):
+    from oracle import bsfg_oracle as O, bsfg_oracle_rtwin as R
+    g, d, rv, pri, rp, st, v = _twin_inputs(name)
+    Y, X, Z = d["Y"], d["X"], d["Z_1"]
+    H = rp["h2_divisions"]
+    tol = 1e-9
+    Yt = Y - X @ st["B"]
+    a = O.sample_Lambda_c(Yt, st["F"], st["resid_Y_prec"], st["E_a_prec"], st["Plam"], rv["invert_aI_bZAZ"], v["z_Lambda"])
+    b = R.sample_Lambda(Yt, st["F"], st["resid_Y_prec"], st["E_a_prec"], st["Plam"], rv["invert_aI_bZAZ"], v["z_Lambda"])
+    assert rowwise_relerr(a, b) < tol
+    Lam = a
+    Yt = Y - st["F"] @ Lam.T
+    a = O.sample_means_c(Yt, st["resid_Y_prec"], st["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    b = R.sample_means(Yt, st["resid_Y_prec"], st["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    assert relerr(a, b) < tol
+    a = O.sample_h2s_discrete_c(st["F"], H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"])
+    b = R.sample_h2s_discrete(st["F"], H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"])
+    assert np.array_equal(a, b)
+    h2 = a
+    a = O.sample_F_a_c(st["F"], Z, h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
+    b = R.sample_F_a(st["F"], Z, h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
+    assert relerr(a, b) < tol
+    Fa = a
+    Yt = Y - X @ st["B"] - Z @ st["E_a"]
+    a = O.sample_factors_scores_c(Yt, Z, Lam, st["resid_Y_prec"], Fa, h2, v["z_F"])
+    b = R.sample_factors_scores(Yt, Z, Lam, st["resid_Y_prec"], Fa, h2, v["z_F"])
+    assert rowwise_relerr(a, b) < 1e-8
+    # the off-sweep export: twins agree for even n (the integer n/2 of cpp:274 only bites for odd n)
+    n = Y.shape[0]
+    u = g["prec_cond"]["u"]
+    a = O.sample_prec_discrete_conditional_c(Y, H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], st["resid_Y_prec"], u)
+    b = R.sample_prec_discrete_conditional(Y, H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], st["resid_Y_prec"], u)
+    assert n % 2 == 0
+    fin = np.isfinite(a)
+    assert np.array_equal(fin, np.isfinite(b)) and relerr(a[fin], b[fin]) < tol
+
+
+def test_twins_differ_exactly_where_the_reference_does():
+    """cpp:274 integer n/2 vs BSFG_functions.R:99 real n/2 (odd n); cpp:326 `> 10000` vs R:229 `== Inf`."""
+    from oracle import bsfg_oracle as O, bsfg_oracle_rtwin as R, init_oracle as I
+    n, p = 9, 6
+    rng = np.random.default_rng(0)
+    A = I.halfsib_A(3, 3)
+    s, U = np.linalg.eigh(A)
+    lst = {"U": U, "s": s}
+    Y = rng.standard_normal((n, p))
+    rp_ = rng.gamma(2.0, 1.0, p) + 0.5
+    pri = np.ones(10) / 10
+    lo = O.prec_log_ps(Y, 10, pri, lst, rp_)
+    # the only column the integer division touches is h2 = 0: difference = (n/2 - n//2) log(1/rp)
+    Yt_u = Y.T @ U
+    want0 = np.sum(O.dnorm_std_log(Y.T * np.sqrt(rp_)[:, None]), axis=1) - (n // 2) * np.log(1 / rp_) + np.log(pri[0])
+    assert relerr(lo[:, 0], want0) < 1e-13
+    real0 = want0 + (n // 2 - n / 2) * np.log(1 / rp_)
+    assert np.max(np.abs(real0 - lo[:, 0])) > 1e-3
+    del Yt_u
+    # F_a: h2 so close to 1 that tau_e > 10000 but finite -> C++ copies F, R samples
+    F = rng.standard_normal((n, 2))
+    h2 = np.array([1 - 1e-5, 0.5])
+    l3 = {"U": U, "s1": np.ones(n) * 0.5, "s2": np.ones(n) * 0.5}
+    z = rng.standard_normal((n, 2))
+    c = O.sample_F_a_c(F, np.eye(n), h2, l3, z)
+    r_ = R.sample_F_a(F, np.eye(n), h2, l3, z)
+    assert np.array_equal(c[:, 0], F[:, 0]) and not np.allclose(r_[:, 0], F[:, 0])
+    assert relerr(c[:, 1], r_[:, 1]) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) closed-form identities (dense algebra straight from the model statement)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dense_case():
+    from oracle import init_oracle as I
+    n, p, k = 30, 7, 4
+    setup = I.make_synthetic(n, p, 2, pedigree="random", seed=3, b=2)
+    pri = I.default_priors(k_init=k)
+    st = I.sampler_init(setup, pri, I.default_run_parameters(), seed=4, lists="stable")
+    return st, np.asarray(setup["A"])
+
+
+def test_sample_Lambda_is_the_dense_gaussian_conditional(dense_case):
+    """Lambda_j | . ~ N(Q^-1 F' S_j^-1 y_j, Q^-1), Q = F' S_j^-1 F + diag(Plam_j), S_j = ZAZ'/ep_j + I/rp_j
+    (the marginal model in the comment block of cpp:93-99)."""
+    from oracle import bsfg_oracle as O
+    st, A = dense_case
+    d, rv, cs = st["data_matrices"], st["run_variables"], st["current_state"]
+    Y, Z = d["Y"], d["Z_1"]
+    n, p = Y.shape
+    k = cs["F"].shape[1]
+    F = cs["F"]
+    zero = O.sample_Lambda_c(Y, F, cs["resid_Y_prec"], cs["E_a_prec"], cs["Plam"], rv["invert_aI_bZAZ"], np.zeros((k, p)))
+    cols = [O.sample_Lambda_c(Y, F, cs["resid_Y_prec"], cs["E_a_prec"], cs["Plam"], rv["invert_aI_bZAZ"],
+                              np.tile(np.eye(k)[:, [c]], (1, p))) - zero for c in range(k)]
+    for j in range(p):
+        S = Z @ A @ Z.T / cs["E_a_prec"][j] + np.eye(n) / cs["resid_Y_prec"][j]
+        Si = np.linalg.inv(S)
+        Q = F.T @ Si @ F + np.diag(cs["Plam"][j])
+        mean = np.linalg.solve(Q, F.T @ Si @ Y[:, j])
+        assert relerr(zero[j], mean) < 1e-8
+        Rinv = np.column_stack([c[j] for c in cols])           # columns of R^-1 (R'R = Q)
+        assert relerr(Rinv @ Rinv.T, np.linalg.inv(Q)) < 1e-8
+
+
+def test_sample_means_is_the_dense_gaussian_conditional(dense_case):
+    from oracle import bsfg_oracle as O
+    st, A = dense_case
+    d, rv, cs, pri = st["data_matrices"], st["run_variables"], st["current_state"], st["priors"]
+    Y, X, Z = d["Y"], d["X"], d["Z_1"]
+    b, r = X.shape[1], Z.shape[1]
+    D = np.column_stack([X, Z])
+    P = np.zeros((b + r, b + r)); P[:b, :b] = pri["b_X_prec"]; P[b:, b:] = rv["Ainv"]
+    got = O.sample_means_c(Y, cs["resid_Y_prec"], cs["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], np.zeros((b + r, Y.shape[1])))
+    for j in range(Y.shape[1]):
+        C = P * cs["E_a_prec"][j] + D.T @ D * cs["resid_Y_prec"][j]
+        # fixed-effect rows carry prior precision b_X_prec * E_a_prec_j (cpp:52-54 applies `a` to the whole block)
+        want = np.linalg.solve(C, D.T @ Y[:, j] * cs["resid_Y_prec"][j])
+        assert relerr(got[:, j], want) < 1e-7
+
+
+def test_sample_F_a_and_factor_scores_dense(dense_case):
+    from oracle import bsfg_oracle as O
+    st, A = dense_case
+    d, rv, cs = st["data_matrices"], st["run_variables"], st["current_state"]
+    Y, Z = d["Y"], d["Z_1"]
+    n, p = Y.shape
+    F, k = cs["F"], cs["F"].shape[1]
+    h2 = np.array([0.0, 0.3, 0.62, 0.98])
+    got = O.sample_F_a_c(F, Z, h2, rv["invert_aZZt_Ainv"], np.zeros((Z.shape[1], k)))
+    assert np.all(got[:, 0] == 0)
+    for j in range(1, k):
+        te, tu = 1 / (1 - h2[j]), 1 / h2[j]
+        want = np.linalg.solve(Z.T @ Z * te + rv["Ainv"] * tu, Z.T @ F[:, j] * te)
+        assert relerr(got[:, j], want) < 1e-8
+    Lam, rp_ = cs["Lambda"], cs["resid_Y_prec"]
+    Fa = got
+    gotF = O.sample_factors_scores_c(Y, Z, Lam, rp_, Fa, h2, np.zeros((n, k)))
+    te = 1 / (1 - h2)
+    Q = Lam.T @ (Lam * rp_[:, None]) + np.diag(te)
+    want = np.linalg.solve(Q, (Y @ (Lam * rp_[:, None]) + (Z @ Fa) * te[None, :]).T).T
+    assert rowwise_relerr(gotF, want) < 1e-8
+    # px variant = same with tau_e supplied; px_factor is ignored (cpp:166-193)
+    gotP = O.sample_px_factors_scores_c(Y, Z, Lam, rp_, Fa, te, np.full(k, 7.0), np.zeros((n, k)))
+    assert np.array_equal(gotP, gotF)
+
+
+def test_h2_grid_log_posteriors_are_mvn_densities(dense_case):
+    """log_ps[j,i] - log prior_i = log N(F_j; 0, h2 ZAZ' + (1-h2) I)   (cpp:211-226)."""
+    from oracle import bsfg_oracle as O
+    from scipy.stats import multivariate_normal
+    st, A = dense_case
+    d, rv, cs, pri = st["data_matrices"], st["run_variables"], st["current_state"], st["priors"]
+    Z = d["Z_1"]
+    n = Z.shape[0]
+    H = 10
+    prior = np.linspace(1, 2, H) / 15.0
+    lp = O.h2s_log_ps(cs["F"], H, prior, rv["invert_aI_bZAZ"])
+    for i in range(H):
+        h2 = i / H
+        cov = h2 * Z @ A @ Z.T + (1 - h2) * np.eye(n)
+        for j in range(cs["F"].shape[1]):
+            want = multivariate_normal(mean=np.zeros(n), cov=cov).logpdf(cs["F"][:, j]) + np.log(prior[i])
+            assert abs(lp[j, i] - want) < 1e-8 * max(1.0, abs(want))
+    # draw: count of cumsum edges below u
+    u = np.array([0.0, 0.5, 0.999999, 1.0])
+    got = O.sample_h2s_discrete_c(cs["F"], H, prior, rv["invert_aI_bZAZ"], u)
+    assert got[0] == 0.0 and np.all((got * H) % 1 == 0) and np.all(got <= 1.0)
+
+
+def test_sample_delta_follows_the_R_loop():
+    """BSFG_functions.R:296 `for(h in 2:(k-1))`: delta_k is never resampled; k = 2 visits h = 2, 1."""
+    from oracle import bsfg_oracle as O
+    assert O.delta_loop_indices(5) == [2, 3, 4]
+    assert O.delta_loop_indices(3) == [2]
+    assert O.delta_loop_indices(2) == [2, 1]
+    rng = np.random.default_rng(1)
+    p, k = 11, 5
+    LP = rng.gamma(1.5, 1.0, (p, k)); L2 = rng.standard_normal((p, k)) ** 2
+    delta = rng.gamma(3.0, 1.0, k); tauh = np.cumprod(delta)
+    g = rng.gamma(5.0, 1.0, k)
+    new, shapes, rates = O.sample_delta(delta, tauh, LP, 2.1, 0.05, 4.5, 1.0, L2, g)
+    assert new[-1] == delta[-1] and len(shapes) == k - 1
+    c = np.sum(LP * L2, axis=0)
+    assert abs(rates[0] - (0.05 + 0.5 / delta[0] * np.sum(tauh * c))) < 1e-12 * rates[0]
+    assert shapes[0] == 2.1 + 0.5 * p * k and shapes[1] == 4.5 + 0.5 * p * (k - 1)
+    d1 = delta.copy(); d1[0] = g[0] / rates[0]
+    t1 = np.cumprod(d1)
+    assert abs(rates[1] - (1.0 + 0.5 / d1[1] * np.sum(t1[1:] * c[1:]))) < 1e-12 * rates[1]
+
+
+def test_update_k_arms_follow_R():
+    """BSFG_functions.R:311-372: gate `uu < prob && i > 200`; add arm appends in R's draw order; drop arm folds
+    delta[red+1] *= delta[red] except for the last column and recomputes tauh/Plam."""
+    from oracle import bsfg_oracle as O
+    rng = np.random.default_rng(2)
+    n, p, k, r = 8, 12, 4, 8
+    F = rng.standard_normal((n, k)); Lam = rng.standard_normal((p, k)) + 2.0
+    Fa = rng.standard_normal((r, k)); h2 = rng.uniform(size=k)
+    LP = rng.gamma(2, 1, (p, k)); delta = rng.gamma(3, 1, k); tauh = np.cumprod(delta); Plam = LP * tauh
+    v = dict(u_k=0.0, k_g_lp=rng.gamma(1.5, 1, p), k_g_delta=2.5, k_z_lambda=rng.standard_normal(p), k_u_h2=0.37,
+             k_z_Fa=rng.standard_normal(r), k_z_F=rng.standard_normal(n))
+    args = (3.0, 4.5, 1.0, 1.0, 0.0005)
+    same = O.update_k(F, Lam, Fa, h2, LP, Plam, delta, tauh, np.eye(n), *args, 200, 1e-2, 1.0, v)
+    assert same["F"].shape[1] == k                                   # i > 200 gate
+    add = O.update_k(F, Lam, Fa, h2, LP, Plam, delta, tauh, np.eye(n), *args, 201, 1e-2, 1.0, v)
+    assert add["F"].shape[1] == k + 1
+    assert np.allclose(add["Lambda_prec"][:, k], v["k_g_lp"] / 1.5)
+    assert np.isclose(add["delta"][k], 2.5) and np.isclose(add["tauh"][k], tauh[-1] * 2.5)
+    assert np.allclose(add["Lambda"][:, k], v["k_z_lambda"] / np.sqrt(add["Plam"][:, k]))
+    assert np.allclose(add["F_a"][:, k], v["k_z_Fa"] * np.sqrt(0.37))
+    assert np.allclose(add["F"][:, k], add["F_a"][:, k] + v["k_z_F"] * np.sqrt(1 - 0.37))
+    Lam2 = Lam.copy(); Lam2[:, 1] = 1e-4; Lam2[:, 3] = 1e-5          # columns 2 and 4 (1-based) redundant
+    drop = O.update_k(F, Lam2, Fa, h2, LP, Plam, delta, tauh, np.eye(n), *args, 300, 1e-2, 1.0, v)
+    assert drop["F"].shape[1] == 2
+    dd = delta.copy(); dd[2] *= dd[1]                                  # red = 2 folds into 3; red = 4 = k skipped
+    assert np.allclose(drop["delta"], dd[[0, 2]]) and np.allclose(drop["tauh"], np.cumprod(dd[[0, 2]]))
+    assert np.allclose(drop["Plam"], LP[:, [0, 2]] * drop["tauh"])
+    nope = O.update_k(F, Lam2, Fa, h2, LP, Plam, delta, tauh, np.eye(n), *args, 300, 1e-2, 1.0, dict(v, u_k=0.99))
+    assert nope["F"].shape[1] == k                                   # uu >= prob
+
+
+def test_gsvd_2_c_contract():
+    """GSVD_2_c (cpp:27-40): A'A = X C^2 X', B'B = X S^2 X', C^2 + S^2 = I."""
+    from oracle import bsfg_oracle as O
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((6, 6)); B = rng.standard_normal((6, 6)) + 3 * np.eye(6)
+    res = O.GSVD_2_c(A, B)
+    X, C, S = res["X"], res["C"], res["S"]
+    assert relerr(X @ C @ C @ X.T, A.T @ A) < 1e-10
+    assert relerr(X @ S @ S @ X.T, B.T @ B) < 1e-10
+    assert relerr(C @ C + S @ S, np.eye(6)) < 1e-12
