@@ -343,10 +343,16 @@ def run_ours(args):
     sw.set_state(full); sw.sweep(1); sw.get_state(with_E_a=False)         # warm the path
     barrier()
     t0 = time.perf_counter()
+    e2e_parts = [0.0, 0.0, 0.0]
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         sw.set_state(full)
+        tb = time.perf_counter()
         sw.sweep(1)
+        tc = time.perf_counter()
         out = sw.get_state(with_E_a=False)
+        td = time.perf_counter()
+        e2e_parts[0] += tb - ta; e2e_parts[1] += tc - tb; e2e_parts[2] += td - tc
         full.update({nm: out[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})   # replicated members carry over
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -386,7 +392,9 @@ def run_ours(args):
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "what": f"{e2e_steps} x [set_state(pinned host current_state) -> bsfg_sweep(1) -> get_state(posterior-sample fields)]; "
-                        "E_a (r x p) is resampled before use and only read back on request"},
+                        "E_a (r x p) is resampled before use and only read back on request",
+                "ms_per_step_parts": {"set_state_h2d": 1e3 * e2e_parts[0] / e2e_steps, "sweep": 1e3 * e2e_parts[1] / e2e_steps,
+                                      "get_state_d2h": 1e3 * e2e_parts[2] / e2e_steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,

@@ -3,7 +3,9 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
+#include "chol_blocked.cuh"
 #include <algorithm>
+#include <map>
 
 namespace bsfg {
 static thread_local char g_err[1024] = "";

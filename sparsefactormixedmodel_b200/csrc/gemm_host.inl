@@ -62,14 +62,27 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     g.group_n = 8;
     const int tiles = g.tiles_m * g.tiles_n;
     const int ktiles = ceil_div(K, GEMM_BK);
+    // split-K, chosen by a small cost model (microseconds): waves of one CTA per SM, 2.1 us per 128x128x16 k-tile at
+    // the DMMA rate of one SM, ~8 us of pipeline fill + epilogue per CTA, and for s > 1 the extra pass over the
+    // s x M x N partials plus the reduce launch.  E.g. M=k=100, N=p=20000, K=5000 (157 tiles = 2 waves at 53%):
+    // s=7 -> 870 us instead of 1330; Lambda'Lmsg (1 tile, K=20000): s=148.  Partials are summed in a fixed order by
+    // splitk_reduce_kernel, so results stay bit-reproducible.
     int splits = 1;
-    if (ws && tiles < sm_count) {
-        splits = sm_count / tiles;                    // fill the machine once
-        const int max_by_k = ktiles / 8 > 0 ? ktiles / 8 : 1;   // keep >= 8 k-tiles per split
-        if (splits > max_by_k) splits = max_by_k;
-        const size_t per = (size_t)M * (size_t)N;
-        if ((size_t)splits * per > ws_doubles) splits = (int)(ws_doubles / per);
-        if (splits < 1) splits = 1;
+    if (ws) {
+        const double per = (double)M * (double)N;
+        auto cost = [&](int s) {
+            const long ctas = (long)tiles * s;
+            const double waves = (double)((ctas + sm_count - 1) / sm_count);
+            double c = waves * (ceil_div(ktiles, s) * 2.1 + 8.0);
+            if (s > 1) c += 16e-6 * s * per / 5.0 + 5.0;
+            return c;
+        };
+        double best = cost(1);
+        const int smax = std::min(std::min(ktiles / 4, 2 * sm_count), (int)std::min<double>(1e9, (double)ws_doubles / per));
+        for (int s = 2; s <= smax; s++) {
+            const double c = cost(s);
+            if (c < 0.95 * best) { best = c; splits = s; }
+        }
     }
     g.ktiles_per_split = ceil_div(ktiles, splits);
     splits = ceil_div(ktiles, g.ktiles_per_split);    // no empty splits

@@ -125,116 +125,6 @@ __global__ void lambda_weights_kernel(const double* __restrict__ UtY, long ldy, 
     }
 }
 
-// ------------------------------------------------------------------------------------
-// Batched k x k Cholesky + the three triangular solves of cpp:124-130, one CTA per system.
-//   Q_j   = unpack(Qp[:, j]) + diag(dadd_j)        (packed lower, pair = a(a+1)/2 + b)
-//   L L'  = Q_j                                     (L = t(chol(Qlam)), cpp:124)
-//   out_j = L'^-1 (L^-1 m_j + z_j)                 (= mlam + ylam, cpp:125-130)
-// Shared memory: packed L (k(k+1)/2 doubles) + 2k doubles.  If Lout != null the factor is also
-// written (packed) -- used by sample_factors_scores for its single k x k system.
-// ------------------------------------------------------------------------------------
-template <int KT>   // KT = ceil(k/32) entries per lane in the solve phase
-__global__ void __launch_bounds__(128)
-chol_solve_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys,
-                  const double* __restrict__ dadd, long dadd_sys_stride, long dadd_elem_stride,
-                  const double* __restrict__ rhs, long ldr, VarSrc zsrc,
-                  double* __restrict__ out, long ldo, double* __restrict__ Lout, int* __restrict__ fail_flag) {
-    extern __shared__ double sm[];
-    const int npairs = k * (k + 1) / 2;
-    double* L = sm;
-    double* vec = sm + npairs;      // k
-    const int sys = blockIdx.x;
-    if (sys >= nsys) return;
-    const int tid = threadIdx.x, T = blockDim.x;
-
-    const double* q = Qp + (long)sys * ldq;
-    for (int idx = tid; idx < npairs; idx += T) L[idx] = q[idx];
-    __syncthreads();
-    if (dadd) {
-        for (int a = tid; a < k; a += T) L[a * (a + 1) / 2 + a] += dadd[(long)sys * dadd_sys_stride + (long)a * dadd_elem_stride];
-    }
-    __syncthreads();
-
-    // right-looking Cholesky on the packed lower triangle, rows dealt cyclically to threads
-    bool bad = false;
-    for (int j = 0; j < k; j++) {
-        const int jj = j * (j + 1) / 2 + j;
-        const double djj = L[jj];
-        if (!(djj > 0.0)) { bad = true; break; }     // uniform across the block (same smem value)
-        const double dinv = 1.0 / sqrt(djj);
-        __syncthreads();                              // everyone has read L[jj] before it is overwritten
-        if (tid == 0) L[jj] = sqrt(djj);
-        for (int i = j + 1 + tid; i < k; i += T) L[i * (i + 1) / 2 + j] *= dinv;
-        __syncthreads();
-        for (int i = j + 1 + tid; i < k; i += T) {
-            const double lij = L[i * (i + 1) / 2 + j];
-            double* row = L + i * (i + 1) / 2;
-            for (int l = j + 1; l <= i; l++) row[l] -= lij * L[l * (l + 1) / 2 + j];
-        }
-        __syncthreads();
-    }
-    if (bad) {
-        if (tid == 0) atomicMax(fail_flag, sys + 1);
-        return;
-    }
-    if (Lout) {
-        for (int idx = tid; idx < npairs; idx += T) Lout[(long)sys * npairs + idx] = L[idx];
-    }
-    if (!out) return;
-
-    // ---- solves, warp 0 only: lane owns entries i = lane + 32 t ----
-    if (tid >= 32) return;
-    const int lane = tid;
-    double x[KT];
-#pragma unroll
-    for (int t = 0; t < KT; t++) {
-        const int i = lane + 32 * t;
-        x[t] = (i < k) ? rhs[(long)sys * ldr + i] : 0.0;
-    }
-    // forward: v_i = (m_i - sum_{j<i} L[i][j] v_j) / L[i][i]   (row-oriented dot products)
-    for (int i = 0; i < k; i++) {
-        const double* row = L + i * (i + 1) / 2;
-        double part = 0.0;
-#pragma unroll
-        for (int t = 0; t < KT; t++) {
-            const int j = lane + 32 * t;
-            if (j < i) part += row[j] * x[t];
-        }
-        part = warp_sum(part);
-        const int own = i & 31, ti = i >> 5;
-#pragma unroll
-        for (int t = 0; t < KT; t++)
-            if (t == ti && lane == own) x[t] = (x[t] - part) / row[i];
-    }
-    // w = v + z
-#pragma unroll
-    for (int t = 0; t < KT; t++) {
-        const int i = lane + 32 * t;
-        if (i < k) x[t] += var_normal(zsrc, i, sys);
-    }
-    // backward: x_j = w_j / L[j][j]; w_i -= L[j][i] x_j for i < j   (rows of L are contiguous)
-    for (int j = k - 1; j >= 0; j--) {
-        const double* row = L + j * (j + 1) / 2;
-        const int own = j & 31, tj = j >> 5;
-        double xj = 0.0;
-#pragma unroll
-        for (int t = 0; t < KT; t++)
-            if (t == tj) xj = x[t];
-        xj = __shfl_sync(0xffffffffu, xj, own) / row[j];
-#pragma unroll
-        for (int t = 0; t < KT; t++) {
-            const int i = lane + 32 * t;
-            if (t == tj && lane == own) x[t] = xj;
-            else if (i < j) x[t] -= row[i] * xj;
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < KT; t++) {
-        const int i = lane + 32 * t;
-        if (i < k) out[(long)sys * ldo + i] = x[t];
-    }
-}
-
 // pack a full symmetric k x k (column-major, ld) into packed-lower order
 __global__ void pack_lower_kernel(const double* __restrict__ A, long ld, int k, double* __restrict__ out) {
     const int npairs = k * (k + 1) / 2;
@@ -323,17 +213,42 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 // sample_means element-wise step (cpp:75-78 without the U product):
 //   theta[i,j] = (DtYt[i,j] * rp_j) / d + z[i,j] / sqrt(d),  d = s1_i ep_j + s2_i rp_j
 // ------------------------------------------------------------------------------------
-__global__ void means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
-                                   const double* __restrict__ s1, const double* __restrict__ s2,
-                                   const double* __restrict__ rp, const double* __restrict__ ep, VarSrc zsrc,
-                                   double* __restrict__ theta, long ldt) {
-    const int j = blockIdx.y;
+// One CTA per trait.  When Bout != null the first b (<= MEANS_BMAX) rows of location_sample = U theta (cpp:78),
+// i.e. B (fast_BSFG_sampler.R:206), are reduced in the same pass: B[c,j] = sum_i U[c,i] theta[i,j], U given
+// transposed (Ut[i,c], column c contiguous).
+constexpr int MEANS_BMAX = 4;
+__global__ void __launch_bounds__(256)
+means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
+                   const double* __restrict__ s1, const double* __restrict__ s2,
+                   const double* __restrict__ rp, const double* __restrict__ ep, VarSrc zsrc,
+                   double* __restrict__ theta, long ldt,
+                   const double* __restrict__ Ut, long ldu, int b, double* __restrict__ Bout, long ldb) {
+    __shared__ double red[32];
+    const int j = blockIdx.x;
     if (j >= p) return;
     const double rpj = rp[j], epj = ep[j];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < br; i += gridDim.x * blockDim.x) {
+    double acc[MEANS_BMAX];
+#pragma unroll
+    for (int c = 0; c < MEANS_BMAX; c++) acc[c] = 0.0;
+    for (int i = threadIdx.x; i < br; i += blockDim.x) {
         const double d = s1[i] * epj + s2[i] * rpj;
         const double mean = (DtYt[(long)j * ldd + i] * rpj) / d;
-        theta[(long)j * ldt + i] = mean + var_normal(zsrc, i, j) / sqrt(d);
+        const double th = mean + var_normal(zsrc, i, j) / sqrt(d);
+        theta[(long)j * ldt + i] = th;
+        if (Bout) {
+#pragma unroll
+            for (int c = 0; c < MEANS_BMAX; c++)
+                if (c < b) acc[c] += Ut[(long)c * ldu + i] * th;
+        }
+    }
+    if (Bout) {
+#pragma unroll
+        for (int c = 0; c < MEANS_BMAX; c++) {
+            if (c < b) {
+                const double v = block_sum(acc[c], red);
+                if (threadIdx.x == 0) Bout[(long)j * ldb + c] = v;
+            }
+        }
     }
 }
 
@@ -660,13 +575,14 @@ __global__ void factor_reduce_kernel(const double* __restrict__ LP, long ldp, co
 }
 
 // per-trait reductions + the two Gamma precision draws (fast_BSFG_sampler.R:239-245), one warp per trait.
-//   SS_j = yy - 2 th.DtY - 2 l.FtY + q2 + 2 th.acc2 + l.G2          (expanded ||y - Design_U th - F l||^2)
+//   SS_j = yy - 2 th.DtY - 2 l.FtY + q2 + 2 l.FDth + l.G2          (expanded ||y - Design_U th - F l||^2;
+//          FDth = F'Design_U th_j, k values per trait instead of the br-vector Design_U'F l_j)
 //   q2   = sum s2 th^2 (diag mode)  or  th.(M2 th) (direct mode);  q1 likewise with s1 / M1
 //   resid_Y_prec ~ Gamma(a_r + n/2, b_r + SS/2);  E_a_prec ~ Gamma(a_e + r/2, b_e + (q1 - bX sum B^2)/2)
 struct TraitReduceArgs {
     const double* theta; long ldth;
     const double* DtY; long lddy;
-    const double* acc2; long ldacc;
+    const double* FDth; long ldfd;                        // (F' Design_U) theta, k x p
     const double* M1th; const double* M2th; long ldm;     // null in diag mode
     const double* s1; const double* s2;
     const double* Lt; long ldlt;
@@ -686,26 +602,26 @@ __global__ void trait_reduce_kernel(TraitReduceArgs a, VarSrc g_resid, VarSrc g_
     if (j >= a.p) return;
     const double* th = a.theta + (long)j * a.ldth;
     const double* dy = a.DtY + (long)j * a.lddy;
-    const double* ac = a.acc2 + (long)j * a.ldacc;
     double a1 = 0, a2 = 0, q1 = 0, q2 = 0;
     if (a.M1th) {
         const double* m1 = a.M1th + (long)j * a.ldm;
         const double* m2 = a.M2th + (long)j * a.ldm;
         for (int i = lane; i < a.br; i += 32) {
             const double t = th[i];
-            a1 += t * dy[i]; a2 += t * ac[i]; q1 += t * m1[i]; q2 += t * m2[i];
+            a1 += t * dy[i]; q1 += t * m1[i]; q2 += t * m2[i];
         }
     } else {
         for (int i = lane; i < a.br; i += 32) {
             const double t = th[i];
-            a1 += t * dy[i]; a2 += t * ac[i]; q1 += a.s1[i] * (t * t); q2 += a.s2[i] * (t * t);
+            a1 += t * dy[i]; q1 += a.s1[i] * (t * t); q2 += a.s2[i] * (t * t);
         }
     }
     double l1 = 0, l2 = 0;
     const double* lt = a.Lt + (long)j * a.ldlt;
     const double* fy = a.FtY + (long)j * a.ldfy;
     const double* g2 = a.G2 + (long)j * a.ldg2;
-    for (int h = lane; h < a.k; h += 32) { const double l = lt[h]; l1 += l * fy[h]; l2 += l * g2[h]; }
+    const double* fd = a.FDth + (long)j * a.ldfd;
+    for (int h = lane; h < a.k; h += 32) { const double l = lt[h]; l1 += l * fy[h]; l2 += l * g2[h]; a2 += l * fd[h]; }
     double bb = 0;
     for (int c = lane; c < a.b; c += 32) { const double v = a.Bfix[(long)j * a.ldb + c]; bb += v * v; }
     a1 = warp_sum(a1); a2 = warp_sum(a2); q1 = warp_sum(q1); q2 = warp_sum(q2);

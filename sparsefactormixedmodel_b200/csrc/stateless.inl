@@ -8,7 +8,8 @@ struct Device {
     int sms = 0;
     DVec ws;          // split-K workspace
     int* d_flag = nullptr;
-    static constexpr size_t WS_DOUBLES = (size_t)160 * 128 * 128;
+    std::map<int, uint16_t*> chol_maps;   // k -> packed-lower index -> tile offset (chol_blocked.cuh)
+    static constexpr size_t WS_DOUBLES = (size_t)24 << 20;   // 192 MB of split-K partials
     void init() {
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -50,6 +51,21 @@ struct Device {
         scale_kernel<<<blocks, 256, 0, st>>>(in.p, in.ld, in.rows, in.cols, rowscale, colscale, out.p, out.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
+    // table for chol_blocked_kernel: packed-lower pair(a,b) = a(a+1)/2 + b  ->  offset of element (a,b) in the tiled layout
+    const uint16_t* chol_map(int k) {
+        auto it = chol_maps.find(k);
+        if (it != chol_maps.end()) return it->second;
+        std::vector<uint16_t> h((size_t)k * (k + 1) / 2);
+        for (int a = 0; a < k; a++)
+            for (int b = 0; b <= a; b++)
+                h[(size_t)a * (a + 1) / 2 + b] = (uint16_t)(cb_tile_id(a >> 3, b >> 3) * 64 + cb_swz(a & 7, b & 7));
+        uint16_t* dptr = nullptr;
+        BSFG_CUDA(cudaMalloc(&dptr, sizeof(uint16_t) * h.size()));
+        BSFG_CUDA(cudaMemcpyAsync(dptr, h.data(), sizeof(uint16_t) * h.size(), cudaMemcpyHostToDevice, st));
+        sync();
+        chol_maps[k] = dptr;
+        return dptr;
+    }
     int read_flag_and_clear() {
         int h = 0;
         BSFG_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -79,33 +95,32 @@ static VarSrc make_var(const DMat* injected, uint64_t seed, uint32_t site, uint3
 }
 
 // ---- reusable device-level pieces (also used by the sweep) -----------------------------------
+constexpr int BSFG_K_LIMIT = 232;   // 29 x 29 tiles of 8 x 8 doubles = 222.7 KB of the 227 KB shared memory per CTA
 static int kt_for(int k) {
+    if (k > BSFG_K_LIMIT) fail(BSFG_ESHAPE, "k = %d exceeds the supported maximum of %d factors", k, BSFG_K_LIMIT);
     if (k <= 32) return 1;
     if (k <= 64) return 2;
     if (k <= 128) return 4;
-    if (k <= 256) return 8;
-    fail(BSFG_ESHAPE, "k = %d exceeds the supported maximum of 256 factors", k);
+    return 8;
 }
 
+// batched Cholesky + solves (chol_blocked.cuh): 4 warps per system up to k = 128, 8 warps above
 static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int nsys, const double* dadd,
                               long dadd_sys_stride, long dadd_elem_stride, const double* rhs, long ldr,
                               const VarSrc& z, double* out, long ldo, double* Lout) {
     if (nsys <= 0) return;
-    const size_t smem = sizeof(double) * ((size_t)k * (k + 1) / 2 + 2 * (size_t)k);
-    if (smem > 227 * 1024) fail(BSFG_ESHAPE, "k = %d: packed Cholesky tile (%zu B) exceeds shared memory", k, smem);
-#define BSFG_LAUNCH_CHOL(KT)                                                                                   \
-    do {                                                                                                       \
-        BSFG_CUDA(cudaFuncSetAttribute(chol_solve_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        chol_solve_kernel<KT><<<nsys, 128, smem, d.st>>>(Qp, ldq, k, nsys, dadd, dadd_sys_stride, dadd_elem_stride, \
-                                                         rhs, ldr, z, out, ldo, Lout, d.d_flag);            \
-    } while (0)
-    switch (kt_for(k)) {
-        case 1: BSFG_LAUNCH_CHOL(1); break;
-        case 2: BSFG_LAUNCH_CHOL(2); break;
-        case 4: BSFG_LAUNCH_CHOL(4); break;
-        default: BSFG_LAUNCH_CHOL(8); break;
+    kt_for(k);
+    const size_t smem = cb_smem_bytes(k);
+    const uint16_t* map = d.chol_map(k);
+    if (k <= 128) {
+        BSFG_CUDA(cudaFuncSetAttribute(chol_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chol_blocked_kernel<4><<<nsys, 128, smem, d.st>>>(Qp, ldq, k, nsys, map, dadd, dadd_sys_stride, dadd_elem_stride,
+                                                          rhs, ldr, z, out, ldo, Lout, d.d_flag);
+    } else {
+        BSFG_CUDA(cudaFuncSetAttribute(chol_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chol_blocked_kernel<8><<<nsys, 256, smem, d.st>>>(Qp, ldq, k, nsys, map, dadd, dadd_sys_stride, dadd_elem_stride,
+                                                          rhs, ldr, z, out, ldo, Lout, d.d_flag);
     }
-#undef BSFG_LAUNCH_CHOL
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
 }
 
@@ -262,8 +277,8 @@ extern "C" int bsfg_sample_means_c(const double* Y_tilde, int n, int p, const do
     d.gemm(1.0, dD, dY, 0.0, DtY);                       // Design_U' Y_tilde, cpp:65
     VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_MEANS, 0, 0, br);
     {
-        dim3 grid(std::min(ceil_div(br, 256), 64), p);
-        means_theta_kernel<<<grid, 256, 0, d.st>>>(DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p, theta.ld);
+        means_theta_kernel<<<p, 256, 0, d.st>>>(DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p, theta.ld,
+                                                nullptr, 0, 0, nullptr, 0);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     d.transpose(dU, dUt);

@@ -3,6 +3,8 @@
 // per-iteration n^2 p products remain.  Included by bsfg.cu.
 
 #include <dlfcn.h>
+#include <chrono>
+#include <cstdlib>
 #include <nccl.h>
 
 namespace bsfg {
@@ -62,14 +64,14 @@ struct bsfg_ctx {
     bsfg::DMat UtY, UtYt, DtY, U1, U1t, UtX, U2, U2t, DU, DUt, U3, U3t, Z1, Z1t, M1, M2;
     bsfg::DVec yy, s, s1_2, s2_2, s1_3, s2_3, h2_prior;
     // state (factor-indexed storage has kmax columns / rows)
-    bsfg::DMat Lt, Lam, Lmsg, LP, Plamt, F, Fa, Bfix, theta, thetat, Ea_in;
+    bsfg::DMat Lt, Lam, Lmsg, LP, Plamt, Ptmp, F, Fa, Bfix, theta, thetat, Ea_in;
     bsfg::DVec F_h2, delta, tauh, rp, ep;
     bool theta_valid = false, derived_valid = false;
     // derived from F
-    bsfg::DMat UtF, FtD;
+    bsfg::DMat UtF, FtD, DtF;
     // scratch
     bsfg::LambdaScratch lsc;
-    bsfg::DMat tmp_brp, acc2, M1th, M2th, red1, YL, ZFa, T1, b3, vfa, FtF, FtY, G2;
+    bsfg::DMat tmp_brp, FDth, M1th, M2th, red1, YL, ZFa, T1, b3, vfa, FtF, FtY, G2;
     bsfg::DVec tau_e, Lp, Lfac, det, ll, red2, colsum_cnt, delta_shapes, delta_rates;
     int* d_ndraws = nullptr;
     int* d_map = nullptr;
@@ -94,11 +96,11 @@ namespace bsfg {
 
 static void ctx_alloc_factor_storage(bsfg_ctx* c) {
     const int n = c->n, pl = c->pl, km = c->kmax, r = c->r, br = c->br;
-    c->Lt.alloc(km, pl); c->Lam.alloc(pl, km); c->Lmsg.alloc(pl, km); c->LP.alloc(pl, km); c->Plamt.alloc(km, pl);
-    c->F.alloc(n, km); c->Fa.alloc(r, km); c->UtF.alloc(n, km); c->FtD.alloc(km, br);
+    c->Lt.alloc(km, pl); c->Lam.alloc(pl, km); c->Lmsg.alloc(pl, km); c->LP.alloc(pl, km); c->Plamt.alloc(km, pl); c->Ptmp.alloc(pl, km);
+    c->F.alloc(n, km); c->Fa.alloc(r, km); c->UtF.alloc(n, km); c->FtD.alloc(km, br); c->DtF.alloc(br, km);
     c->F_h2.alloc(km); c->delta.alloc(km); c->tauh.alloc(km); c->tau_e.alloc(km);
     c->YL.alloc(n, km); c->ZFa.alloc(n, km); c->T1.alloc(r, km); c->b3.alloc(r, km); c->vfa.alloc(r, km);
-    c->FtF.alloc(km, km); c->FtY.alloc(km, pl); c->G2.alloc(km, pl);
+    c->FtF.alloc(km, km); c->FtY.alloc(km, pl); c->G2.alloc(km, pl); c->FDth.alloc(km, pl);
     c->Lp.alloc((long)km * (km + 1) / 2); c->Lfac.alloc((long)km * (km + 1) / 2);
     c->det.alloc(c->H); c->ll.alloc((long)km * c->H);
     // red1 = [LtL (km x km) | P1 (n x km) | P2 (br x km)] stacked by rows: one allreduce buffer
@@ -124,8 +126,10 @@ static void refresh_derived(bsfg_ctx* c) {
     // UtF = U'F (t(FtU), cpp:107) and FtD = F' Design_U: depend only on F
     Device& d = c->dev;
     DMat F = view(c->F, c->n, c->k), UtF = view(c->UtF, c->n, c->k), FtD = view(c->FtD, c->k, c->br);
+    DMat DtF = view(c->DtF, c->br, c->k);
     d.gemm(1.0, c->U1, F, 0.0, UtF);
     d.gemm(1.0, F, c->DU, 0.0, FtD);
+    d.transpose(FtD, DtF);
     c->derived_valid = true;
 }
 
@@ -166,16 +170,17 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     dgemm_tn(d.st, d.sms, br, pl, k, -1.0, FtD.p, FtD.ld, Lt.p, Lt.ld, 1.0, c->DtY.p, c->DtY.ld, c->tmp_brp.p,
              c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
     {
-        dim3 grid(std::min(ceil_div(br, 256), 64), pl);
-        means_theta_kernel<<<grid, 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
-                                                   c->ep.p, v.zM, c->theta.p, c->theta.ld);
+        const bool fuse_b = b > 0 && b <= MEANS_BMAX;      // B = location_sample[1:b,] (R:206) reduced in the same pass
+        means_theta_kernel<<<pl, 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
+                                                 c->ep.p, v.zM, c->theta.p, c->theta.ld, c->U2t.p, c->U2t.ld, b,
+                                                 fuse_b ? c->Bfix.p : nullptr, c->Bfix.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (b > 0 && !fuse_b) {
+            DMat U2Bt = view(c->U2t, br, b);               // first b columns of U2' = rows 0..b-1 of U2
+            d.gemm(1.0, U2Bt, c->theta, 0.0, c->Bfix);
+        }
     }
     d.transpose(c->theta, c->thetat);
-    if (b > 0) {
-        DMat U2Bt = view(c->U2t, br, b);                   // first b columns of U2' = rows 0..b-1 of U2
-        d.gemm(1.0, U2Bt, c->theta, 0.0, c->Bfix);         // B = location_sample[1:b,], R:206
-    }
     c->theta_valid = true;
     phase_mark(c, 4);
 
@@ -238,14 +243,15 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
         d.gemm(1.0, F, F, 0.0, FtF);
         d.gemm(1.0, UtF, c->UtY, 0.0, FtY);                // F'Y = (U'F)'(U'Y)
         d.gemm(1.0, FtF, Lt, 0.0, G2);                     // F'F lambda_j
-        d.gemm(1.0, FtD, Lt, 0.0, c->acc2);                // Design_U' F lambda_j
+        DMat DtF = view(c->DtF, br, k), FDth = view(c->FDth, k, pl);
+        d.gemm(1.0, DtF, c->theta, 0.0, FDth);             // (F' Design_U) theta_j: k values per trait
         if (c->mode == 1) {
             d.gemm(1.0, c->M1, c->theta, 0.0, c->M1th);
             d.gemm(1.0, c->M2, c->theta, 0.0, c->M2th);
         }
         TraitReduceArgs a;
         a.theta = c->theta.p; a.ldth = c->theta.ld; a.DtY = c->DtY.p; a.lddy = c->DtY.ld;
-        a.acc2 = c->acc2.p; a.ldacc = c->acc2.ld;
+        a.FDth = FDth.p; a.ldfd = FDth.ld;
         a.M1th = c->mode == 1 ? c->M1th.p : nullptr; a.M2th = c->mode == 1 ? c->M2th.p : nullptr; a.ldm = c->M1th.ld;
         a.s1 = c->s1_2.p; a.s2 = c->s2_2.p;
         a.Lt = Lt.p; a.ldlt = Lt.ld; a.FtY = FtY.p; a.ldfy = FtY.ld; a.G2 = G2.p; a.ldg2 = G2.ld;
@@ -433,7 +439,7 @@ extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
         ctx_alloc_factor_storage(c);
         const int n = c->n, pl = c->pl, br = c->br, b = c->b;
         c->Bfix.alloc(std::max(b, 1), pl); c->theta.alloc(br, pl); c->thetat.alloc(pl, br);
-        c->tmp_brp.alloc(br, pl); c->acc2.alloc(br, pl);
+        c->tmp_brp.alloc(br, pl);
         c->rp.alloc(pl); c->ep.alloc(pl); c->yy.alloc(pl);
         c->aux_lp_rate.alloc(pl, c->kmax); c->aux_rr.alloc(pl); c->aux_re.alloc(pl);
         BSFG_CUDA(cudaMalloc(&c->d_ndraws, sizeof(int)));
@@ -587,10 +593,9 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
     BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, st->tauh, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
     if (b > 0) c->Bfix.upload(st->B, d.st);
     {
-        DMat Plam(pl, k), Plamt = view(c->Plamt, k, pl);
+        DMat Plam = view(c->Ptmp, pl, k), Plamt = view(c->Plamt, k, pl);   // persistent scratch: no cudaMalloc on the state path
         Plam.upload(st->Plam, d.st);
         d.transpose(Plam, Plamt);
-        d.sync();
     }
     if (st->Lambda) {
         DMat Lam = view(c->Lam, pl, k), Lt = view(c->Lt, k, pl);
@@ -619,26 +624,37 @@ extern "C" int bsfg_get_state(bsfg_ctx* c, bsfg_state* st) {
     const int n = c->n, pl = c->pl, r = c->r, b = c->b, br = c->br, k = c->k;
     st->k = k;
     st->nrun = (int)c->iter;
+    static const bool trace = getenv("BSFG_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        d.sync();
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bsfg_get_state] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     if (st->Lambda) { DMat Lam = view(c->Lam, pl, k); Lam.download(st->Lambda, d.st); }
+    lap("Lambda");
     if (st->Lambda_prec) { DMat LP = view(c->LP, pl, k); LP.download(st->Lambda_prec, d.st); }
+    lap("Lambda_prec");
     if (st->Plam) {
-        DMat Plam(pl, k), Plamt = view(c->Plamt, k, pl);
+        DMat Plam = view(c->Ptmp, pl, k), Plamt = view(c->Plamt, k, pl);
         d.transpose(Plamt, Plam);
         Plam.download(st->Plam, d.st);
-        d.sync();
     }
+    lap("Plam");
     if (st->F) { DMat F = view(c->F, n, k); F.download(st->F, d.st); }
     if (st->F_a) { DMat Fa = view(c->Fa, r, k); Fa.download(st->F_a, d.st); }
     if (st->F_h2) BSFG_CUDA(cudaMemcpyAsync(st->F_h2, c->F_h2.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
     if (st->B && b > 0) c->Bfix.download(st->B, d.st);
+    lap("F,F_a,h2,B");
     if (st->E_a) {
         if (c->theta_valid) {
             // E_a = location_sample[b+(1:r),] = U2[b.., :] theta   (fast_BSFG_sampler.R:207); U2t columns b.. = that block'
-            DMat Ea(r, pl);
+            DMat Ea = view(c->tmp_brp, r, pl);       // scratch that is dead between iterations
             DMat U2Et = view_at(c->U2t.p + (long)b * c->U2t.ld, br, r, c->U2t.ld);
             d.gemm(1.0, U2Et, c->theta, 0.0, Ea);
             Ea.download(st->E_a, d.st);
-            d.sync();
         } else if (c->Ea_in.p) {
             c->Ea_in.download(st->E_a, d.st);
         } else {
@@ -650,6 +666,7 @@ extern "C" int bsfg_get_state(bsfg_ctx* c, bsfg_state* st) {
     if (st->delta) BSFG_CUDA(cudaMemcpyAsync(st->delta, c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
     if (st->tauh) BSFG_CUDA(cudaMemcpyAsync(st->tauh, c->tauh.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
     d.sync();
+    lap("rest");
     BSFG_API_END
 }
 
