@@ -112,6 +112,10 @@ int bsfg_sample_delta_c(const double* delta, const double* tauh, int k, const do
                         unsigned long long seed, double* delta_out, int* n_draws_out,
                         double* shapes_out, double* rates_out);
 
+/* Process-wide default for the weighted-Gram evaluation used by bsfg_sample_Lambda_c and by contexts created with
+ * gram_mode == 0 (see bsfg_config): mode 1 exact, 2 exponential sum (library default); terms/step 0 = keep.      */
+int bsfg_set_gram_default(int mode, int terms, double step);
+
 /* FP64 GEMM core used by everything above, exposed for testing and for `bench.py`'s roofline leg:
  * C (M x N, ldc) = alpha * At' * B + beta * C, At is K x M (lda), B is K x N (ldb); HOST pointers. */
 int bsfg_dgemm_tn_host(int M, int N, int K, double alpha, const double* At, int lda, const double* B,
@@ -137,6 +141,12 @@ typedef struct bsfg_config {
     unsigned long long seed; /* Philox key                                                */
     int z1_is_identity;      /* 1: Z_1 == I_n (r == n), Z_1 pointer may be NULL           */
     int mode;                /* 0 auto, 1 force "direct" residual/E_a forms, 2 force "diag" */
+    /* weighted-Gram evaluation for the Lambda draw: 0 library default, 1 exact DMMA GEMM
+     * over the n individuals, 2 exponential-sum factorisation (relative error ~1e-14, exact fallback on device
+     * when `gram_terms` nodes cannot cover the dynamic range).  gram_terms / gram_step: 0 = default (256 / 0.28). */
+    int gram_mode;
+    int gram_terms;
+    double gram_step;
 } bsfg_config;
 
 typedef struct bsfg_priors {           /* model_setup.R:49-63, fast_BSFG_sampler_init.R:114 */
@@ -213,6 +223,10 @@ int bsfg_sweep_injected(bsfg_ctx* ctx, const bsfg_variates* v);
 /* which residual / E_a_prec formulation the context selected (1 direct, 2 diag) and the measured
  * ||U2' P U2 - diag(s1)||_max, ||Design_U' Design_U - diag(s2)||_max that drove the choice.        */
 int bsfg_get_mode(bsfg_ctx* ctx, int* mode, double* resid_s1, double* resid_s2);
+/* weighted-Gram evaluation in use, number of iterations that fell back to the exact GEMM because the exponential
+ * sum could not cover the range of E_a_prec/resid_Y_prec, and that range at the last iteration.                    */
+int bsfg_get_gram_stats(bsfg_ctx* ctx, int* mode, int* terms, double* step, long long* fallbacks,
+                        double* c_min, double* c_max);
 /* timing of the last bsfg_sweep call: total device milliseconds (CUDA events on the sweep stream),
  * kernel launches issued, and per-phase milliseconds (array of BSFG_N_PHASES doubles, may be NULL) */
 #define BSFG_N_PHASES 12

@@ -34,7 +34,8 @@ class bsfg_config(C.Structure):
     _fields_ = [("n", C.c_int), ("p_total", C.c_int), ("p_offset", C.c_int), ("p_local", C.c_int),
                 ("k", C.c_int), ("k_max", C.c_int), ("r", C.c_int), ("b", C.c_int),
                 ("h2_divisions", C.c_int), ("rank", C.c_int), ("world", C.c_int),
-                ("seed", C.c_ulonglong), ("z1_is_identity", C.c_int), ("mode", C.c_int)]
+                ("seed", C.c_ulonglong), ("z1_is_identity", C.c_int), ("mode", C.c_int),
+                ("gram_mode", C.c_int), ("gram_terms", C.c_int), ("gram_step", C.c_double)]
 
 
 class bsfg_priors(C.Structure):
@@ -75,7 +76,7 @@ EXPORTS = [
     "bsfg_sample_Lambda_c", "bsfg_sample_lambda_c", "bsfg_sample_means_c",
     "bsfg_sample_factors_scores_c", "bsfg_sample_px_factors_scores_c", "bsfg_sample_h2s_discrete_c",
     "bsfg_sample_prec_discrete_conditional_c", "bsfg_sample_F_a_c", "bsfg_sample_delta_c",
-    "bsfg_dgemm_tn_host",
+    "bsfg_dgemm_tn_host", "bsfg_set_gram_default", "bsfg_get_gram_stats",
     "bsfg_create", "bsfg_destroy", "bsfg_set_priors", "bsfg_upload_constants", "bsfg_set_state",
     "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_get_mode",
     "bsfg_get_timing", "bsfg_nccl_unique_id", "bsfg_comm_init", "bsfg_launch_count",

@@ -41,6 +41,7 @@ struct GemmArgs {
     double* ws;            // [splits][N][M] raw partials when splits > 1
     int tiles_m, tiles_n;
     int group_n;           // rasterisation: tiles are walked m-fastest inside groups of `group_n` n-tiles
+    const int* run_if;     // optional device flag: the whole launch is a no-op when *run_if == 0
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -106,6 +107,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     static_assert(BM == 128 && BN == 128, "warp layout below is written for 128x128 CTA tiles");
     using S = GemmSmem<BM, BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
+    if (g.run_if && *g.run_if == 0) return;        // uniform across the grid: a conditional launch (exact-Gram fallback)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -238,6 +240,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 __global__ void splitk_reduce_kernel(GemmArgs g) {
+    if (g.run_if && *g.run_if == 0) return;
     const size_t total = (size_t)g.M * g.N;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
@@ -258,6 +261,6 @@ struct GemmPlan;   // opaque to callers; see gemm_host.cu
 // even, pointers 16-byte aligned.  `ws`/`ws_doubles` is scratch for split-K (may be null: no split).
 void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
               const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
-              double* ws, size_t ws_doubles);
+              double* ws, size_t ws_doubles, const int* run_if = nullptr);
 
 }  // namespace bsfg

@@ -40,7 +40,7 @@ static long long g_launch_counter = 0;   // kernels launched by this library (be
 
 void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
               const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
-              double* ws, size_t ws_doubles) {
+              double* ws, size_t ws_doubles, const int* run_if) {
     if (M <= 0 || N <= 0) return;
     if (K <= 0) fail(BSFG_ESHAPE, "dgemm_tn: K must be positive");
     static bool attr_set = false;
@@ -57,6 +57,7 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     g.C = C; g.ldc = ldc;
     g.Cin = (beta != 0.0) ? Cin : nullptr; g.ldcin = ldcin;
     g.alpha = alpha; g.beta = beta;
+    g.run_if = run_if;
     g.tiles_m = ceil_div(M, 128);
     g.tiles_n = ceil_div(N, 128);
     g.group_n = 8;

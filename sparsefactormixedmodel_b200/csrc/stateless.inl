@@ -145,28 +145,79 @@ static void launch_factor_rows(Device& d, const double* Lp, int k, int n, const 
 }
 
 // Lambda draw given rotated inputs.  UtF n x k, UtY n x p (rotated data), optional UtX (n x b), B (b x p).
-// Writes Lt (k x p).  Scratch: Gt (n x npairs), W, WY (n x p), Q (npairs x p), Mn (k x p).
+// Writes Lt (k x p).  Scratch: Gt (n x npairs), W, WY (n x p), Q (npairs x p), Mn (k x p) and, for the
+// exponential-sum Gram (kernels.cuh), A (n x R), Ht (R x npairs), E (R x p), the device plan and the fallback flag.
+enum GramMode { GRAM_DEFAULT = 0, GRAM_EXACT = 1, GRAM_EXPSUM = 2 };
+struct GramOpts {
+    int mode = GRAM_EXPSUM;      // resolved (never GRAM_DEFAULT)
+    int terms = 256;             // R
+    double step = 0.28;          // h: relative quadrature error ~1.2e-14
+    double s_min = 0.0, s_max = 0.0;
+};
+static GramOpts g_gram_default;
+static GramOpts resolve_gram(int mode, int terms, double step) {
+    GramOpts o = g_gram_default;
+    if (mode != GRAM_DEFAULT) o.mode = mode;
+    if (terms > 0) o.terms = terms;
+    if (step > 0.0) o.step = step;
+    if (o.mode != GRAM_EXACT && o.mode != GRAM_EXPSUM) fail(BSFG_EARG, "gram_mode must be 0 (default), 1 (exact) or 2 (expsum)");
+    if (o.terms < 16 || o.terms > 4096 || o.terms % 16 != 0) fail(BSFG_EARG, "gram_terms must be a multiple of 16 in [16, 4096]");
+    if (!(o.step >= 0.05 && o.step <= 0.5)) fail(BSFG_EARG, "gram_step must lie in [0.05, 0.5]");
+    return o;
+}
+static void host_minmax(const double* s, int n, double* lo, double* hi) {
+    double a = s[0], b = s[0];
+    for (int i = 1; i < n; i++) { a = std::min(a, s[i]); b = std::max(b, s[i]); }
+    *lo = a; *hi = b;
+}
 struct LambdaScratch {
-    DMat Gt, W, WY, Q, Mn;
-    void ensure(long n, long p, long k) {
+    DMat Gt, W, WY, Q, Mn, A, Ht, E;
+    ExpSumPlan* plan = nullptr;
+    int* need_exact = nullptr;
+    unsigned long long* fallbacks = nullptr;
+    ~LambdaScratch() {
+        if (plan) cudaFree(plan);
+        if (need_exact) cudaFree(need_exact);
+        if (fallbacks) cudaFree(fallbacks);
+    }
+    void ensure(long n, long p, long k, long R) {
         const long np = k * (k + 1) / 2;
         if (Gt.rows != n || Gt.cols != np) Gt.alloc(n, np);
         if (W.rows != n || W.cols != p) { W.alloc(n, p); WY.alloc(n, p); }
         if (Q.rows != np || Q.cols != p) Q.alloc(np, p);
         if (Mn.rows != k || Mn.cols != p) Mn.alloc(k, p);
+        if (R > 0) {
+            if (A.rows != n || A.cols != R) A.alloc(n, R);
+            if (Ht.rows != R || Ht.cols != np) Ht.alloc(R, np);
+            if (E.rows != R || E.cols != p) E.alloc(R, p);
+        }
+        if (!plan) {
+            BSFG_CUDA(cudaMalloc(&plan, sizeof(ExpSumPlan)));
+            BSFG_CUDA(cudaMemset(plan, 0, sizeof(ExpSumPlan)));
+            BSFG_CUDA(cudaMalloc(&need_exact, sizeof(int)));
+            BSFG_CUDA(cudaMemset(need_exact, 0, sizeof(int)));
+            BSFG_CUDA(cudaMalloc(&fallbacks, sizeof(unsigned long long)));
+            BSFG_CUDA(cudaMemset(fallbacks, 0, sizeof(unsigned long long)));
+        }
     }
 };
 
-static void lambda_core(Device& d, LambdaScratch& sc, const DMat& UtF, const DMat& UtY, const double* s,
+static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const DMat& UtF, const DMat& UtY, const double* s,
                         const double* rp, const double* ep, const DMat* UtX, const DMat* B,
                         const double* plam, long plam_sys_stride, long plam_elem_stride, const VarSrc& z,
-                        DMat& Lt, cudaEvent_t* ev = nullptr /* 3 marks: before Gram GEMM, after it, after chol */) {
+                        DMat& Lt, cudaEvent_t* ev = nullptr /* 3 marks: before the Gram product, after it, after chol */) {
     const int n = (int)UtF.rows, k = (int)UtF.cols, p = (int)UtY.cols;
     const int np = k * (k + 1) / 2;
-    sc.ensure(n, p, k);
+    const bool expsum = go.mode == GRAM_EXPSUM;
+    const int R = expsum ? go.terms : 0;
+    sc.ensure(n, p, k, R);
     {
         dim3 grid(std::min(ceil_div(n, 256), 64), np);
         gram_features_kernel<<<grid, 256, 0, d.st>>>(UtF.p, UtF.ld, n, k, sc.Gt.p, sc.Gt.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    if (expsum) {
+        expsum_plan_kernel<<<1, 1024, 0, d.st>>>(ep, rp, p, go.s_min, go.s_max, go.step, R, 0, sc.plan, sc.need_exact, sc.fallbacks);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     {
@@ -174,13 +225,28 @@ static void lambda_core(Device& d, LambdaScratch& sc, const DMat& UtF, const DMa
         const int b = UtX ? (int)UtX->cols : 0;
         lambda_weights_kernel<<<grid, 256, 0, d.st>>>(UtY.p, UtY.ld, n, p, s, rp, ep, UtX ? UtX->p : nullptr,
                                                       UtX ? UtX->ld : 0, B ? B->p : nullptr, B ? B->ld : 0, b,
-                                                      sc.W.p, sc.W.ld, sc.WY.p, sc.WY.ld);
+                                                      sc.W.p, sc.W.ld, expsum ? sc.need_exact : nullptr, sc.WY.p, sc.WY.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    if (expsum) {
+        dim3 grid(std::min(ceil_div(n, 256), 64), R);
+        expsum_nodes_kernel<<<grid, 256, 0, d.st>>>(sc.plan, s, n, sc.A.p, sc.A.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        expsum_traits_kernel<<<p, 256, 0, d.st>>>(sc.plan, ep, rp, p, sc.E.p, sc.E.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     if (ev) BSFG_CUDA(cudaEventRecord(ev[0], d.st));
-    d.gemm(1.0, sc.Gt, sc.W, 0.0, sc.Q);       // Q[pair, j] = sum_i f_ia f_ib w_ij
+    if (expsum) {
+        d.gemm(1.0, sc.A, sc.Gt, 0.0, sc.Ht);      // Ht[m, pair] = sum_i A[i,m] f_ia f_ib
+        d.gemm(1.0, sc.Ht, sc.E, 0.0, sc.Q);       // Q[pair, j]  = sum_m Ht[m,pair] E[m,j]
+        // exact fallback: a no-op launch unless the plan kernel raised need_exact
+        dgemm_tn(d.st, d.sms, np, p, n, 1.0, sc.Gt.p, sc.Gt.ld, sc.W.p, sc.W.ld, 0.0, nullptr, 0, sc.Q.p, sc.Q.ld,
+                 nullptr, 0, sc.need_exact);
+    } else {
+        d.gemm(1.0, sc.Gt, sc.W, 0.0, sc.Q);       // Q[pair, j] = sum_i f_ia f_ib w_ij
+    }
     if (ev) BSFG_CUDA(cudaEventRecord(ev[1], d.st));
-    d.gemm(1.0, UtF, sc.WY, 0.0, sc.Mn);       // m[a, j]    = sum_i f_ia w_ij y_ij
+    d.gemm(1.0, UtF, sc.WY, 0.0, sc.Mn);           // m[a, j]    = sum_i f_ia w_ij y_ij
     launch_chol_solve(d, sc.Q.p, sc.Q.ld, k, p, plam, plam_sys_stride, plam_elem_stride, sc.Mn.p, sc.Mn.ld, z,
                       Lt.p, Lt.ld, nullptr);
     if (ev) BSFG_CUDA(cudaEventRecord(ev[2], d.st));
@@ -209,6 +275,16 @@ using namespace bsfg;
     }
 
 #define REQUIRE_PTR(p) do { if (!(p)) bsfg::fail(BSFG_EARG, "argument %s is NULL", #p); } while (0)
+
+extern "C" int bsfg_set_gram_default(int mode, int terms, double step) {
+    BSFG_API_BEGIN
+    if (mode == GRAM_DEFAULT) mode = GRAM_EXPSUM;
+    GramOpts saved = g_gram_default;
+    g_gram_default = GramOpts();
+    try { g_gram_default = resolve_gram(mode, terms, step); }
+    catch (...) { g_gram_default = saved; throw; }
+    BSFG_API_END
+}
 
 extern "C" int bsfg_dgemm_tn_host(int M, int N, int K, double alpha, const double* At, int lda, const double* B,
                                   int ldb, double beta, double* C, int ldc) {
@@ -245,8 +321,10 @@ extern "C" int bsfg_sample_Lambda_c(const double* Y_tilde, int n, int p, const d
     d.gemm(1.0, dU, dF, 0.0, UtF);       // U'F  = t(FtU), cpp:107
     d.gemm(1.0, dU, dY, 0.0, UtY);       // U'Y_tilde, cpp:108
     LambdaScratch sc;
+    GramOpts go = resolve_gram(GRAM_DEFAULT, 0, 0.0);
+    host_minmax(s, n, &go.s_min, &go.s_max);
     VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_LAMBDA, 0, 0, k);
-    lambda_core(d, sc, UtF, UtY, ds.p, drp.p, dep.p, nullptr, nullptr, dPlam.p, 1, dPlam.ld, zs, Lt);
+    lambda_core(d, sc, go, UtF, UtY, ds.p, drp.p, dep.p, nullptr, nullptr, dPlam.p, 1, dPlam.ld, zs, Lt);
     d.transpose(Lt, Lam);
     Lam.download(Lambda_out, d.st);
     check_notpd(d, "sample_Lambda_c");

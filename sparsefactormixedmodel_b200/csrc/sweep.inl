@@ -71,6 +71,7 @@ struct bsfg_ctx {
     bsfg::DMat UtF, FtD, DtF;
     // scratch
     bsfg::LambdaScratch lsc;
+    bsfg::GramOpts gram;
     bsfg::DMat tmp_brp, FDth, M1th, M2th, red1, YL, ZFa, T1, b3, vfa, FtF, FtY, G2;
     bsfg::DVec tau_e, Lp, Lfac, det, ll, red2, colsum_cnt, delta_shapes, delta_rates;
     int* d_ndraws = nullptr;
@@ -158,7 +159,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
 
     // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
     phase_mark(c, 0);
-    lambda_core(d, c->lsc, UtF, c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
+    lambda_core(d, c->lsc, c->gram, UtF, c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
                 Plamt.p, Plamt.ld, 1, v.zL, Lt, c->phase_timing ? &c->ev_phase[1] : nullptr);
     {
         dim3 grid(ceil_div(k, 32), ceil_div(pl, 32)), block(32, 8);
@@ -429,10 +430,12 @@ extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
         fail(BSFG_ESHAPE, "bsfg_create: inconsistent sizes");
     if (cfg->z1_is_identity && cfg->r != cfg->n) fail(BSFG_ESHAPE, "z1_is_identity requires r == n");
     kt_for(cfg->k_max);
+    GramOpts gram = resolve_gram(cfg->gram_mode, cfg->gram_terms, cfg->gram_step);
     bsfg_ctx* c = new bsfg_ctx();
     try {
         c->dev.init();
         c->cfg = *cfg;
+        c->gram = gram;
         c->n = cfg->n; c->pl = cfg->p_local; c->p_total = cfg->p_total; c->p_off = cfg->p_offset;
         c->k = cfg->k; c->kmax = cfg->k_max; c->r = cfg->r; c->b = cfg->b; c->br = cfg->b + cfg->r; c->H = cfg->h2_divisions;
         c->z1_identity = cfg->z1_is_identity != 0;
@@ -500,6 +503,7 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
     c->U3.alloc(r, r); c->U3t.alloc(r, r);
     c->s.alloc(n); c->s1_2.alloc(br); c->s2_2.alloc(br); c->s1_3.alloc(r); c->s2_3.alloc(r);
     c->U1.upload(k->U1, d.st); c->U2.upload(k->U2, d.st); c->DU.upload(k->Design_U, d.st); c->U3.upload(k->U3, d.st);
+    host_minmax(k->s, n, &c->gram.s_min, &c->gram.s_max);
     c->s.upload(k->s, d.st); c->s1_2.upload(k->s1_2, d.st); c->s2_2.upload(k->s2_2, d.st);
     c->s1_3.upload(k->s1_3, d.st); c->s2_3.upload(k->s2_3, d.st);
     d.transpose(c->U1, c->U1t); d.transpose(c->U2, c->U2t); d.transpose(c->DU, c->DUt); d.transpose(c->U3, c->U3t);
@@ -572,6 +576,27 @@ extern "C" int bsfg_get_mode(bsfg_ctx* c, int* mode, double* resid_s1, double* r
     if (mode) *mode = c->mode;
     if (resid_s1) *resid_s1 = c->resid_s1;
     if (resid_s2) *resid_s2 = c->resid_s2;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_get_gram_stats(bsfg_ctx* c, int* mode, int* terms, double* step, long long* fallbacks,
+                                   double* c_min, double* c_max) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c);
+    if (mode) *mode = c->gram.mode;
+    if (terms) *terms = c->gram.terms;
+    if (step) *step = c->gram.step;
+    ExpSumPlan pl;
+    memset(&pl, 0, sizeof pl);
+    unsigned long long fb = 0;
+    if (c->lsc.plan) {
+        BSFG_CUDA(cudaMemcpyAsync(&pl, c->lsc.plan, sizeof pl, cudaMemcpyDeviceToHost, c->dev.st));
+        BSFG_CUDA(cudaMemcpyAsync(&fb, c->lsc.fallbacks, sizeof fb, cudaMemcpyDeviceToHost, c->dev.st));
+        c->dev.sync();
+    }
+    if (fallbacks) *fallbacks = (long long)fb;
+    if (c_min) *c_min = pl.c_min;
+    if (c_max) *c_max = pl.c_max;
     BSFG_API_END
 }
 

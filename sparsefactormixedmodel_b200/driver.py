@@ -29,6 +29,16 @@ _VARIATE_FIELDS = ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec"
                    "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F")
 
 
+_GRAM_MODES = {"default": 0, "exact": 1, "expsum": 2}
+
+
+def set_gram_default(gram="expsum", terms=0, step=0.0):
+    """Process-wide default for the weighted-Gram evaluation of the Lambda draw (include/bsfg_b200.h
+    `bsfg_set_gram_default`): "exact" = DMMA GEMM over the n individuals, "expsum" = exponential-sum factorisation
+    (library default).  Applies to `sample_Lambda_c` and to sweeps created with gram="default"."""
+    check(_lib.load().bsfg_set_gram_default(_GRAM_MODES[gram], int(terms), C.c_double(step)))
+
+
 def shard_bounds(p, rank, world):
     """Contiguous, balanced split of the p trait columns: rank g owns [lo, hi)."""
     base, rem = divmod(p, world)
@@ -46,7 +56,7 @@ class BSFGSweep:
     """Device-resident Gibbs sweep for one chain (one rank's trait shard)."""
 
     def __init__(self, data_matrices, run_variables, priors, run_parameters, *, k_max=None, k_init=None,
-                 seed=0, rank=0, world=1, mode="auto", nccl_id=None):
+                 seed=0, rank=0, world=1, mode="auto", nccl_id=None, gram="default", gram_terms=0, gram_step=0.0):
         self.lib = _lib.load()
         Y = np.asarray(data_matrices["Y"], dtype=np.float64)
         if np.isnan(Y).any():
@@ -69,7 +79,8 @@ class BSFGSweep:
         ident = _is_identity(Z_1)
         cfg = _lib.bsfg_config(n=n, p_total=p, p_offset=self.lo, p_local=self.pl, k=k0, k_max=self.k_max,
                                r=r, b=b, h2_divisions=self.H, rank=rank, world=world, seed=seed,
-                               z1_is_identity=int(ident), mode={"auto": 0, "direct": 1, "diag": 2}[mode])
+                               z1_is_identity=int(ident), mode={"auto": 0, "direct": 1, "diag": 2}[mode],
+                               gram_mode=_GRAM_MODES[gram], gram_terms=int(gram_terms), gram_step=float(gram_step))
         self._ctx = C.c_void_p()
         check(self.lib.bsfg_create(C.byref(cfg), C.byref(self._ctx)))
         # priors / run parameters
@@ -204,6 +215,12 @@ class BSFGSweep:
         m = C.c_int(0); r1 = C.c_double(0); r2 = C.c_double(0)
         check(self.lib.bsfg_get_mode(self._ctx, C.byref(m), C.byref(r1), C.byref(r2)))
         return {1: "direct", 2: "diag"}.get(m.value, "?"), r1.value, r2.value
+
+    def gram_stats(self):
+        m = C.c_int(0); t = C.c_int(0); h = C.c_double(0); fb = C.c_longlong(0); lo = C.c_double(0); hi = C.c_double(0)
+        check(self.lib.bsfg_get_gram_stats(self._ctx, C.byref(m), C.byref(t), C.byref(h), C.byref(fb), C.byref(lo), C.byref(hi)))
+        return dict(mode={1: "exact", 2: "expsum"}.get(m.value, "?"), terms=t.value, step=h.value, fallbacks=fb.value,
+                    c_min=lo.value, c_max=hi.value)
 
     def timing(self):
         t = C.c_double(0); n = C.c_longlong(0)

@@ -41,13 +41,21 @@ def test_dgemm_linearity_large(pkg):
     assert relerr(c1, A1.T @ B) < 1e-13
 
 
+@pytest.fixture(params=["expsum", "exact"])
+def gram(request, pkg):
+    """Both evaluations of the weighted Gram behind sample_Lambda_c; restores the default."""
+    pkg.set_gram_default(request.param)
+    yield request.param
+    pkg.set_gram_default("expsum")
+
+
 def _prob(small_problem):
     st = small_problem["state"]
     return (st["data_matrices"], st["run_variables"], st["current_state"], st["priors"],
             small_problem["n"], small_problem["p"], small_problem["k"], small_problem["r"], small_problem["b"])
 
 
-def test_sample_Lambda_c(pkg, small_problem):
+def test_sample_Lambda_c(pkg, small_problem, gram):
     from oracle import bsfg_oracle as O
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     rng = np.random.default_rng(11)
@@ -64,7 +72,7 @@ def test_sample_Lambda_c(pkg, small_problem):
 
 
 @pytest.mark.parametrize("n,p,k", [(33, 17, 3), (100, 257, 20), (250, 100, 40), (64, 50, 70)])
-def test_sample_Lambda_c_shapes(pkg, n, p, k):
+def test_sample_Lambda_c_shapes(pkg, n, p, k, gram):
     """ragged sizes incl. odd n (padded leading dimensions), k in each solve bucket (KT=1,2,4)."""
     from oracle import bsfg_oracle as O
     rng = np.random.default_rng(n + p + k)
@@ -77,6 +85,31 @@ def test_sample_Lambda_c_shapes(pkg, n, p, k):
     inv = {"U": U, "s": s}
     want = O.sample_Lambda_c(Y, F, rp, ep, Plam, inv, z)
     got = pkg.sample_Lambda_c(Y, F, rp, ep, Plam, inv, variates=z)
+    assert rowwise_relerr(got, want) < TOL
+
+
+@pytest.mark.parametrize("spread,terms", [(1e4, 0), (1e9, 0), (1e2, 64), (1e2, 512)])
+def test_sample_Lambda_c_expsum_range_guard(pkg, spread, terms):
+    """The exponential-sum Gram must never lose accuracy silently: with a precision ratio E_a_prec/resid_Y_prec
+    spread over 2*log10(spread) decades, or too few nodes, the device guard falls back to the exact GEMM; either way
+    the draw matches the oracle to 1e-9."""
+    from oracle import bsfg_oracle as O
+    rng = np.random.default_rng(3)
+    n, p, k = 96, 40, 9
+    A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n) * 0.05
+    s, U = np.linalg.eigh(A); s = s[::-1].copy(); U = U[:, ::-1].copy()
+    Y = rng.standard_normal((n, p)); F = rng.standard_normal((n, k))
+    ep = np.exp(rng.uniform(-np.log(spread), np.log(spread), p)); rp = np.exp(rng.uniform(-np.log(spread), np.log(spread), p))
+    ep[0], rp[0] = spread, 1 / spread; ep[1], rp[1] = 1 / spread, spread
+    Plam = rng.gamma(2, 1, (p, k)) * np.cumprod(rng.gamma(3, 1, k))[None, :]
+    z = rng.standard_normal((k, p))
+    inv = {"U": U, "s": s}
+    want = O.sample_Lambda_c(Y, F, rp, ep, Plam, inv, z)
+    pkg.set_gram_default("expsum", terms=terms)
+    try:
+        got = pkg.sample_Lambda_c(Y, F, rp, ep, Plam, inv, variates=z)
+    finally:
+        pkg.set_gram_default("expsum", terms=256)
     assert rowwise_relerr(got, want) < TOL
 
 

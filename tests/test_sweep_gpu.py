@@ -35,16 +35,18 @@ def _compare_states(dev, ora, b, tol=TOL, h2_exact=True):
     assert relerr(dev["Plam"], ora["Plam"]) < tol * 10
 
 
+@pytest.mark.parametrize("gram", ["expsum", "exact"])
 @pytest.mark.parametrize("lists,mode,expect", [("stable", "auto", "diag"), ("reference", "auto", "direct"),
                                                ("stable", "direct", "direct")])
-def test_sweep_injected_matches_oracle(lists, mode, expect):
+def test_sweep_injected_matches_oracle(lists, mode, expect, gram):
     from oracle import bsfg_oracle as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 60, 45, 6
     st = _build(n, p, k, lists)
     d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
-    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, mode=mode)
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, mode=mode, gram=gram)
     try:
+        assert sw.gram_stats()["mode"] == gram
         got_mode, r1, r2 = sw.mode()
         assert got_mode == expect, (got_mode, r1, r2)
         rng = np.random.default_rng(21)
@@ -64,6 +66,40 @@ def test_sweep_injected_matches_oracle(lists, mode, expect):
             nd = len(aux["delta_rate"])
             assert relerr(a["delta_rate"][:nd], aux["delta_rate"]) < TOL
             ora = ora_next
+        assert sw.gram_stats()["fallbacks"] == 0
+    finally:
+        sw.close()
+
+
+def test_sweep_expsum_falls_back_to_exact_gram_when_range_is_too_wide():
+    """(s + E_a_prec/resid_Y_prec) spanning 15 decades cannot be covered by 256 nodes: the device raises the fallback flag,
+    the exact Gram GEMM runs for that iteration, the result still matches the oracle, and the event is counted."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 60, 45, 6
+    st = _build(n, p, k, "stable")
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    cs = dict(cs)
+    cs["E_a_prec"] = cs["E_a_prec"].copy(); cs["resid_Y_prec"] = cs["resid_Y_prec"].copy()
+    cs["E_a_prec"][0] *= 1e15; cs["resid_Y_prec"][1] *= 1e3
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, gram="expsum")
+    try:
+        v = I.draw_variates(np.random.default_rng(5), n, p, k, n, 1 + n, pri)
+        sw.set_state(cs)
+        ora, _ = O.gibbs_iteration(d, rv, pri, rp, cs, 1, v)
+        sw.sweep_injected(v)
+        gs = sw.gram_stats()
+        assert gs["fallbacks"] == 1 and gs["c_max"] / gs["c_min"] > 1e16, gs
+        dev = sw.get_state()
+        assert rowwise_relerr(dev["Lambda"], ora["Lambda"]) < TOL
+        assert rowwise_relerr(dev["F"], ora["F"]) < TOL
+        # the next iteration has ordinary precisions again -> no further fallback
+        v = I.draw_variates(np.random.default_rng(6), n, p, k, n, 1 + n, pri)
+        sw.set_state(ora)
+        ora2, _ = O.gibbs_iteration(d, rv, pri, rp, ora, 2, v)
+        sw.sweep_injected(v)
+        assert sw.gram_stats()["fallbacks"] == 1
+        assert rowwise_relerr(sw.get_state()["Lambda"], ora2["Lambda"]) < TOL
     finally:
         sw.close()
 
