@@ -291,7 +291,8 @@ def run_ours(args):
     nccl_id = None
     if world > 1:
         nccl_id = bcast_obj(BSFGSweep.nccl_unique_id() if rank == 0 else None)
-    sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k, seed=20131, rank=rank, world=world, nccl_id=nccl_id)
+    sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k, seed=20131, rank=rank, world=world, nccl_id=nccl_id,
+                   gram=args.gram)
     sw.set_state(cs)
     mode, r1, r2 = sw.mode()
     t_setup = time.time() - t_setup
@@ -323,7 +324,7 @@ def run_ours(args):
     dev_ms, _, phases = sw.timing()
     dev_ms = max_over_ranks(dev_ms)
     value = args.steps / (dev_ms * 1e-3)
-    gram_ms = phases["lambda"]               # exactly one dgemm_tn launch (weighted Gram), last timed iteration
+    gstats = sw.gram_stats()                 # Gram evaluation in use + its two GEMM timings (last timed iteration)
 
     # ---- end to end through the host API, per iteration -----------------------------------
     def pinned(a):
@@ -332,7 +333,12 @@ def run_ours(args):
         v = t.numpy().T
         v[...] = a
         return v
-    host = sw.get_state(with_E_a=False)
+    def pinned_empty(shape):
+        shape = tuple(shape)
+        t = torch.empty(shape[::-1], dtype=torch.float64).pin_memory()
+        return t.numpy().T if len(shape) > 1 else t.numpy()
+    host = sw.alloc_state(k, with_E_a=False, empty=pinned_empty)      # pinned result buffers, reused every step
+    sw.get_state(with_E_a=False, out=host)
     full = dict(cs)
     # trait-indexed members of set_state are given for all p traits and sliced per rank; keep them pinned
     for nm in ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "B"):
@@ -340,7 +346,7 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 5))
     h2d = 8 * (3 * sw.pl * k + 2 * n * k + sw.b * sw.pl + 2 * sw.pl + 3 * k)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
     d2h = 8 * (3 * sw.pl * k + n * k + n * k + k + sw.b * sw.pl + 2 * sw.pl + 2 * k)
-    sw.set_state(full); sw.sweep(1); sw.get_state(with_E_a=False)         # warm the path
+    sw.set_state(full); sw.sweep(1); sw.get_state(with_E_a=False, out=host)         # warm the path
     barrier()
     t0 = time.perf_counter()
     e2e_parts = [0.0, 0.0, 0.0]
@@ -350,7 +356,7 @@ def run_ours(args):
         tb = time.perf_counter()
         sw.sweep(1)
         tc = time.perf_counter()
-        out = sw.get_state(with_E_a=False)
+        out = sw.get_state(with_E_a=False, out=host)
         td = time.perf_counter()
         e2e_parts[0] += tb - ta; e2e_parts[1] += tc - tb; e2e_parts[2] += td - tc
         full.update({nm: out[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})   # replicated members carry over
@@ -358,8 +364,50 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = e2e_steps / e2e_s
 
-    if rank != 0:
+    npairs = k * (k + 1) // 2
+    if gstats["mode"] == "expsum":
+        # dominant tensor kernel: the trait product Q = (G'A)' E, M = k(k+1)/2, N = p_local, K = R nodes
+        kern_flop = 2 * npairs * gstats["terms"] * sw.pl
+        kern_ms = gstats["ms_traits"]
+        kern_name = (f"dgemm_tn_kernel<128,128,6> (exponential-sum weighted Gram, trait product Q = (G'A)'E: "
+                     f"M=k(k+1)/2={npairs}, N=p_local={sw.pl}, K=R={gstats['terms']})")
+    else:
+        kern_flop = k * (k + 1) * n * sw.pl
+        kern_ms = phases["lambda"]
+        kern_name = "dgemm_tn_kernel<128,128,6> (exact weighted Gram Q = G'W, M=k(k+1)/2, N=p_local, K=n)"
+    achieved = kern_flop / (kern_ms * 1e-3) * 1e-12 if kern_ms > 0 else None
+    traffic = None
+    if os.path.exists(NCU_SUMMARY_FILE):
+        try:
+            traffic = json.load(open(NCU_SUMMARY_FILE)).get("dram_bytes_per_launch_" + gstats["mode"])
+        except Exception:
+            traffic = None
+
+    # ---- the exact (reference-order) Gram evaluation, timed beside the default: the full-size DMMA GEMM -------
+    exact_leg = None
+    if gstats["mode"] != "exact" and not args.no_exact_leg:
         sw.close()
+        sw = None
+        ex = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k, seed=20131, rank=rank, world=world, nccl_id=None if world == 1 else
+                       bcast_obj(BSFGSweep.nccl_unique_id() if rank == 0 else None), gram="exact")
+        ex.set_state(cs)
+        ex.sweep(3)
+        barrier()
+        ex.sweep(3)
+        barrier()
+        ex_ms, _, ex_ph = ex.timing()
+        ex_ms = max_over_ranks(ex_ms)
+        ex_flop = k * (k + 1) * n * ex.pl
+        ex_ach = ex_flop / (ex_ph["lambda"] * 1e-3) * 1e-12
+        exact_leg = {"value": 3 / (ex_ms * 1e-3), "unit": "iter/s", "ms_per_step": ex_ms / 3,
+                     "roofline": {"bound": "tensor", "achieved": ex_ach, "unit": "TFLOP/s",
+                                  "kernel": "dgemm_tn_kernel<128,128,6> (exact weighted Gram Q = G'W, M=k(k+1)/2, N=p_local, K=n)",
+                                  "flop_per_launch": ex_flop, "ms_per_launch": ex_ph["lambda"]}}
+        ex.close()
+
+    if rank != 0:
+        if sw is not None:
+            sw.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -369,14 +417,9 @@ def run_ours(args):
         pk = json.load(open(FP64_PEAK_FILE))
         peak_tf = float(pk.get("dgemm_8192_sustained_tflops", peak_tf))
         peak_src = "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json; MEASURED_PEAKS.json has no FP64 entry)"
-    gram_flop = k * (k + 1) * n * sw.pl
-    achieved = gram_flop / (gram_ms * 1e-3) * 1e-12 if gram_ms > 0 else None
-    traffic = None
-    if os.path.exists(NCU_SUMMARY_FILE):
-        try:
-            traffic = json.load(open(NCU_SUMMARY_FILE)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    if exact_leg:
+        exact_leg["roofline"]["peak"] = peak_tf
+        exact_leg["roofline"]["frac"] = exact_leg["roofline"]["achieved"] / peak_tf
     line = {
         "metric": "Gibbs iter/sec at n=5000,p=20000,k=100 (1/2/4/8 B200) vs Rcpp host" if args.workload == "C4"
                   else f"Gibbs iter/sec at n={n},p={p},k={k}",
@@ -388,26 +431,32 @@ def run_ours(args):
                    "parallelism": f"trait-shard x{world}", "l2": "inputs larger than L2 (rotated data 2.4 GB/rank-set, "
                    "Gram operands 1 GB) -- no explicit flush", "formulation": mode,
                    "diag_identity_residuals": [r1, r2], "update_k": "gated off by i<=200 (uu still drawn)",
+                   "gram": {kk: gstats[kk] for kk in ("mode", "terms", "step", "fallbacks", "c_min", "c_max")},
                    "rng": "device Philox4x32-10", "setup_s": round(t_setup, 1), "wall_s_timed_region": round(wall, 3)},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": f"{e2e_steps} x [set_state(pinned host current_state) -> bsfg_sweep(1) -> get_state(posterior-sample fields)]; "
+                "what": f"{e2e_steps} x [set_state(pinned host current_state) -> bsfg_sweep(1) -> get_state(posterior-sample fields, pinned)]; "
                         "E_a (r x p) is resampled before use and only read back on request",
                 "ms_per_step_parts": {"set_state_h2d": 1e3 * e2e_parts[0] / e2e_steps, "sweep": 1e3 * e2e_parts[1] / e2e_steps,
                                       "get_state_d2h": 1e3 * e2e_parts[2] / e2e_steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
-                     "kernel": "dgemm_tn_kernel<128,128,6> (weighted Gram Q = G'W, M=k(k+1)/2, N=p_local, K=n)",
-                     "flop_per_launch": gram_flop, "ms_per_launch": gram_ms, "peak_source": peak_src,
+                     "kernel": kern_name,
+                     "flop_per_launch": kern_flop, "ms_per_launch": kern_ms, "peak_source": peak_src,
                      "dmma_issue_peak_tflops": 37.1},
         "phases_ms_last_iter": phases,
-        "sweep_achieved_tflops": algorithmic_flops(n, p, k) / world / (dev_ms / args.steps * 1e-3) * 1e-12,
+        "sweep_algorithmic_tflops": algorithmic_flops(n, p, k) / world / (dev_ms / args.steps * 1e-3) * 1e-12,
+        "sweep_algorithmic_tflops_note": "SURVEY.md 8d W_flop of the exact formulation (k(k+1)np weighted Gram) per GPU / time; in expsum "
+                                         "mode fewer FLOPs are executed, so this can exceed the FP64 peak",
     }
+    if exact_leg:
+        line["exact_gram"] = exact_leg
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(data, rv, priors, rp, cs, n, p, k, args.cpu_sample_traits)
     print(json.dumps(line), flush=True)
-    sw.close()
+    if sw is not None:
+        sw.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -443,6 +492,9 @@ def main():
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-traits", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gram", default="default", choices=["default", "expsum", "exact"],
+                    help="weighted-Gram evaluation of the Lambda draw (DESIGN.md section 3a)")
+    ap.add_argument("--no-exact-leg", action="store_true", help="skip the extra exact-Gram timing beside the default")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

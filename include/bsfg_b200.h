@@ -224,9 +224,10 @@ int bsfg_sweep_injected(bsfg_ctx* ctx, const bsfg_variates* v);
  * ||U2' P U2 - diag(s1)||_max, ||Design_U' Design_U - diag(s2)||_max that drove the choice.        */
 int bsfg_get_mode(bsfg_ctx* ctx, int* mode, double* resid_s1, double* resid_s2);
 /* weighted-Gram evaluation in use, number of iterations that fell back to the exact GEMM because the exponential
- * sum could not cover the range of E_a_prec/resid_Y_prec, and that range at the last iteration.                    */
+ * sum could not cover the range of E_a_prec/resid_Y_prec, that range at the last iteration, and (expsum mode) the
+ * device milliseconds of the two GEMMs of the last timed iteration: G'A (nodes) and (G'A)'E (traits).              */
 int bsfg_get_gram_stats(bsfg_ctx* ctx, int* mode, int* terms, double* step, long long* fallbacks,
-                        double* c_min, double* c_max);
+                        double* c_min, double* c_max, double* ms_nodes, double* ms_traits);
 /* timing of the last bsfg_sweep call: total device milliseconds (CUDA events on the sweep stream),
  * kernel launches issued, and per-phase milliseconds (array of BSFG_N_PHASES doubles, may be NULL) */
 #define BSFG_N_PHASES 12

@@ -45,6 +45,14 @@ const char* get_last_error();
 
 #define BSFG_CHECK_LAUNCH() BSFG_CUDA(cudaGetLastError())
 
+// cudaMemset runs on the legacy default stream and may return before the fill has happened; the library works on a
+// non-blocking stream, which the legacy stream does NOT order against.  Every allocation-time clear therefore waits
+// for the fill, or a later kernel/copy on the library stream could be overwritten by a late memset.
+inline void memset_sync(void* p, int value, size_t bytes) {
+    BSFG_CUDA(cudaMemset(p, value, bytes));
+    BSFG_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+}
+
 inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
@@ -80,7 +88,7 @@ struct DMat {
         size_t bytes = sizeof(double) * (size_t)ld * (size_t)(c > 0 ? c : 1);
         BSFG_CUDA(cudaMalloc(&p, bytes));
         owner = true;
-        BSFG_CUDA(cudaMemset(p, 0, bytes));
+        memset_sync(p, 0, bytes);
     }
     // capacity-preserving logical resize (cols only); used for factor-indexed state under update_k
     size_t bytes() const { return sizeof(double) * (size_t)ld * (size_t)(cols > 0 ? cols : 1); }
@@ -115,7 +123,7 @@ struct DVec {
         n = n_;
         size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
         BSFG_CUDA(cudaMalloc(&p, bytes));
-        BSFG_CUDA(cudaMemset(p, 0, bytes));
+        memset_sync(p, 0, bytes);
     }
     void upload(const double* host, cudaStream_t st) {
         if (n) BSFG_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -184,15 +192,30 @@ struct RngStream {
     uint32_t iter;
 };
 
-// N(0,1) for element `idx` of a stream (Box-Muller on one Philox block; element-addressed so
-// the value is independent of launch geometry)
+// N(0,1) for element `idx` of a stream: elements 2q and 2q+1 are the cosine and sine branches of one Box-Muller
+// transform on Philox block q, so a thread that owns an aligned pair pays for one block; element-addressed, so the
+// value is independent of launch geometry and of how traits are sharded.
+__host__ __device__ inline void philox_normal_pair(const RngStream& s, uint64_t pair, double* z_even, double* z_odd) {
+    Philox ph(s.seed);
+    uint32_t o[4];
+    ph((uint32_t)pair, (uint32_t)(pair >> 32), s.site, s.iter, o);
+    const double u1 = u01_from_bits(o[0], o[1]);
+    const double u2 = u01_from_bits(o[2], o[3]);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    *z_even = r * cs;
+    *z_odd = r * sn;
+}
 __host__ __device__ inline double philox_normal(const RngStream& s, uint64_t idx) {
     Philox ph(s.seed);
     uint32_t o[4];
-    ph((uint32_t)idx, (uint32_t)(idx >> 32), s.site, s.iter, o);
-    double u1 = u01_from_bits(o[0], o[1]);
-    double u2 = u01_from_bits(o[2], o[3]);
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    const uint64_t pair = idx >> 1;
+    ph((uint32_t)pair, (uint32_t)(pair >> 32), s.site, s.iter, o);
+    const double u1 = u01_from_bits(o[0], o[1]);
+    const double u2 = u01_from_bits(o[2], o[3]);
+    const double r = sqrt(-2.0 * log(u1));
+    return (idx & 1) ? r * sinpi(2.0 * u2) : r * cospi(2.0 * u2);
 }
 
 __host__ __device__ inline double philox_uniform(const RngStream& s, uint64_t idx) {

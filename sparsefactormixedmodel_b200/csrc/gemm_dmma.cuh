@@ -220,18 +220,32 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         return;
     }
+    // beta != 0: the 16 Cin values of one 8-column fragment strip are loaded as one batch before any of them is
+    // used, so 16 independent 8-byte loads per thread are in flight (a load->FMA->store chain per element made the
+    // K = k products, which are all epilogue, 2.5x slower).
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int m = m0 + wm0 + 8 * i + gq;
-        if (m >= g.M) continue;
+    for (int j = 0; j < 4; j++) {
+        double cin[8][2];
+        if (g.Cin) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+            for (int i = 0; i < 8; i++) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int m = m0 + wm0 + 8 * i + gq;
+                    const int n = n0 + wn0 + 8 * j + 2 * q + c;
+                    cin[i][c] = (m < g.M && n < g.N) ? g.Cin[(size_t)n * g.ldcin + m] : 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
 #pragma unroll
             for (int c = 0; c < 2; c++) {
+                const int m = m0 + wm0 + 8 * i + gq;
                 const int n = n0 + wn0 + 8 * j + 2 * q + c;
-                if (n < g.N) {
+                if (m < g.M && n < g.N) {
                     double v = g.alpha * acc[i][j][c];
-                    if (g.Cin) v += g.beta * g.Cin[(size_t)n * g.ldcin + m];
+                    if (g.Cin) v += g.beta * cin[i][c];
                     g.C[(size_t)n * g.ldc + m] = v;
                 }
             }

@@ -114,17 +114,25 @@ __global__ void lambda_weights_kernel(const double* __restrict__ UtY, long ldy, 
                                       const double* __restrict__ B, long ldb, int b,
                                       double* __restrict__ W, long ldw, const int* __restrict__ need_w,
                                       double* __restrict__ WY, long ldwy) {
-    const int j = blockIdx.y;
+    const int j = blockIdx.x;                      // one CTA per trait: 400 K 256-element blocks were latency bound
     if (j >= p) return;
     const bool write_w = W && (!need_w || *need_w != 0);
     const double epj = ep[j];
     const double c = epj / rp[j];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double w = epj / (s[i] + c);
-        double y = UtY[(long)j * ldy + i];
-        for (int cc = 0; cc < b; cc++) y -= UtX[(long)cc * ldx + i] * B[(long)j * ldb + cc];
+    double bj[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int cc = 0; cc < b && cc < 4; cc++) bj[cc] = B[(long)j * ldb + cc];
+    const double* __restrict__ ycol = UtY + (long)j * ldy;
+    double* __restrict__ wycol = WY + (long)j * ldwy;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double w = epj / (s[i] + c);
+        double y = ycol[i];
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++)
+            if (cc < b) y -= UtX[(long)cc * ldx + i] * bj[cc];
+        for (int cc = 4; cc < b; cc++) y -= UtX[(long)cc * ldx + i] * B[(long)j * ldb + cc];
         if (write_w) W[(long)j * ldw + i] = w;
-        WY[(long)j * ldwy + i] = w * y;
+        wycol[i] = w * y;
     }
 }
 
@@ -317,15 +325,31 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
     double acc[MEANS_BMAX];
 #pragma unroll
     for (int c = 0; c < MEANS_BMAX; c++) acc[c] = 0.0;
-    for (int i = threadIdx.x; i < br; i += blockDim.x) {
-        const double d = s1[i] * epj + s2[i] * rpj;
-        const double mean = (DtYt[(long)j * ldd + i] * rpj) / d;
-        const double th = mean + var_normal(zsrc, i, j) / sqrt(d);
-        theta[(long)j * ldt + i] = th;
-        if (Bout) {
+    // each thread owns Philox-aligned element pairs (rows r0, r0+1 with an even stream index) -> one block per 2 draws
+    const long base = zsrc.ptr ? 0 : (long)(j + zsrc.col_offset) * zsrc.rows_total;
+    const int par = (int)(base & 1);
+    for (int t = threadIdx.x; 2 * t - par < br; t += blockDim.x) {
+        const int r0 = 2 * t - par;
+        double z[2];
+        if (zsrc.ptr) {
+            z[0] = (r0 >= 0) ? zsrc.ptr[(long)j * zsrc.ld + r0] : 0.0;
+            z[1] = (r0 + 1 < br) ? zsrc.ptr[(long)j * zsrc.ld + r0 + 1] : 0.0;
+        } else {
+            philox_normal_pair(zsrc.rs, (uint64_t)((base + r0) >> 1), &z[0], &z[1]);
+        }
 #pragma unroll
-            for (int c = 0; c < MEANS_BMAX; c++)
-                if (c < b) acc[c] += Ut[(long)c * ldu + i] * th;
+        for (int e = 0; e < 2; e++) {
+            const int i = r0 + e;
+            if (i < 0 || i >= br) continue;
+            const double d = s1[i] * epj + s2[i] * rpj;
+            const double mean = (DtYt[(long)j * ldd + i] * rpj) / d;
+            const double th = mean + z[e] / sqrt(d);
+            theta[(long)j * ldt + i] = th;
+            if (Bout) {
+#pragma unroll
+                for (int c = 0; c < MEANS_BMAX; c++)
+                    if (c < b) acc[c] += Ut[(long)c * ldu + i] * th;
+            }
         }
     }
     if (Bout) {
@@ -542,44 +566,62 @@ __global__ void delta_colsum_kernel(const double* __restrict__ LP, long ldp, con
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) colsum[h] = acc;
 }
-// the scalar recursion; one thread.  Loop order = R's 2:(k-1) (counts down when k == 2).
-__global__ void delta_recursion_kernel(double* __restrict__ delta, int k, const double* __restrict__ colsum,
+// the recursion of BSFG_functions.R:286-306, one warp, delta/tauh/colsum staged in shared memory.  After delta[h]
+// changes, R recomputes tauh = cumprod(delta); entries l < h are unchanged and entries l >= h scale by new/old, which
+// is what the lanes apply (relative rounding difference <= k ulp, far inside the 1e-9 contract); the tauh written
+// out at the end is the plain sequential cumprod of the final delta.  The draws stay sequential.
+// Loop order = R's 2:(k-1) (counts down when k == 2).  Shared memory: 3k doubles.
+__global__ void delta_recursion_kernel(double* __restrict__ delta_g, int k, const double* __restrict__ colsum_g,
                                        double n_genes, double d1s, double d1r, double d2s, double d2r,
                                        VarSrc gsrc, double* __restrict__ tauh_out, double* __restrict__ shapes,
                                        double* __restrict__ rates, int* __restrict__ ndraws) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    extern __shared__ double tauh[];
-    double cp = 1.0;
-    for (int h = 0; h < k; h++) { cp *= delta[h]; tauh[h] = cp; }
-    int draw = 0;
-    {
-        const double shape = d1s + 0.5 * n_genes * k;
-        double acc = 0.0;
-        for (int h = 0; h < k; h++) acc += tauh[h] * colsum[h];
-        const double rate = d1r + 0.5 * (1.0 / delta[0]) * acc;
-        if (shapes) shapes[draw] = shape;
-        if (rates) rates[draw] = rate;
-        delta[0] = var_gamma(gsrc, draw, 0, shape) / rate;
-        draw++;
-        cp = 1.0;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    extern __shared__ double dsm[];
+    double* tauh = dsm;
+    double* delta = dsm + k;
+    double* colsum = dsm + 2 * k;
+    const int lane = threadIdx.x;
+    for (int h = lane; h < k; h += 32) { delta[h] = delta_g[h]; colsum[h] = colsum_g[h]; }
+    __syncwarp();
+    if (lane == 0) {
+        double cp = 1.0;
         for (int h = 0; h < k; h++) { cp *= delta[h]; tauh[h] = cp; }
     }
+    __syncwarp();
+    auto tail_sum = [&](int from) {              // sum_{l >= from} tauh[l] * colsum[l]
+        double acc = 0.0;
+        for (int l = from + lane; l < k; l += 32) acc += tauh[l] * colsum[l];
+        return warp_sum(acc);
+    };
+    auto redraw = [&](int h0, double shape, double prior_rate, int draw) {   // 0-based h0
+        const double ts = tail_sum(h0);
+        const double old = delta[h0];
+        const double rate = prior_rate + 0.5 * (1.0 / old) * ts;
+        const double dnew = var_gamma(gsrc, draw, 0, shape) / rate;          // same value on every lane
+        const double ratio = dnew / old;
+        __syncwarp();
+        for (int l = h0 + lane; l < k; l += 32) tauh[l] *= ratio;
+        if (lane == 0) {
+            delta[h0] = dnew;
+            if (shapes) shapes[draw] = shape;
+            if (rates) rates[draw] = rate;
+        }
+        __syncwarp();
+    };
+    int draw = 0;
+    redraw(0, d1s + 0.5 * n_genes * k, d1r, draw++);
     const int hi = k - 1;
     const int step = (hi >= 2) ? 1 : -1;
-    for (int h = 2; (step > 0) ? (h <= hi) : (h >= hi); h += step) {   // 1-based h
-        const double shape = d2s + 0.5 * n_genes * (k - h + 1);
-        double acc = 0.0;
-        for (int l = h - 1; l < k; l++) acc += tauh[l] * colsum[l];
-        const double rate = d2r + 0.5 * (1.0 / delta[h - 1]) * acc;
-        if (shapes) shapes[draw] = shape;
-        if (rates) rates[draw] = rate;
-        delta[h - 1] = var_gamma(gsrc, draw, 0, shape) / rate;
-        draw++;
-        cp = 1.0;
-        for (int l = 0; l < k; l++) { cp *= delta[l]; tauh[l] = cp; }
+    for (int h = 2; (step > 0) ? (h <= hi) : (h >= hi); h += step)       // 1-based h
+        redraw(h - 1, d2s + 0.5 * n_genes * (k - h + 1), d2r, draw++);
+    for (int h = lane; h < k; h += 32) delta_g[h] = delta[h];
+    if (lane == 0) {
+        if (tauh_out) {
+            double cp = 1.0;
+            for (int h = 0; h < k; h++) { cp *= delta[h]; tauh_out[h] = cp; }
+        }
+        if (ndraws) *ndraws = draw;
     }
-    if (tauh_out) for (int h = 0; h < k; h++) tauh_out[h] = tauh[h];
-    if (ndraws) *ndraws = draw;
 }
 
 }  // namespace bsfg

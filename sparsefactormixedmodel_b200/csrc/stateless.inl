@@ -24,7 +24,7 @@ struct Device {
         BSFG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         ws.alloc(WS_DOUBLES);
         BSFG_CUDA(cudaMalloc(&d_flag, sizeof(int)));
-        BSFG_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
+        memset_sync(d_flag, 0, sizeof(int));
     }
     void sync() { BSFG_CUDA(cudaStreamSynchronize(st)); }
     // C = alpha * At' * B + beta * C
@@ -175,7 +175,10 @@ struct LambdaScratch {
     ExpSumPlan* plan = nullptr;
     int* need_exact = nullptr;
     unsigned long long* fallbacks = nullptr;
+    cudaEvent_t ev_sub[2] = {nullptr, nullptr};   // after the node product G'A, after the trait product (before the no-op fallback)
+    bool sub_timed = false;
     ~LambdaScratch() {
+        for (auto& e : ev_sub) if (e) cudaEventDestroy(e);
         if (plan) cudaFree(plan);
         if (need_exact) cudaFree(need_exact);
         if (fallbacks) cudaFree(fallbacks);
@@ -193,11 +196,12 @@ struct LambdaScratch {
         }
         if (!plan) {
             BSFG_CUDA(cudaMalloc(&plan, sizeof(ExpSumPlan)));
-            BSFG_CUDA(cudaMemset(plan, 0, sizeof(ExpSumPlan)));
+            memset_sync(plan, 0, sizeof(ExpSumPlan));
             BSFG_CUDA(cudaMalloc(&need_exact, sizeof(int)));
-            BSFG_CUDA(cudaMemset(need_exact, 0, sizeof(int)));
+            memset_sync(need_exact, 0, sizeof(int));
             BSFG_CUDA(cudaMalloc(&fallbacks, sizeof(unsigned long long)));
-            BSFG_CUDA(cudaMemset(fallbacks, 0, sizeof(unsigned long long)));
+            memset_sync(fallbacks, 0, sizeof(unsigned long long));
+            for (auto& e : ev_sub) BSFG_CUDA(cudaEventCreate(&e));
         }
     }
 };
@@ -221,9 +225,8 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     {
-        dim3 grid(std::min(ceil_div(n, 256), 64), p);
         const int b = UtX ? (int)UtX->cols : 0;
-        lambda_weights_kernel<<<grid, 256, 0, d.st>>>(UtY.p, UtY.ld, n, p, s, rp, ep, UtX ? UtX->p : nullptr,
+        lambda_weights_kernel<<<p, 256, 0, d.st>>>(UtY.p, UtY.ld, n, p, s, rp, ep, UtX ? UtX->p : nullptr,
                                                       UtX ? UtX->ld : 0, B ? B->p : nullptr, B ? B->ld : 0, b,
                                                       sc.W.p, sc.W.ld, expsum ? sc.need_exact : nullptr, sc.WY.p, sc.WY.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
@@ -238,7 +241,9 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
     if (ev) BSFG_CUDA(cudaEventRecord(ev[0], d.st));
     if (expsum) {
         d.gemm(1.0, sc.A, sc.Gt, 0.0, sc.Ht);      // Ht[m, pair] = sum_i A[i,m] f_ia f_ib
+        if (ev) BSFG_CUDA(cudaEventRecord(sc.ev_sub[0], d.st));
         d.gemm(1.0, sc.Ht, sc.E, 0.0, sc.Q);       // Q[pair, j]  = sum_m Ht[m,pair] E[m,j]
+        if (ev) { BSFG_CUDA(cudaEventRecord(sc.ev_sub[1], d.st)); sc.sub_timed = true; }
         // exact fallback: a no-op launch unless the plan kernel raised need_exact
         dgemm_tn(d.st, d.sms, np, p, n, 1.0, sc.Gt.p, sc.Gt.ld, sc.W.p, sc.W.ld, 0.0, nullptr, 0, sc.Q.p, sc.Q.ld,
                  nullptr, 0, sc.need_exact);
@@ -577,7 +582,7 @@ extern "C" int bsfg_sample_delta_c(const double* delta, const double* tauh, int 
     delta_colsum_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, L2.p, L2.ld, p, k, 0, colsum.p);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     VarSrc gs = make_var(g ? &dG : nullptr, seed, SITE_G_DELTA, 0, 0, k);
-    delta_recursion_kernel<<<1, 32, sizeof(double) * k, d.st>>>(dd.p, k, colsum.p, (double)p, delta_1_shape, delta_1_rate,
+    delta_recursion_kernel<<<1, 32, 3 * sizeof(double) * k, d.st>>>(dd.p, k, colsum.p, (double)p, delta_1_shape, delta_1_rate,
                                                                delta_2_shape, delta_2_rate, gs, nullptr, shapes.p, rates.p, d_nd);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     dd.download(delta_out, d.st);

@@ -273,7 +273,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
                                               c->colsum_cnt.p + c->kmax);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     allreduce(c, c->colsum_cnt.p, (size_t)2 * c->kmax);
-    delta_recursion_kernel<<<1, 32, sizeof(double) * k, d.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
+    delta_recursion_kernel<<<1, 32, 3 * sizeof(double) * k, d.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
                                                                c->pri.delta_1_shape, c->pri.delta_1_rate,
                                                                c->pri.delta_2_shape, c->pri.delta_2_rate, v.gD, c->tauh.p,
                                                                c->delta_shapes.p, c->delta_rates.p, c->d_ndraws);
@@ -580,7 +580,7 @@ extern "C" int bsfg_get_mode(bsfg_ctx* c, int* mode, double* resid_s1, double* r
 }
 
 extern "C" int bsfg_get_gram_stats(bsfg_ctx* c, int* mode, int* terms, double* step, long long* fallbacks,
-                                   double* c_min, double* c_max) {
+                                   double* c_min, double* c_max, double* ms_nodes, double* ms_traits) {
     BSFG_API_BEGIN
     REQUIRE_PTR(c);
     if (mode) *mode = c->gram.mode;
@@ -597,6 +597,15 @@ extern "C" int bsfg_get_gram_stats(bsfg_ctx* c, int* mode, int* terms, double* s
     if (fallbacks) *fallbacks = (long long)fb;
     if (c_min) *c_min = pl.c_min;
     if (c_max) *c_max = pl.c_max;
+    // split of the last timed iteration's "lambda" phase (expsum mode): G'A over the n individuals, then (G'A)'E over the traits
+    float t_nodes = 0, t_traits = 0;
+    if (c->lsc.sub_timed && c->gram.mode == GRAM_EXPSUM) {
+        c->dev.sync();
+        BSFG_CUDA(cudaEventElapsedTime(&t_nodes, c->ev_phase[1], c->lsc.ev_sub[0]));
+        BSFG_CUDA(cudaEventElapsedTime(&t_traits, c->lsc.ev_sub[0], c->lsc.ev_sub[1]));
+    }
+    if (ms_nodes) *ms_nodes = t_nodes;
+    if (ms_traits) *ms_traits = t_traits;
     BSFG_API_END
 }
 

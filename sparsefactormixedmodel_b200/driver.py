@@ -150,25 +150,32 @@ class BSFGSweep:
         st.nrun = int(cs.get("nrun", 0))
         check(self.lib.bsfg_set_state(self._ctx, C.byref(st)))
 
-    def get_state(self, with_E_a=True):
+    def get_state(self, with_E_a=True, out=None):
         """Download this rank's shard of `current_state` (same field names; trait-indexed members cover
-        columns [lo, hi) only)."""
+        columns [lo, hi) only).  `out`: dict of preallocated F-ordered arrays from `alloc_state` to fill in place
+        (e.g. pinned host memory); valid while k is unchanged."""
         probe = _lib.bsfg_state()
         check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))     # all-NULL call: just k and nrun
         k = probe.k
-        out = dict(Lambda=np.zeros((self.pl, k), order="F"), Lambda_prec=np.zeros((self.pl, k), order="F"),
-                   Plam=np.zeros((self.pl, k), order="F"), F=np.zeros((self.n, k), order="F"),
-                   F_a=np.zeros((self.r, k), order="F"), F_h2=np.zeros(k), B=np.zeros((self.b, self.pl), order="F"),
-                   resid_Y_prec=np.zeros(self.pl), E_a_prec=np.zeros(self.pl), delta=np.zeros(k), tauh=np.zeros(k))
-        if with_E_a:
-            out["E_a"] = np.zeros((self.r, self.pl), order="F")
+        if out is None or out["F"].shape[1] != k:
+            out = self.alloc_state(k, with_E_a)
         st = _lib.bsfg_state()
         for name in _STATE_FIELDS:
-            if name in out and out[name].size:
+            if name in out and out[name] is not None and out[name].size:
                 setattr(st, name, ptr(out[name]))
         check(self.lib.bsfg_get_state(self._ctx, C.byref(st)))
         out["nrun"] = st.nrun
         out["W"] = np.zeros((0, self.pl)); out["W_prec"] = np.zeros(self.pl)
+        return out
+
+    def alloc_state(self, k, with_E_a=True, empty=None):
+        """Host buffers for get_state; `empty(shape)` may return pinned F-ordered float64 arrays."""
+        mk = empty or (lambda shape: np.zeros(shape, order="F"))
+        out = dict(Lambda=mk((self.pl, k)), Lambda_prec=mk((self.pl, k)), Plam=mk((self.pl, k)), F=mk((self.n, k)),
+                   F_a=mk((self.r, k)), F_h2=mk((k,)), B=mk((self.b, self.pl)), resid_Y_prec=mk((self.pl,)),
+                   E_a_prec=mk((self.pl,)), delta=mk((k,)), tauh=mk((k,)))
+        if with_E_a:
+            out["E_a"] = mk((self.r, self.pl))
         return out
 
     # -- sweeping --------------------------------------------------------------------------
@@ -218,9 +225,11 @@ class BSFGSweep:
 
     def gram_stats(self):
         m = C.c_int(0); t = C.c_int(0); h = C.c_double(0); fb = C.c_longlong(0); lo = C.c_double(0); hi = C.c_double(0)
-        check(self.lib.bsfg_get_gram_stats(self._ctx, C.byref(m), C.byref(t), C.byref(h), C.byref(fb), C.byref(lo), C.byref(hi)))
+        tn = C.c_double(0); tt = C.c_double(0)
+        check(self.lib.bsfg_get_gram_stats(self._ctx, C.byref(m), C.byref(t), C.byref(h), C.byref(fb), C.byref(lo), C.byref(hi),
+                                           C.byref(tn), C.byref(tt)))
         return dict(mode={1: "exact", 2: "expsum"}.get(m.value, "?"), terms=t.value, step=h.value, fallbacks=fb.value,
-                    c_min=lo.value, c_max=hi.value)
+                    c_min=lo.value, c_max=hi.value, ms_nodes=tn.value, ms_traits=tt.value)
 
     def timing(self):
         t = C.c_double(0); n = C.c_longlong(0)
