@@ -101,10 +101,16 @@ struct GemmSmem {
 };
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int BM, int BN, int STAGES>
+// WM = warps along M (the other 8/WM along N).  WM = 2: 64 x 32 warp tiles, the only layout instantiated (gemm_host.inl
+// records why the all-rows / all-columns layouts for M = k or N = k products are not used).
+template <int BM, int BN, int STAGES, int WM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
     static_assert(BM == 128 && BN == 128, "warp layout below is written for 128x128 CTA tiles");
+    static_assert(WM == 1 || WM == 2 || WM == 8, "supported warp layouts");
+    constexpr int WN = GEMM_CONSUMERS / WM;
+    constexpr int FM = (BM / 8) / WM;      // 8-row fragments per warp
+    constexpr int FN = (BN / 8) / WN;      // 8-column fragments per warp
     using S = GemmSmem<BM, BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     if (g.run_if && *g.run_if == 0) return;        // uniform across the grid: a conditional launch (exact-Gram fallback)
@@ -144,14 +150,14 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== DMMA consumers =====================
     const int gq = lane >> 2;      // row inside an 8x8 fragment (0..7)
     const int q = lane & 3;        // k slot (0..3)
-    const int wm0 = (warp & 1) * 64;
-    const int wn0 = (warp >> 1) * 32;
+    const int wm0 = (warp % WM) * (FM * 8);
+    const int wn0 = (warp / WM) * (FN * 8);
 
-    double acc[8][4][2];
+    double acc[FM][FN][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < FM; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // byte offset inside a 128-byte row for k-step j: chunk = j + 4*(q>>1), swizzled by (row&7)==gq
     uint32_t koff[4];
@@ -187,15 +193,17 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sbase = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            double a[8], b[4];
+            double a[FM], b[FN];
 #pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = lds_f64(sbase + a_row + i * 8 * 128 + koff[j]);
+            for (int i = 0; i < FM; i++) a[i] = lds_f64(sbase + a_row + i * 8 * 128 + koff[j]);
 #pragma unroll
-            for (int i = 0; i < 4; i++) b[i] = lds_f64(sbase + b_row + i * 8 * 128 + koff[j]);
+            for (int i = 0; i < FN; i++) b[i] = lds_f64(sbase + b_row + i * 8 * 128 + koff[j]);
+            // fragments beyond the matrix edge multiply TMA zero fill: skipping them (predicated DMMAs) was measured
+            // slower than issuing them, because the other warps of the CTA do the full work anyway
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < FM; i++)
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
+                for (int jj = 0; jj < FN; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -206,11 +214,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (g.splits > 1) {
         double* ws = g.ws + (size_t)split * (size_t)g.M * (size_t)g.N;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < FM; i++) {
             const int m = m0 + wm0 + 8 * i + gq;
             if (m >= g.M) continue;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < FN; j++) {
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     const int n = n0 + wn0 + 8 * j + 2 * q + c;
@@ -224,11 +232,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // used, so 16 independent 8-byte loads per thread are in flight (a load->FMA->store chain per element made the
     // K = k products, which are all epilogue, 2.5x slower).
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        double cin[8][2];
+    for (int j = 0; j < FN; j++) {
+        double cin[FM][2];
         if (g.Cin) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < FM; i++) {
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     const int m = m0 + wm0 + 8 * i + gq;
@@ -238,7 +246,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < FM; i++) {
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 const int m = m0 + wm0 + 8 * i + gq;

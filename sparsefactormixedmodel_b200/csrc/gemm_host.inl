@@ -45,8 +45,7 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     if (K <= 0) fail(BSFG_ESHAPE, "dgemm_tn: K must be positive");
     static bool attr_set = false;
     if (!attr_set) {
-        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<128, 128, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       GemmCfg::TOTAL));
+        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<128, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg::TOTAL));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
@@ -71,10 +70,11 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     int splits = 1;
     if (ws) {
         const double per = (double)M * (double)N;
+        const double kt_us = 2.1;
         auto cost = [&](int s) {
             const long ctas = (long)tiles * s;
             const double waves = (double)((ctas + sm_count - 1) / sm_count);
-            double c = waves * (ceil_div(ktiles, s) * 2.1 + 8.0);
+            double c = waves * (ceil_div(ktiles, s) * kt_us + 8.0);
             if (s > 1) c += 16e-6 * s * per / 5.0 + 5.0;
             return c;
         };
@@ -90,7 +90,10 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     g.splits = splits;
     g.ws = ws;
     dim3 grid(tiles, splits);
-    dgemm_tn_kernel<128, 128, GEMM_STAGES><<<grid, GEMM_THREADS, GemmCfg::TOTAL, st>>>(tmA, tmB, g);
+    // WM = 2 (64 x 32 warp tiles) for every shape: the all-rows / all-columns layouts (WM = 1 / 8) that skip the empty
+    // fragments of M = k or N = k products evenly were measured SLOWER on B200 (sweep 13.3 -> 14.0 ms at C4: 18 instead
+    // of 12 fragment loads per 32 DMMAs and a predicated DMMA sequence), so they are not instantiated.
+    dgemm_tn_kernel<128, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, GemmCfg::TOTAL, st>>>(tmA, tmB, g);
     BSFG_CHECK_LAUNCH();
     g_launch_counter++;
     if (splits > 1) {
