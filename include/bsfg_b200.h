@@ -147,6 +147,7 @@ typedef struct bsfg_config {
     int gram_mode;
     int gram_terms;
     double gram_step;
+    int r2;                  /* ncol(Z_2): levels of the second random effect W (0: none)          */
 } bsfg_config;
 
 typedef struct bsfg_priors {           /* model_setup.R:49-63, fast_BSFG_sampler_init.R:114 */
@@ -157,6 +158,7 @@ typedef struct bsfg_priors {           /* model_setup.R:49-63, fast_BSFG_sampler
     double b_X_prec;                   /* scalar on the diagonal of priors$b_X_prec */
     const double* h2_priors_factors;   /* h2_divisions entries */
     double b0, b1, epsilon, prop;      /* run_parameters used by update_k */
+    double W_prec_shape, W_prec_rate;  /* second random effect (model_setup.R:53-54); used when r2 > 0 */
 } bsfg_priors;
 
 /* Constants of one chain (host pointers; Y and everything trait-indexed holds THIS RANK's columns):
@@ -171,6 +173,12 @@ typedef struct bsfg_constants {
     const double* U2; const double* s1_2; const double* s2_2; const double* Design_U;
     const double* U3; const double* s1_3; const double* s2_3;
     const double* Ainv;
+    /* second random effect (r2 > 0): Z_2 n x r2, invert_aPXA_bDesignDesignT_rand2 {U r2 x r2, s1, s2}
+     * (fast_BSFG_sampler_init.R:300-311; its Design_U = Z_2 U is recomputed on the device), A_2_inv r2 x r2
+     * (NULL = identity, init:264).                                                                     */
+    const double* Z_2;
+    const double* U4; const double* s1_4; const double* s2_4;
+    const double* A_2_inv;
 } bsfg_constants;
 
 /* current_state (fast_BSFG_sampler_init.R:238-254).  Trait-indexed members hold this rank's rows /
@@ -185,6 +193,7 @@ typedef struct bsfg_state {
     double* delta; double* tauh;
     int k;       /* in: number of factor columns supplied; out: current k */
     int nrun;    /* iteration counter i (current_state$nrun) */
+    double* W; double* W_prec;   /* r2 x p_local, p_local (required on set_state when r2 > 0) */
 } bsfg_state;
 
 /* One iteration's injected variates (NULL members fall back to device Philox).
@@ -198,6 +207,9 @@ typedef struct bsfg_variates {
     /* add-a-factor arm of update_k, R draw order BSFG_functions.R:334-341 */
     const double* k_g_lp; const double* k_g_delta; const double* k_z_lambda; const double* k_u_h2;
     const double* k_z_Fa; const double* k_z_F;
+    /* second random effect: z_W r2 x p_local (= randn(br,p) of the second sample_means_c call,
+     * fast_BSFG_sampler.R:214), g_W p_local ~ Gamma(a + r2/2, 1) (R:249) */
+    const double* z_W; const double* g_W;
 } bsfg_variates;
 
 /* Gamma (shape, rate) parameters of the last iteration's precision draws, for parity checks. */
@@ -207,6 +219,7 @@ typedef struct bsfg_aux {
     double* E_a_prec_rate;      /* p_local */
     double* delta_rate;         /* k (draw order) */
     double* h2_log_ps;          /* k x H */
+    double* W_prec_rate;        /* p_local (r2 > 0) */
 } bsfg_aux;
 
 int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out);

@@ -330,7 +330,8 @@ def update_k(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, Z_W, Lambda_d
 def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     """One pass of the loop body of `fast_BSFG_sampler` with injected variates.
 
-    data: dict Y, X, Z_1 (Z_2 must have 0 columns here; Y has no NaN)
+    data: dict Y, X, Z_1 and optionally Z_2 (n x r2; then rv has invert_aPXA_bDesignDesignT_rand2 / A_2_inv, the
+          state has W (r2 x p) / W_prec (p) and v has z_W (r2 x p) / g_W (p)); Y has no NaN
     rv  : run_variables (Ainv, invert_aI_bZAZ, invert_aPXA_bDesignDesignT, invert_aZZt_Ainv, n,p,r,b)
     st  : current_state dict (modified copy is returned)
     v   : variates dict: z_Lambda (k,p), z_means (br,p), u_h2 (k), z_Fa (r,k), z_F (n,k),
@@ -340,26 +341,40 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     n, p = Y.shape
     r = Z_1.shape[1]
     b = X.shape[1]
+    Z_2 = data.get("Z_2")
+    r2 = 0 if Z_2 is None else np.asarray(Z_2).shape[1]
     st = {k_: (np.array(v_, dtype=np.float64, copy=True) if isinstance(v_, np.ndarray) else v_)
           for k_, v_ in st.items()}
     B, F = st["B"], st["F"]
+    if r2 > 0:
+        Z_2 = np.asarray(Z_2, dtype=np.float64)
+        W, W_prec = st["W"], st["W_prec"]
+        ZW = Z_2 @ W
+    else:
+        W, W_prec = np.zeros((0, p)), st.get("W_prec", np.zeros(p))
+        ZW = 0.0
     aux = {}
     # -- Lambda (R:189-191)
-    Y_tilde = Y - X @ B
+    Y_tilde = Y - X @ B - ZW
     Lambda = sample_Lambda_c(Y_tilde, F, st["resid_Y_prec"], st["E_a_prec"], st["Plam"],
                              rv["invert_aI_bZAZ"], v["z_Lambda"])
     # -- B, E_a (R:203-207)
-    Y_tilde = Y - F @ Lambda.T
+    Y_tilde = Y - F @ Lambda.T - ZW
     loc = sample_means_c(Y_tilde, st["resid_Y_prec"], st["E_a_prec"],
                          rv["invert_aPXA_bDesignDesignT"], v["z_means"])
     B = loc[:b, :]
     E_a = loc[b:b + r, :]
+    # -- W (R:211-216): second call of sample_means_c, with W_prec and the rand2 list
+    if r2 > 0:
+        Y_tilde = Y - X @ B - Z_1 @ E_a - F @ Lambda.T
+        W = sample_means_c(Y_tilde, st["resid_Y_prec"], W_prec, rv["invert_aPXA_bDesignDesignT_rand2"], v["z_W"])
+        ZW = Z_2 @ W
     # -- F_h2, F_a (R:221, 226)
     F_h2 = sample_h2s_discrete_c(F, rp["h2_divisions"], priors["h2_priors_factors"],
                                  rv["invert_aI_bZAZ"], v["u_h2"])
     F_a = sample_F_a_c(F, Z_1, F_h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
     # -- F (R:230-232)
-    Y_tilde = Y - X @ B - Z_1 @ E_a
+    Y_tilde = Y - X @ B - Z_1 @ E_a - ZW
     F = sample_factors_scores_c(Y_tilde, Z_1, Lambda, st["resid_Y_prec"], F_a, F_h2, v["z_F"])
     # -- Lambda_prec (R:235-236)
     Lambda2 = Lambda ** 2
@@ -369,7 +384,7 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     Lambda_prec = v["g_Lambda_prec"] / lp_rate
     aux["Lambda_prec_shape"], aux["Lambda_prec_rate"] = lp_shape, lp_rate
     # -- resid_Y_prec (R:239-240)
-    Y_tilde = Y - X @ B - F @ Lambda.T - Z_1 @ E_a
+    Y_tilde = Y - X @ B - F @ Lambda.T - Z_1 @ E_a - ZW
     ry_rate = priors["resid_Y_prec_rate"] + 0.5 * np.sum(Y_tilde ** 2, axis=0)
     resid_Y_prec = v["g_resid"] / ry_rate
     aux["resid_Y_prec_shape"], aux["resid_Y_prec_rate"] = priors["resid_Y_prec_shape"] + n / 2.0, ry_rate
@@ -377,6 +392,13 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     ea_rate = priors["E_a_prec_rate"] + 0.5 * np.einsum("ij,ij->j", E_a, rv["Ainv"] @ E_a)
     E_a_prec = v["g_Ea"] / ea_rate
     aux["E_a_prec_shape"], aux["E_a_prec_rate"] = priors["E_a_prec_shape"] + r / 2.0, ea_rate
+    # -- W_prec (R:248-250): diag(t(W) %*% A_2_inv %*% W)
+    if r2 > 0:
+        A2 = rv.get("A_2_inv")
+        A2 = np.eye(r2) if A2 is None else np.asarray(A2, dtype=np.float64)
+        w_rate = priors["W_prec_rate"] + 0.5 * np.einsum("ij,ij->j", W, A2 @ W)
+        W_prec = v["g_W"] / w_rate
+        aux["W_prec_shape"], aux["W_prec_rate"] = priors["W_prec_shape"] + r2 / 2.0, w_rate
     # -- delta, tauh, Plam (R:253-257)
     delta, d_shapes, d_rates = sample_delta(st["delta"], st["tauh"], Lambda_prec,
                                             priors["delta_1_shape"], priors["delta_1_rate"],
@@ -388,6 +410,8 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     out = dict(st)
     out.update(Lambda=Lambda, B=B, E_a=E_a, F_h2=F_h2, F_a=F_a, F=F, Lambda_prec=Lambda_prec,
                resid_Y_prec=resid_Y_prec, E_a_prec=E_a_prec, delta=delta, tauh=tauh, Plam=Plam)
+    if r2 > 0:
+        out.update(W=W, W_prec=W_prec)
     # -- update_k (R:260-269)
     if with_update_k:
         res = update_k(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, Z_1, df,

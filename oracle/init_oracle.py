@@ -125,8 +125,12 @@ def sampler_init(setup, priors, run_parameters, seed=1, lists="reference"):
         X = X.T                                                         # init:90
     assert X.shape[0] == n
     b = X.shape[1]
-    Z_2 = np.zeros((n, 0))
-    r2 = 0
+    Z_2 = setup.get("Z_2")
+    Z_2 = np.zeros((n, 0)) if Z_2 is None else np.array(Z_2, dtype=np.float64)
+    if Z_2.shape[0] != n:
+        Z_2 = Z_2.T
+    assert Z_2.shape[0] == n                                            # init:100
+    r2 = Z_2.shape[1]
     priors = dict(priors)
     priors["b_X_prec"] = 1e-10 * np.eye(b)                              # init:114
     k = int(priors["k_init"])
@@ -145,16 +149,26 @@ def sampler_init(setup, priors, run_parameters, seed=1, lists="reference"):
     F_a = rng.standard_normal((r, k)) * np.sqrt(F_h2)[None, :]
     F = Z_1 @ F_a + rng.standard_normal((n, k)) * np.sqrt(1 - F_h2)[None, :]
     W_prec = g(priors["W_prec_shape"], priors["W_prec_rate"], p)
-    W = np.zeros((r2, p))
+    W = rng.standard_normal((r2, p)) * np.sqrt(1.0 / W_prec)[None, :]          # byrow fill, init:210
     B = rng.standard_normal((b, p))
     current_state = dict(resid_Y_prec=resid_Y_prec, Lambda_prec=Lambda_prec, delta=delta, tauh=tauh,
                          Plam=Plam, Lambda=Lambda, F_h2=F_h2, E_a_prec=E_a_prec, W_prec=W_prec,
                          F_a=F_a, F=F, E_a=E_a, B=B, W=W, nrun=0)
     fn = gsvd_lists_reference if lists == "reference" else gsvd_lists_stable
     Ainv, inv1, inv2, inv3 = fn(X, Z_1, A)
+    inv_rand2 = {}
+    if r2 > 0:                                                          # init:300-311, A_2_inv = I (init:264)
+        if lists == "reference":
+            res = GSVD_2_c(cholcov(np.eye(r2)), cholcov(Z_2.T @ Z_2))
+            Uw = np.linalg.solve(res["X"], np.eye(r2)).T
+            inv_rand2 = {"U": Uw, "s1": np.diag(res["C"]) ** 2, "s2": np.diag(res["S"]) ** 2}
+        else:
+            Uw, s1w, s2w = _joint_diag(np.eye(r2), Z_2.T @ Z_2)
+            inv_rand2 = {"U": Uw, "s1": s1w, "s2": s2w}
+        inv_rand2["Design_U"] = Z_2 @ inv_rand2["U"]
     run_variables = dict(p=p, n=n, r=r, r2=r2, b=b, Mean_Y=Mean_Y, VY=VY, Ainv=Ainv,
                          A_2_inv=np.eye(r2), invert_aI_bZAZ=inv1, invert_aPXA_bDesignDesignT=inv2,
-                         invert_aZZt_Ainv=inv3, invert_aPXA_bDesignDesignT_rand2={})
+                         invert_aZZt_Ainv=inv3, invert_aPXA_bDesignDesignT_rand2=inv_rand2)
     rp = dict(run_parameters)
     rp["simulation"] = simulation
     return dict(data_matrices=dict(Y=Y, Z_1=Z_1, Z_2=Z_2, X=X, Y_missing=Y_missing),
@@ -234,7 +248,7 @@ def make_synthetic(n, p, k_true, seed=20131, pedigree="random", b=1):
                 error_factor_Lambda=Lambda, n=n, p=p, r=n)
 
 
-def draw_variates(rng, n, p, k, r, br, priors, add_arm=False):
+def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0):
     """One iteration's worth of injected variates in the layouts of oracle.bsfg_oracle.gibbs_iteration."""
     df = priors["Lambda_df"]
     v = dict(z_Lambda=rng.standard_normal((k, p)), z_means=rng.standard_normal((br, p)),
@@ -247,6 +261,9 @@ def draw_variates(rng, n, p, k, r, br, priors, add_arm=False):
     shapes = [priors["delta_1_shape"] + 0.5 * p * k]
     shapes += [priors["delta_2_shape"] + 0.5 * p * (k - h + 1) for h in delta_loop_indices(k)]
     v["g_delta"] = np.array([rng.gamma(s, 1.0) for s in shapes])
+    if r2 > 0:
+        v["z_W"] = rng.standard_normal((r2, p))
+        v["g_W"] = rng.gamma(priors["W_prec_shape"] + r2 / 2.0, 1.0, size=p)
     if add_arm:
         v.update(k_g_lp=rng.gamma(df / 2.0, 1.0, size=p),
                  k_g_delta=float(rng.gamma(priors["delta_2_shape"], 1.0)),

@@ -35,14 +35,16 @@ sample_delta_c <- function(delta, tauh, Lambda_prec, delta_1_shape, delta_1_rate
 bsfg_sweep_loop <- function(BSFG_state, n_samples, k_max = NULL) {
   dm <- BSFG_state$data_matrices; rv <- BSFG_state$run_variables; pr <- BSFG_state$priors
   rp <- BSFG_state$run_parameters; cs <- BSFG_state$current_state
-  stopifnot(sum(dm$Y_missing) == 0, ncol(dm$Z_2) == 0)           # not on the device path yet (DESIGN.md section 7)
+  stopifnot(sum(dm$Y_missing) == 0)                              # imputation step not on the device path yet (DESIGN.md section 8)
   k <- ncol(cs$F); if (is.null(k_max)) k_max <- max(2 * k, k + 8)
-  dims <- as.integer(c(rv$n, rv$p, k, k_max, rv$r, rv$b, rp$h2_divisions))
+  dims <- as.integer(c(rv$n, rv$p, k, k_max, rv$r, rv$b, rp$h2_divisions, rv$r2))
   pri <- c(pr$resid_Y_prec_shape, pr$resid_Y_prec_rate, pr$E_a_prec_shape, pr$E_a_prec_rate, pr$Lambda_df,
-           pr$delta_1_shape, pr$delta_1_rate, pr$delta_2_shape, pr$delta_2_rate, pr$b_X_prec[1], rp$b0, rp$b1, rp$epsilon, rp$prop)
+           pr$delta_1_shape, pr$delta_1_rate, pr$delta_2_shape, pr$delta_2_rate, pr$b_X_prec[1], rp$b0, rp$b1, rp$epsilon, rp$prop,
+           pr$W_prec_shape, pr$W_prec_rate)
   ident <- nrow(dm$Z_1) == ncol(dm$Z_1) && all(dm$Z_1 == diag(nrow(dm$Z_1)))
   ctx <- .Call('R_bsfg_create', dims, pri, as.double(pr$h2_priors_factors), dm$Y, dm$X, dm$Z_1, rv$invert_aI_bZAZ,
-               rv$invert_aPXA_bDesignDesignT, rv$invert_aZZt_Ainv, rv$Ainv, ident, .bsfg_seed())
+               rv$invert_aPXA_bDesignDesignT, rv$invert_aZZt_Ainv, rv$Ainv, ident, .bsfg_seed(), dm$Z_2,
+               rv$invert_aPXA_bDesignDesignT_rand2)
   .Call('R_bsfg_set_state', ctx, cs)
   i <- cs$nrun; end <- i + n_samples; sp_num <- ncol(BSFG_state$Posterior$Lambda)
   pull <- function() {
@@ -50,9 +52,10 @@ bsfg_sweep_loop <- function(BSFG_state, n_samples, k_max = NULL) {
     k <- kn[1]
     out <- list(Lambda = matrix(0, rv$p, k), Lambda_prec = matrix(0, rv$p, k), Plam = matrix(0, rv$p, k), F = matrix(0, rv$n, k),
                 F_a = matrix(0, rv$r, k), F_h2 = matrix(0, k, 1), B = matrix(0, rv$b, rv$p), E_a = matrix(0, rv$r, rv$p),
-                resid_Y_prec = numeric(rv$p), E_a_prec = numeric(rv$p), delta = numeric(k), tauh = numeric(k))
+                resid_Y_prec = numeric(rv$p), E_a_prec = numeric(rv$p), delta = numeric(k), tauh = numeric(k),
+                W = matrix(0, rv$r2, rv$p), W_prec = numeric(rv$p))
     kn <- .Call('R_bsfg_get_state', ctx, out)                     # fills the preallocated members in place
-    out$nrun <- kn[2]; out$W <- cs$W; out$W_prec <- cs$W_prec
+    out$nrun <- kn[2]
     out
   }
   while (i < end) {

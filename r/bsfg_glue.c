@@ -110,11 +110,15 @@ static void ctx_finalizer(SEXP ptr) {
 /* dims = c(n,p,k,k_max,r,b,h2_divisions); pri = c(resid shape,rate, E_a shape,rate, Lambda_df, delta_1 shape,rate,
  * delta_2 shape,rate, b_X_prec, b0,b1,epsilon,prop); lists as in BSFG_state$run_variables */
 SEXP R_bsfg_create(SEXP dims, SEXP pri, SEXP h2_priors, SEXP Y, SEXP X, SEXP Z1, SEXP inv1, SEXP inv2, SEXP inv3,
-                   SEXP Ainv, SEXP z1_identity, SEXP seed) {
-    int* d = INTEGER(dims);
-    double* q = REAL(pri);
-    bsfg_config cfg = {d[0], d[1], 0, d[1], d[2], d[3], d[4], d[5], d[6], 0, 1, seed_of(seed), Rf_asLogical(z1_identity), 0};
-    bsfg_priors pr = {q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], REAL(h2_priors), q[10], q[11], q[12], q[13]};
+                   SEXP Ainv, SEXP z1_identity, SEXP seed, SEXP Z2, SEXP inv4) {
+    int* d = INTEGER(dims);            /* c(n,p,k,k_max,r,b,h2_divisions,r2) */
+    double* q = REAL(pri);             /* ..., prop, W_prec_shape, W_prec_rate */
+    bsfg_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.n = d[0]; cfg.p_total = d[1]; cfg.p_local = d[1]; cfg.k = d[2]; cfg.k_max = d[3]; cfg.r = d[4]; cfg.b = d[5];
+    cfg.h2_divisions = d[6]; cfg.r2 = d[7]; cfg.world = 1; cfg.seed = seed_of(seed); cfg.z1_is_identity = Rf_asLogical(z1_identity);
+    bsfg_priors pr = {q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], REAL(h2_priors), q[10], q[11], q[12], q[13],
+                      q[14], q[15]};
     bsfg_ctx* c = NULL;
     chk(bsfg_create(&cfg, &c));
     SEXP ptr = PROTECT(R_MakeExternalPtr(c, R_NilValue, R_NilValue));
@@ -123,7 +127,10 @@ SEXP R_bsfg_create(SEXP dims, SEXP pri, SEXP h2_priors, SEXP Y, SEXP X, SEXP Z1,
     bsfg_constants k = {REAL(Y), d[5] > 0 ? REAL(X) : NULL, Rf_asLogical(z1_identity) ? NULL : REAL(Z1),
                         REAL(member(inv1, "U")), REAL(member(inv1, "s")),
                         REAL(member(inv2, "U")), REAL(member(inv2, "s1")), REAL(member(inv2, "s2")), REAL(member(inv2, "Design_U")),
-                        REAL(member(inv3, "U")), REAL(member(inv3, "s1")), REAL(member(inv3, "s2")), opt(Ainv)};
+                        REAL(member(inv3, "U")), REAL(member(inv3, "s1")), REAL(member(inv3, "s2")), opt(Ainv),
+                        d[7] > 0 ? REAL(Z2) : NULL, d[7] > 0 ? REAL(member(inv4, "U")) : NULL,
+                        d[7] > 0 ? REAL(member(inv4, "s1")) : NULL, d[7] > 0 ? REAL(member(inv4, "s2")) : NULL,
+                        NULL /* A_2_inv = diag(1, r2), fast_BSFG_sampler_init.R:264 */};
     chk(bsfg_upload_constants(c, &k));
     UNPROTECT(1);
     return ptr;
@@ -134,6 +141,7 @@ static void fill_state(bsfg_state* st, SEXP cs, int k, int nrun) {
     st->B = REAL(member(cs, "B")); st->E_a = REAL(member(cs, "E_a"));
     st->resid_Y_prec = REAL(member(cs, "resid_Y_prec")); st->E_a_prec = REAL(member(cs, "E_a_prec"));
     st->delta = REAL(member(cs, "delta")); st->tauh = REAL(member(cs, "tauh"));
+    st->W = REAL(member(cs, "W")); st->W_prec = REAL(member(cs, "W_prec"));      /* ignored by the library when r2 == 0 */
     st->k = k; st->nrun = nrun;
 }
 SEXP R_bsfg_set_state(SEXP ptr, SEXP cs) {

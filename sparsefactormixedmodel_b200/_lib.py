@@ -35,7 +35,7 @@ class bsfg_config(C.Structure):
                 ("k", C.c_int), ("k_max", C.c_int), ("r", C.c_int), ("b", C.c_int),
                 ("h2_divisions", C.c_int), ("rank", C.c_int), ("world", C.c_int),
                 ("seed", C.c_ulonglong), ("z1_is_identity", C.c_int), ("mode", C.c_int),
-                ("gram_mode", C.c_int), ("gram_terms", C.c_int), ("gram_step", C.c_double)]
+                ("gram_mode", C.c_int), ("gram_terms", C.c_int), ("gram_step", C.c_double), ("r2", C.c_int)]
 
 
 class bsfg_priors(C.Structure):
@@ -45,29 +45,32 @@ class bsfg_priors(C.Structure):
                 ("delta_1_shape", C.c_double), ("delta_1_rate", C.c_double),
                 ("delta_2_shape", C.c_double), ("delta_2_rate", C.c_double),
                 ("b_X_prec", C.c_double), ("h2_priors_factors", c_double_p),
-                ("b0", C.c_double), ("b1", C.c_double), ("epsilon", C.c_double), ("prop", C.c_double)]
+                ("b0", C.c_double), ("b1", C.c_double), ("epsilon", C.c_double), ("prop", C.c_double),
+                ("W_prec_shape", C.c_double), ("W_prec_rate", C.c_double)]
 
 
 class bsfg_constants(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
-                ("Y", "X", "Z_1", "U1", "s", "U2", "s1_2", "s2_2", "Design_U", "U3", "s1_3", "s2_3", "Ainv")]
+                ("Y", "X", "Z_1", "U1", "s", "U2", "s1_2", "s2_2", "Design_U", "U3", "s1_3", "s2_3", "Ainv",
+                 "Z_2", "U4", "s1_4", "s2_4", "A_2_inv")]
 
 
 class bsfg_state(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
-                 "E_a_prec", "delta", "tauh")] + [("k", C.c_int), ("nrun", C.c_int)]
+                 "E_a_prec", "delta", "tauh")] + [("k", C.c_int), ("nrun", C.c_int)] + \
+               [("W", c_double_p), ("W_prec", c_double_p)]
 
 
 class bsfg_variates(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
-                 "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F")]
+                 "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W")]
 
 
 class bsfg_aux(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
-                ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps")]
+                ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate")]
 
 
 # every symbol include/bsfg_b200.h declares (tests/test_abi.py checks this list against the header)

@@ -724,8 +724,14 @@ struct TraitReduceArgs {
     double rr_shape, rr_rate, re_shape, re_rate, bX;
     double* rp; double* ep;
     double* rr_rate_out; double* re_rate_out;     // optional aux
+    // second random effect (null W: none).  W r2 x p in original coordinates; Z2tY = Z_2'Y, Z2DUth = Z_2'Design_U theta,
+    // ZZW = Z_2'Z_2 W, A2W = A_2_inv W (all r2 x p), FZ2W = F'Z_2 W (k x p)
+    const double* W; long ldw; int r2;
+    const double* Z2tY; long ldzy; const double* Z2DUth; long ldzd; const double* ZZW; long ldzz;
+    const double* A2W; long lda2; const double* FZ2W; long ldfz;
+    double* wp; double rw_shape, rw_rate, r2_half; double* rw_rate_out;
 };
-__global__ void trait_reduce_kernel(TraitReduceArgs a, VarSrc g_resid, VarSrc g_ea) {
+__global__ void trait_reduce_kernel(TraitReduceArgs a, VarSrc g_resid, VarSrc g_ea, VarSrc g_w) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (j >= a.p) return;
@@ -753,10 +759,32 @@ __global__ void trait_reduce_kernel(TraitReduceArgs a, VarSrc g_resid, VarSrc g_
     for (int h = lane; h < a.k; h += 32) { const double l = lt[h]; l1 += l * fy[h]; l2 += l * g2[h]; a2 += l * fd[h]; }
     double bb = 0;
     for (int c = lane; c < a.b; c += 32) { const double v = a.Bfix[(long)j * a.ldb + c]; bb += v * v; }
+    // second random effect: ||..- Z_2 w||^2 adds  -2 w.Z2'y + w.Z2'Z2 w + 2 w.Z2'Design_U th + 2 l.F'Z2 w   (R:239, 249)
+    double w1 = 0, w2 = 0, w3 = 0, w4 = 0, l3 = 0;
+    if (a.W) {
+        const double* w = a.W + (long)j * a.ldw;
+        const double* zy = a.Z2tY + (long)j * a.ldzy;
+        const double* zd = a.Z2DUth + (long)j * a.ldzd;
+        const double* zz = a.ZZW + (long)j * a.ldzz;
+        const double* a2w = a.A2W + (long)j * a.lda2;
+        for (int i = lane; i < a.r2; i += 32) {
+            const double wi = w[i];
+            w1 += wi * zy[i]; w2 += wi * zd[i]; w3 += wi * zz[i]; w4 += wi * a2w[i];
+        }
+        const double* fz = a.FZ2W + (long)j * a.ldfz;
+        for (int h = lane; h < a.k; h += 32) l3 += lt[h] * fz[h];
+        w1 = warp_sum(w1); w2 = warp_sum(w2); w3 = warp_sum(w3); w4 = warp_sum(w4); l3 = warp_sum(l3);
+    }
     a1 = warp_sum(a1); a2 = warp_sum(a2); q1 = warp_sum(q1); q2 = warp_sum(q2);
     l1 = warp_sum(l1); l2 = warp_sum(l2); bb = warp_sum(bb);
     if (lane == 0) {
-        const double ss = a.yy[j] - 2.0 * a1 - 2.0 * l1 + q2 + 2.0 * a2 + l2;
+        double ss = a.yy[j] - 2.0 * a1 - 2.0 * l1 + q2 + 2.0 * a2 + l2;
+        if (a.W) {
+            ss += -2.0 * w1 + w3 + 2.0 * w2 + 2.0 * l3;
+            const double rate_w = a.rw_rate + 0.5 * w4;
+            a.wp[j] = var_gamma(g_w, j, 0, a.rw_shape + a.r2_half) / rate_w;
+            if (a.rw_rate_out) a.rw_rate_out[j] = rate_w;
+        }
         const double rate_r = a.rr_rate + 0.5 * ss;
         const double rate_e = a.re_rate + 0.5 * (q1 - a.bX * bb);
         a.rp[j] = var_gamma(g_resid, j, 0, a.rr_shape + a.n_half) / rate_r;

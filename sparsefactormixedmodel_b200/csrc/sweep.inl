@@ -57,6 +57,12 @@ struct bsfg_ctx {
     bool have_priors = false, have_consts = false, have_state = false;
     int n = 0, pl = 0, p_total = 0, p_off = 0, k = 0, kmax = 0, r = 0, b = 0, br = 0, H = 0;
     bool z1_identity = false;
+    int r2 = 0;                   // second random effect (Z_2 / W), 0: none
+    bsfg::DMat Z2, Z2t, Uw, Uwt, A2inv, UtZ2t, DtZ2, DtZ2t, Z2tY, Z2tZ2;          // constants
+    bsfg::DVec s1w, s2w, wp;
+    bsfg::DMat W, Wt, UtYw, gW, tmpw, thw, Z2DUth, ZZW, A2W, FtZ2, Z2tF, FZ2W;    // state W + scratch
+    bsfg::DMat v_zW, v_gW;
+    bsfg::DVec aux_rw;
     int mode = 0;                 // 1 direct, 2 diag
     double resid_s1 = -1, resid_s2 = -1;
     long iter = 0;                // current_state$nrun
@@ -105,7 +111,8 @@ static void ctx_alloc_factor_storage(bsfg_ctx* c) {
     c->Lp.alloc((long)km * (km + 1) / 2); c->Lfac.alloc((long)km * (km + 1) / 2);
     c->det.alloc(c->H); c->ll.alloc((long)km * c->H);
     // red1 = [LtL (km x km) | P1 (n x km) | P2 (br x km)] stacked by rows: one allreduce buffer
-    c->red1.alloc(round_up(km, 2) + round_up(n, 2) + round_up(br, 2), km);
+    c->red1.alloc(round_up(km, 2) + round_up(n, 2) + round_up(br, 2) + round_up(c->r2, 2), km);
+    if (c->r2 > 0) { c->FtZ2.alloc(km, c->r2); c->Z2tF.alloc(c->r2, km); c->FZ2W.alloc(km, pl); }
     c->colsum_cnt.alloc(2 * (long)km);
     c->delta_shapes.alloc(km + 2); c->delta_rates.alloc(km + 2);
     c->aux_logps.alloc((long)km * c->H);
@@ -131,6 +138,11 @@ static void refresh_derived(bsfg_ctx* c) {
     d.gemm(1.0, c->U1, F, 0.0, UtF);
     d.gemm(1.0, F, c->DU, 0.0, FtD);
     d.transpose(FtD, DtF);
+    if (c->r2 > 0) {
+        DMat FtZ2 = view(c->FtZ2, c->k, c->r2), Z2tF = view(c->Z2tF, c->r2, c->k);
+        d.gemm(1.0, F, c->Z2, 0.0, FtZ2);          // F' Z_2
+        d.transpose(FtZ2, Z2tF);
+    }
     c->derived_valid = true;
 }
 
@@ -141,7 +153,7 @@ static void allreduce(bsfg_ctx* c, double* buf, size_t count) {
 }
 
 struct IterVariates {   // device-side sources for one iteration
-    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD;
+    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD, zW, gW;
 };
 
 static void phase_mark(bsfg_ctx* c, int idx) {
@@ -159,7 +171,11 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
 
     // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
     phase_mark(c, 0);
-    lambda_core(d, c->lsc, c->gram, UtF, c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
+    const int r2 = c->r2;
+    if (r2 > 0)        // U'(Y - Z_2 W): R:189 (the X B part is fused into the weight kernel)
+        dgemm_tn(d.st, d.sms, n, pl, r2, -1.0, c->UtZ2t.p, c->UtZ2t.ld, c->W.p, c->W.ld, 1.0, c->UtY.p, c->UtY.ld,
+                 c->UtYw.p, c->UtYw.ld, d.ws.p, Device::WS_DOUBLES);
+    lambda_core(d, c->lsc, c->gram, UtF, r2 > 0 ? c->UtYw : c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
                 Plamt.p, Plamt.ld, 1, v.zL, Lt, c->phase_timing ? &c->ev_phase[1] : nullptr);
     {
         dim3 grid(ceil_div(k, 32), ceil_div(pl, 32)), block(32, 8);
@@ -170,6 +186,9 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     //    Design_U'(Y - F Lambda') = DtY - (Design_U'F) Lambda'
     dgemm_tn(d.st, d.sms, br, pl, k, -1.0, FtD.p, FtD.ld, Lt.p, Lt.ld, 1.0, c->DtY.p, c->DtY.ld, c->tmp_brp.p,
              c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
+    if (r2 > 0)        // ... - Design_U' Z_2 W  (R:203)
+        dgemm_tn(d.st, d.sms, br, pl, r2, -1.0, c->DtZ2t.p, c->DtZ2t.ld, c->W.p, c->W.ld, 1.0, c->tmp_brp.p, c->tmp_brp.ld,
+                 c->tmp_brp.p, c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
     {
         const bool fuse_b = b > 0 && b <= MEANS_BMAX;      // B = location_sample[1:b,] (R:206) reduced in the same pass
         means_theta_kernel<<<pl, 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
@@ -183,6 +202,21 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     }
     d.transpose(c->theta, c->thetat);
     c->theta_valid = true;
+    // 3. W | B, E_a, F, Lambda: second sample_means_c call, with W_prec and the rand2 list    R:211-216
+    //    Design_U2'(Y - X B - Z_1 E_a - F Lambda') = Uw'[Z_2'Y - (Z_2'Design_U) theta - (Z_2'F) Lambda']
+    if (r2 > 0) {
+        DMat FtZ2 = view(c->FtZ2, k, r2);
+        d.gemm(1.0, c->DtZ2, c->theta, 0.0, c->Z2DUth);                                   // Z_2'Design_U theta (kept for step 8)
+        dgemm_tn(d.st, d.sms, r2, pl, k, -1.0, FtZ2.p, FtZ2.ld, Lt.p, Lt.ld, 1.0, c->Z2tY.p, c->Z2tY.ld, c->gW.p, c->gW.ld,
+                 d.ws.p, Device::WS_DOUBLES);                                             // Z_2'Y - Z_2'F Lambda'
+        d.gemm(1.0, c->Uw, c->gW, 0.0, c->tmpw);
+        d.gemm(-1.0, c->Uw, c->Z2DUth, 1.0, c->tmpw);
+        means_theta_kernel<<<pl, 256, 0, d.st>>>(c->tmpw.p, c->tmpw.ld, r2, pl, c->s1w.p, c->s2w.p, c->rp.p, c->wp.p, v.zW,
+                                                 c->thw.p, c->thw.ld, nullptr, 0, 0, nullptr, 0);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        d.gemm(1.0, c->Uwt, c->thw, 0.0, c->W);                                            // W = U theta_w (cpp:78)
+        d.transpose(c->W, c->Wt);
+    }
     phase_mark(c, 4);
 
     // 4. F_h2 | F (marginal over F_a)                         R:221 -> cpp:196-238
@@ -205,6 +239,9 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     d.gemm(1.0, Lam, Lmsg, 0.0, LtL);
     d.gemm(1.0, c->UtYt, Lmsg, 0.0, P1);
     d.gemm(1.0, c->thetat, Lmsg, 0.0, P2);
+    const long o3 = o2 + round_up(br, 2);
+    DMat P3 = view_at(c->red1.p + o3, r2, k, c->red1.ld);
+    if (r2 > 0) d.gemm(1.0, c->Wt, Lmsg, 0.0, P3);                                         // W Lmsg
     phase_mark(c, 7);
     allreduce(c, c->red1.p, (size_t)c->red1.ld * (size_t)k);
     phase_mark(c, 8);
@@ -212,6 +249,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
         DMat YL = view(c->YL, n, k);
         d.gemm(1.0, c->U1t, P1, 0.0, YL);
         d.gemm(-1.0, c->DUt, P2, 1.0, YL);
+        if (r2 > 0) d.gemm(-1.0, c->Z2t, P3, 1.0, YL);                                     // ... - Z_2 W Lmsg  (R:230)
         const double* zfa_p = nullptr; long zfa_ld = 0;
         if (c->z1_identity) { zfa_p = Fa.p; zfa_ld = Fa.ld; }
         else {
@@ -251,6 +289,18 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
             d.gemm(1.0, c->M2, c->theta, 0.0, c->M2th);
         }
         TraitReduceArgs a;
+        memset(&a, 0, sizeof a);
+        if (r2 > 0) {
+            DMat Z2tF = view(c->Z2tF, r2, k), FZ2W = view(c->FZ2W, k, pl);
+            d.gemm(1.0, Z2tF, c->W, 0.0, FZ2W);              // F'Z_2 W
+            d.gemm(1.0, c->Z2tZ2, c->W, 0.0, c->ZZW);        // Z_2'Z_2 W
+            d.gemm(1.0, c->A2inv, c->W, 0.0, c->A2W);        // A_2_inv W  (R:249)
+            a.W = c->W.p; a.ldw = c->W.ld; a.r2 = r2;
+            a.Z2tY = c->Z2tY.p; a.ldzy = c->Z2tY.ld; a.Z2DUth = c->Z2DUth.p; a.ldzd = c->Z2DUth.ld;
+            a.ZZW = c->ZZW.p; a.ldzz = c->ZZW.ld; a.A2W = c->A2W.p; a.lda2 = c->A2W.ld; a.FZ2W = FZ2W.p; a.ldfz = FZ2W.ld;
+            a.wp = c->wp.p; a.rw_shape = c->pri.W_prec_shape; a.rw_rate = c->pri.W_prec_rate; a.r2_half = r2 / 2.0;
+            a.rw_rate_out = c->aux_on ? c->aux_rw.p : nullptr;
+        }
         a.theta = c->theta.p; a.ldth = c->theta.ld; a.DtY = c->DtY.p; a.lddy = c->DtY.ld;
         a.FDth = FDth.p; a.ldfd = FDth.ld;
         a.M1th = c->mode == 1 ? c->M1th.p : nullptr; a.M2th = c->mode == 1 ? c->M2th.p : nullptr; a.ldm = c->M1th.ld;
@@ -263,7 +313,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
         a.re_shape = c->pri.E_a_prec_shape; a.re_rate = c->pri.E_a_prec_rate; a.bX = c->pri.b_X_prec;
         a.rp = c->rp.p; a.ep = c->ep.p;
         a.rr_rate_out = c->aux_on ? c->aux_rr.p : nullptr; a.re_rate_out = c->aux_on ? c->aux_re.p : nullptr;
-        trait_reduce_kernel<<<ceil_div((long)pl * 32, 256), 256, 0, d.st>>>(a, v.gR, v.gE);
+        trait_reduce_kernel<<<ceil_div((long)pl * 32, 256), 256, 0, d.st>>>(a, v.gR, v.gE, v.gW);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     phase_mark(c, 10);
@@ -425,7 +475,7 @@ extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
     BSFG_API_BEGIN
     REQUIRE_PTR(cfg); REQUIRE_PTR(out);
     if (cfg->n <= 0 || cfg->p_local <= 0 || cfg->p_total < cfg->p_local || cfg->k < 2 || cfg->k_max < cfg->k || cfg->r <= 0 ||
-        cfg->b < 0 || cfg->h2_divisions <= 0 || cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world ||
+        cfg->b < 0 || cfg->r2 < 0 || cfg->h2_divisions <= 0 || cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world ||
         cfg->p_offset < 0 || cfg->p_offset + cfg->p_local > cfg->p_total)
         fail(BSFG_ESHAPE, "bsfg_create: inconsistent sizes");
     if (cfg->z1_is_identity && cfg->r != cfg->n) fail(BSFG_ESHAPE, "z1_is_identity requires r == n");
@@ -439,11 +489,18 @@ extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
         c->n = cfg->n; c->pl = cfg->p_local; c->p_total = cfg->p_total; c->p_off = cfg->p_offset;
         c->k = cfg->k; c->kmax = cfg->k_max; c->r = cfg->r; c->b = cfg->b; c->br = cfg->b + cfg->r; c->H = cfg->h2_divisions;
         c->z1_identity = cfg->z1_is_identity != 0;
+        c->r2 = cfg->r2;
         ctx_alloc_factor_storage(c);
         const int n = c->n, pl = c->pl, br = c->br, b = c->b;
         c->Bfix.alloc(std::max(b, 1), pl); c->theta.alloc(br, pl); c->thetat.alloc(pl, br);
         c->tmp_brp.alloc(br, pl);
         c->rp.alloc(pl); c->ep.alloc(pl); c->yy.alloc(pl);
+        if (c->r2 > 0) {
+            const int r2 = c->r2;
+            c->wp.alloc(pl); c->aux_rw.alloc(pl);
+            c->W.alloc(r2, pl); c->Wt.alloc(pl, r2); c->UtYw.alloc(n, pl); c->gW.alloc(r2, pl); c->tmpw.alloc(r2, pl);
+            c->thw.alloc(r2, pl); c->Z2DUth.alloc(r2, pl); c->ZZW.alloc(r2, pl); c->A2W.alloc(r2, pl);
+        }
         c->aux_lp_rate.alloc(pl, c->kmax); c->aux_rr.alloc(pl); c->aux_re.alloc(pl);
         BSFG_CUDA(cudaMalloc(&c->d_ndraws, sizeof(int)));
         BSFG_CUDA(cudaMalloc(&c->d_map, sizeof(int) * c->kmax));
@@ -512,6 +569,27 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
         c->Z1.upload(k->Z_1, d.st);
         d.transpose(c->Z1, c->Z1t);
     }
+    if (c->r2 > 0) {
+        const int r2 = c->r2;
+        REQUIRE_PTR(k->Z_2); REQUIRE_PTR(k->U4); REQUIRE_PTR(k->s1_4); REQUIRE_PTR(k->s2_4);
+        c->Z2.alloc(n, r2); c->Z2t.alloc(r2, n); c->Uw.alloc(r2, r2); c->Uwt.alloc(r2, r2); c->A2inv.alloc(r2, r2);
+        c->s1w.alloc(r2); c->s2w.alloc(r2);
+        c->Z2.upload(k->Z_2, d.st); c->Uw.upload(k->U4, d.st); c->s1w.upload(k->s1_4, d.st); c->s2w.upload(k->s2_4, d.st);
+        if (k->A_2_inv) c->A2inv.upload(k->A_2_inv, d.st);
+        else {
+            std::vector<double> eye((size_t)r2 * r2, 0.0);
+            for (int i = 0; i < r2; i++) eye[(size_t)i * r2 + i] = 1.0;      // A_2_inv = diag(1, r2), init:264
+            c->A2inv.upload(eye.data(), d.st);
+            d.sync();
+        }
+        d.transpose(c->Z2, c->Z2t); d.transpose(c->Uw, c->Uwt);
+        DMat UtZ2(n, r2);
+        c->UtZ2t.alloc(r2, n); c->DtZ2.alloc(br, r2); c->DtZ2t.alloc(r2, br); c->Z2tZ2.alloc(r2, r2);
+        d.gemm(1.0, c->U1, c->Z2, 0.0, UtZ2);      d.transpose(UtZ2, c->UtZ2t);          // U'Z_2
+        d.gemm(1.0, c->DU, c->Z2, 0.0, c->DtZ2);   d.transpose(c->DtZ2, c->DtZ2t);       // Design_U'Z_2
+        d.gemm(1.0, c->Z2, c->Z2, 0.0, c->Z2tZ2);                                          // Z_2'Z_2
+        d.sync();
+    }
     {   // rotate the data once: U'Y, (U'Y)', Design_U'Y, colSums(Y^2), U'X
         DMat Y(n, pl);
         Y.upload(k->Y, d.st);
@@ -519,6 +597,7 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
         d.gemm(1.0, c->U1, Y, 0.0, c->UtY);
         d.transpose(c->UtY, c->UtYt);
         d.gemm(1.0, c->DU, Y, 0.0, c->DtY);
+        if (c->r2 > 0) { c->Z2tY.alloc(c->r2, pl); d.gemm(1.0, c->Z2, Y, 0.0, c->Z2tY); }
         colsumsq_kernel<<<ceil_div((long)pl * 32, 256), 256, 0, d.st>>>(Y.p, Y.ld, n, pl, c->yy.p);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         if (b > 0) {
@@ -643,6 +722,11 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
         if (c->Ea_in.rows != r) c->Ea_in.alloc(r, pl);
         c->Ea_in.upload(st->E_a, d.st);
     }
+    if (c->r2 > 0) {
+        REQUIRE_PTR(st->W); REQUIRE_PTR(st->W_prec);
+        c->W.upload(st->W, d.st); c->wp.upload(st->W_prec, d.st);
+        d.transpose(c->W, c->Wt);
+    }
     c->theta_valid = false;
     c->derived_valid = false;
     d.sync();
@@ -695,6 +779,10 @@ extern "C" int bsfg_get_state(bsfg_ctx* c, bsfg_state* st) {
             fail(BSFG_ESTATE, "E_a requested but neither a sweep nor set_state provided it");
         }
     }
+    if (c->r2 > 0) {
+        if (st->W) c->W.download(st->W, d.st);
+        if (st->W_prec) c->wp.download(st->W_prec, d.st);
+    }
     if (st->resid_Y_prec) c->rp.download(st->resid_Y_prec, d.st);
     if (st->E_a_prec) c->ep.download(st->E_a_prec, d.st);
     if (st->delta) BSFG_CUDA(cudaMemcpyAsync(st->delta, c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
@@ -713,6 +801,7 @@ extern "C" int bsfg_get_aux(bsfg_ctx* c, bsfg_aux* a) {
     if (a->resid_Y_prec_rate) c->aux_rr.download(a->resid_Y_prec_rate, d.st);
     if (a->E_a_prec_rate) c->aux_re.download(a->E_a_prec_rate, d.st);
     if (a->delta_rate) BSFG_CUDA(cudaMemcpyAsync(a->delta_rate, c->delta_rates.p, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, d.st));
+    if (a->W_prec_rate && c->r2 > 0) c->aux_rw.download(a->W_prec_rate, d.st);
     if (a->h2_log_ps) BSFG_CUDA(cudaMemcpyAsync(a->h2_log_ps, c->aux_logps.p, sizeof(double) * (size_t)k * c->H, cudaMemcpyDeviceToHost, d.st));
     d.sync();
     BSFG_API_END
@@ -740,6 +829,8 @@ extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
         v.gR = make_var(nullptr, seed, SITE_G_RESID, ii, c->p_off, 1);
         v.gE = make_var(nullptr, seed, SITE_G_EA, ii, c->p_off, 1);
         v.gD = make_var(nullptr, seed, SITE_G_DELTA, ii, 0, 1);
+        v.zW = make_var(nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
+        v.gW = make_var(nullptr, seed, SITE_G_W, ii, c->p_off, 1);
         c->phase_timing = (it == n_iter - 1);
         gibbs_iteration(c, v);
         RngStream rs{seed, SITE_U_K, ii};
@@ -774,6 +865,8 @@ extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
     v.gLP = make_var(stage(c->v_gLP, hv->g_Lambda_prec, pl, k), seed, SITE_G_LAMBDA_PREC, ii, c->p_off, c->p_total);
     v.gR = make_var(stage(c->v_gR, hv->g_resid, pl, 1), seed, SITE_G_RESID, ii, c->p_off, 1);
     v.gE = make_var(stage(c->v_gE, hv->g_Ea, pl, 1), seed, SITE_G_EA, ii, c->p_off, 1);
+    v.zW = make_var(c->r2 > 0 ? stage(c->v_zW, hv->z_W, c->r2, pl) : nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
+    v.gW = make_var(c->r2 > 0 ? stage(c->v_gW, hv->g_W, pl, 1) : nullptr, seed, SITE_G_W, ii, c->p_off, 1);
     {
         const DMat* gd = nullptr;
         if (hv->g_delta) {       // only as many entries as sample_delta draws: 1 + |2:(k-1)|

@@ -26,7 +26,7 @@ from ._lib import as_f, check, ptr
 _STATE_FIELDS = ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
                  "E_a_prec", "delta", "tauh")
 _VARIATE_FIELDS = ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
-                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F")
+                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W")
 
 
 _GRAM_MODES = {"default": 0, "exact": 1, "expsum": 2}
@@ -64,8 +64,8 @@ class BSFGSweep:
         X = np.asarray(data_matrices["X"], dtype=np.float64)
         Z_1 = np.asarray(data_matrices["Z_1"], dtype=np.float64)
         Z_2 = data_matrices.get("Z_2")
-        if Z_2 is not None and np.asarray(Z_2).shape[1] > 0:
-            raise ValueError("a second random effect (Z_2) is not supported by the device sweep yet")
+        Z_2 = np.zeros((Y.shape[0], 0)) if Z_2 is None else np.asarray(Z_2, dtype=np.float64)
+        self.r2 = r2 = Z_2.shape[1]
         n, p = Y.shape
         r = Z_1.shape[1]
         b = X.shape[1]
@@ -80,7 +80,7 @@ class BSFGSweep:
         cfg = _lib.bsfg_config(n=n, p_total=p, p_offset=self.lo, p_local=self.pl, k=k0, k_max=self.k_max,
                                r=r, b=b, h2_divisions=self.H, rank=rank, world=world, seed=seed,
                                z1_is_identity=int(ident), mode={"auto": 0, "direct": 1, "diag": 2}[mode],
-                               gram_mode=_GRAM_MODES[gram], gram_terms=int(gram_terms), gram_step=float(gram_step))
+                               gram_mode=_GRAM_MODES[gram], gram_terms=int(gram_terms), gram_step=float(gram_step), r2=r2)
         self._ctx = C.c_void_p()
         check(self.lib.bsfg_create(C.byref(cfg), C.byref(self._ctx)))
         # priors / run parameters
@@ -93,7 +93,8 @@ class BSFGSweep:
                               priors["E_a_prec_rate"], priors["Lambda_df"], priors["delta_1_shape"],
                               priors["delta_1_rate"], priors["delta_2_shape"], priors["delta_2_rate"], bx,
                               ptr(self._h2p), run_parameters["b0"], run_parameters["b1"],
-                              run_parameters["epsilon"], run_parameters["prop"])
+                              run_parameters["epsilon"], run_parameters["prop"],
+                              priors.get("W_prec_shape", 2.0), priors.get("W_prec_rate", 0.1))
         check(self.lib.bsfg_set_priors(self._ctx, C.byref(pr)))
         # constants (this rank's trait columns of Y)
         l1 = run_variables["invert_aI_bZAZ"]; l2 = run_variables["invert_aPXA_bDesignDesignT"]
@@ -105,6 +106,15 @@ class BSFGSweep:
                 as_f(l3["U"], (r, r)), np.ascontiguousarray(np.asarray(l3["s1"], dtype=np.float64).ravel()),
                 np.ascontiguousarray(np.asarray(l3["s2"], dtype=np.float64).ravel()),
                 as_f(run_variables["Ainv"], (r, r)) if run_variables.get("Ainv") is not None else None]
+        if r2 > 0:      # second random effect: Z_2 and invert_aPXA_bDesignDesignT_rand2 (fast_BSFG_sampler_init.R:300-311)
+            l4 = run_variables["invert_aPXA_bDesignDesignT_rand2"]
+            A2 = run_variables.get("A_2_inv")
+            keep += [as_f(Z_2, (n, r2)), as_f(l4["U"], (r2, r2)),
+                     np.ascontiguousarray(np.asarray(l4["s1"], dtype=np.float64).ravel()),
+                     np.ascontiguousarray(np.asarray(l4["s2"], dtype=np.float64).ravel()),
+                     None if A2 is None or np.array_equal(np.asarray(A2), np.eye(r2)) else as_f(A2, (r2, r2))]
+        else:
+            keep += [None] * 5
         consts = _lib.bsfg_constants(*[ptr(a) for a in keep])
         check(self.lib.bsfg_upload_constants(self._ctx, C.byref(consts)))
         if world > 1:
@@ -148,6 +158,9 @@ class BSFGSweep:
         st.tauh = put("tauh", np.ascontiguousarray(np.asarray(cs["tauh"], dtype=np.float64).ravel()))
         st.k = k
         st.nrun = int(cs.get("nrun", 0))
+        if self.r2 > 0:
+            st.W = put("W", as_f(np.asarray(cs["W"])[:, sl]))
+            st.W_prec = put("W_prec", np.ascontiguousarray(np.asarray(cs["W_prec"], dtype=np.float64).ravel()[sl]))
         check(self.lib.bsfg_set_state(self._ctx, C.byref(st)))
 
     def get_state(self, with_E_a=True, out=None):
@@ -160,12 +173,11 @@ class BSFGSweep:
         if out is None or out["F"].shape[1] != k:
             out = self.alloc_state(k, with_E_a)
         st = _lib.bsfg_state()
-        for name in _STATE_FIELDS:
+        for name in _STATE_FIELDS + ("W", "W_prec"):
             if name in out and out[name] is not None and out[name].size:
                 setattr(st, name, ptr(out[name]))
         check(self.lib.bsfg_get_state(self._ctx, C.byref(st)))
         out["nrun"] = st.nrun
-        out["W"] = np.zeros((0, self.pl)); out["W_prec"] = np.zeros(self.pl)
         return out
 
     def alloc_state(self, k, with_E_a=True, empty=None):
@@ -176,6 +188,7 @@ class BSFGSweep:
                    E_a_prec=mk((self.pl,)), delta=mk((k,)), tauh=mk((k,)))
         if with_E_a:
             out["E_a"] = mk((self.r, self.pl))
+        out["W"] = mk((self.r2, self.pl)); out["W_prec"] = mk((self.pl,))
         return out
 
     # -- sweeping --------------------------------------------------------------------------
@@ -192,11 +205,11 @@ class BSFGSweep:
 
         def conv(name, a):
             a = np.asarray(a, dtype=np.float64)
-            if name in ("z_Lambda", "z_means"):
+            if name in ("z_Lambda", "z_means", "z_W"):
                 a = a[:, sl]
             elif name in ("g_Lambda_prec",):
                 a = a[sl, :]
-            elif name in ("g_resid", "g_Ea", "k_g_lp", "k_z_lambda"):
+            elif name in ("g_resid", "g_Ea", "g_W", "k_g_lp", "k_z_lambda"):
                 a = a.ravel()[sl]
             a = np.asfortranarray(a) if a.ndim == 2 else np.ascontiguousarray(a.ravel())
             hold.append(a)
@@ -212,9 +225,10 @@ class BSFGSweep:
         check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))
         k = probe.k
         out = dict(Lambda_prec_rate=np.zeros((self.pl, k), order="F"), resid_Y_prec_rate=np.zeros(self.pl),
-                   E_a_prec_rate=np.zeros(self.pl), delta_rate=np.zeros(k + 2), h2_log_ps=np.zeros((k, self.H), order="F"))
+                   E_a_prec_rate=np.zeros(self.pl), delta_rate=np.zeros(k + 2), h2_log_ps=np.zeros((k, self.H), order="F"),
+                   W_prec_rate=np.zeros(self.pl))
         a = _lib.bsfg_aux(*[ptr(out[nm]) for nm in ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate",
-                                                     "delta_rate", "h2_log_ps")])
+                                                     "delta_rate", "h2_log_ps", "W_prec_rate")])
         check(self.lib.bsfg_get_aux(self._ctx, C.byref(a)))
         return out
 
@@ -268,9 +282,9 @@ def _save_posterior_samples(sp_num, Posterior, cs):
             M = np.vstack([M, np.zeros((vec.shape[0] - M.shape[0], M.shape[1]))])
         M[:vec.shape[0], sp_num - 1] = vec
         Posterior[name] = M
-    for name in ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec"):
+    for name in ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec", "W_prec"):
         put(name, cs[name])
-    for name in ("B", "E_a"):
+    for name in ("B", "E_a", "W"):
         prev = Posterior.get(name)
         cur = np.asarray(cs[name], dtype=np.float64)
         if prev is None or np.shape(prev) != cur.shape:

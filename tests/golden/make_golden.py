@@ -18,7 +18,8 @@ literals, state, variates) and the outputs, so
 Fixtures are sub-sampled to stay small (whole half-sib families / whole lines are kept so A stays a valid
 relationship matrix); the Ayroles panel has missing phenotypes, which the device sweep does not handle yet
 (SURVEY.md section 8f-3): its NaNs are replaced by the trait mean here and the case serves as the
-rectangular-Z_1 (n=200 individuals, r=40 lines, b=2) fixture.
+rectangular-Z_1 (n=200 individuals, r=40 lines, b=2) fixture WITH the second random effect of the real data
+(Z_2 200 x 40, W, W_prec; fast_BSFG_sampler.R:211-216, 248-250).
 """
 import os
 import sys
@@ -56,7 +57,10 @@ def load_setup(name, path, n_keep, p_keep):
         Y = np.where(np.isnan(Y), mu[None, :], Y)
         # keep traits with the fewest imputed values first -> deterministic choice
         keep = np.arange(p_keep)
-        return dict(Y=Y[:, keep], X=X, Z_1=Z_1, A=A, simulation=False)
+        Z_2 = np.asarray(m["Z_2"], dtype=np.float64)
+        if Z_2.shape[0] != n:
+            Z_2 = Z_2.T
+        return dict(Y=Y[:, keep], X=X, Z_1=Z_1, Z_2=Z_2, A=A, simulation=False)
     # simulations: Z_1 = I, individuals are ordered by family -> the first n_keep are whole families
     assert np.array_equal(Z_1, np.eye(n))
     return dict(Y=Y[:n_keep, :p_keep], X=X[:n_keep], Z_1=np.eye(n_keep), A=A[:n_keep, :n_keep], simulation=True)
@@ -83,15 +87,18 @@ def main():
         r, b = d["Z_1"].shape[1], d["X"].shape[1]
         rng = np.random.default_rng(202)
         out = {}
-        flatten("data.", {kk: d[kk] for kk in ("Y", "X", "Z_1")}, out)
-        flatten("rv.", {kk: rv[kk] for kk in ("Ainv", "invert_aI_bZAZ", "invert_aPXA_bDesignDesignT", "invert_aZZt_Ainv")}, out)
-        flatten("state0.", {kk: vv for kk, vv in cs.items() if kk not in ("W", "W_prec")}, out)
+        r2 = d["Z_2"].shape[1]
+        skip = () if r2 > 0 else ("W", "W_prec")
+        flatten("data.", {kk: d[kk] for kk in ("Y", "X", "Z_1") + (("Z_2",) if r2 > 0 else ())}, out)
+        flatten("rv.", {kk: rv[kk] for kk in ("Ainv", "invert_aI_bZAZ", "invert_aPXA_bDesignDesignT", "invert_aZZt_Ainv")
+                        + (("invert_aPXA_bDesignDesignT_rand2",) if r2 > 0 else ())}, out)
+        flatten("state0.", {kk: vv for kk, vv in cs.items() if kk not in skip}, out)
         cur = cs
         for it in (1, 2):
-            v = I.draw_variates(rng, n, p, k, r, b + r, pri)
+            v = I.draw_variates(rng, n, p, k, r, b + r, pri, r2=r2)
             nxt, aux = O.gibbs_iteration(d, rv, pri, rp, cur, it, v)
             flatten(f"variates{it}.", v, out)
-            flatten(f"state{it}.", {kk: vv for kk, vv in nxt.items() if kk not in ("W", "W_prec")}, out)
+            flatten(f"state{it}.", {kk: vv for kk, vv in nxt.items() if kk not in skip}, out)
             flatten(f"aux{it}.", {kk: vv for kk, vv in aux.items() if kk.endswith("_rate")}, out)
             cur = nxt
         # the export that is off the active sweep (fast_BSFG_sampler.R:198-199): stored separately

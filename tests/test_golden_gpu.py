@@ -35,6 +35,9 @@ def test_sweep_injected_matches_golden(name):
             assert rowwise_relerr(dev["E_a"].T, want["E_a"].T) < TOL
             for f in ("Lambda_prec", "resid_Y_prec", "E_a_prec", "delta", "tauh"):
                 assert relerr(dev[f], want[f]) < TOL, f
+            if "Z_2" in d:
+                assert rowwise_relerr(dev["W"].T, want["W"].T) < TOL
+                assert relerr(dev["W_prec"], want["W_prec"]) < TOL
             assert relerr(dev["Plam"], want["Plam"]) < 10 * TOL
             a = sw.aux()
             for f, val in g[f"aux{it}"].items():
@@ -53,6 +56,13 @@ def test_stateless_dropins_match_golden(name):
     st, v, want = g["state0"], g["variates1"], g["state1"]
     b, r = X.shape[1], Z.shape[1]
     H = rp["h2_divisions"]
+    Yfull = Y
+    if "Z_2" in d:
+        # second sample_means_c call (R:214): W from the residual of the NEW B, E_a, Lambda and the OLD F
+        Wn = B.sample_means_c(Y - X @ want["B"].reshape(b, -1) - Z @ want["E_a"] - st["F"] @ want["Lambda"].T, st["resid_Y_prec"],
+                              st["W_prec"], rv["invert_aPXA_bDesignDesignT_rand2"], variates=v["z_W"])
+        assert rowwise_relerr(np.asarray(Wn).T, want["W"].T) < TOL
+        Y = Y - d["Z_2"] @ st["W"]                     # residuals of the Lambda / (B,E_a) steps carry the OLD W
     Lam = B.sample_Lambda_c(Y - X @ st["B"], st["F"], st["resid_Y_prec"], st["E_a_prec"], st["Plam"],
                             rv["invert_aI_bZAZ"], variates=v["z_Lambda"])
     assert rowwise_relerr(Lam, want["Lambda"]) < TOL
@@ -64,6 +74,8 @@ def test_stateless_dropins_match_golden(name):
     assert np.array_equal(np.asarray(h2).ravel(), want["F_h2"])
     Fa = B.sample_F_a_c(st["F"], Z, want["F_h2"], rv["invert_aZZt_Ainv"], variates=v["z_Fa"])
     assert rowwise_relerr(np.asarray(Fa).T, want["F_a"].T) < TOL
+    if "Z_2" in d:
+        Y = Yfull - d["Z_2"] @ want["W"]               # the F step sees the NEW W (R:230)
     F = B.sample_factors_scores_c(Y - X @ want["B"].reshape(b, -1) - Z @ want["E_a"], Z, want["Lambda"],
                                   st["resid_Y_prec"], want["F_a"], want["F_h2"], variates=v["z_F"])
     assert rowwise_relerr(F, want["F"]) < TOL
@@ -71,7 +83,7 @@ def test_stateless_dropins_match_golden(name):
                                        st["resid_Y_prec"], want["F_a"], 1.0 / (1.0 - want["F_h2"]),
                                        np.ones_like(want["F_h2"]), variates=v["z_F"])
     assert rowwise_relerr(Fpx, want["F"]) < TOL
-    prec = np.asarray(B.sample_prec_discrete_conditional_c(Y, H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"],
+    prec = np.asarray(B.sample_prec_discrete_conditional_c(Yfull, H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"],
                                                            st["resid_Y_prec"], variates=g["prec_cond"]["u"])).ravel()
     wp = g["prec_cond"]["Prec"]
     fin = np.isfinite(wp)

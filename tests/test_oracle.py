@@ -44,6 +44,8 @@ def golden_problem(name):
     rv = dict(g["rv"])
     n, p = g["data"]["Y"].shape
     rv.update(n=n, p=p, r=g["data"]["Z_1"].shape[1], b=b)
+    if "Z_2" in g["data"]:
+        rv["A_2_inv"] = np.eye(g["data"]["Z_2"].shape[1])            # fast_BSFG_sampler_init.R:264
     return g, g["data"], rv, pri, rp
 
 
@@ -62,7 +64,7 @@ def test_oracle_reproduces_golden(name):
     for it in (1, 2):
         nxt, aux = O.gibbs_iteration(d, rv, pri, rp, cur, it, g[f"variates{it}"])
         want = g[f"state{it}"]
-        for f in STATE_FIELDS:
+        for f in STATE_FIELDS + (("W", "W_prec") if "Z_2" in d else ()):
             assert relerr(np.asarray(nxt[f]).ravel(), np.asarray(want[f]).ravel()) < 1e-10, (name, it, f)
         for f, val in g[f"aux{it}"].items():
             assert relerr(aux[f], val) < 1e-10, (name, it, f)
@@ -111,6 +113,8 @@ def test_twins_agree_on_reference_fixtures(name):
     from oracle import bsfg_oracle as O, bsfg_oracle_rtwin as R
     g, d, rv, pri, rp, st, v = _twin_inputs(name)
     Y, X, Z = d["Y"], d["X"], d["Z_1"]
+    if "Z_2" in d:
+        Y = Y - d["Z_2"] @ st["W"]           # the twins are per-function: feed them the W-free residual
     H = rp["h2_divisions"]
     tol = 1e-9
     Yt = Y - X @ st["B"]

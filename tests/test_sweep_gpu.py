@@ -104,6 +104,45 @@ def test_sweep_expsum_falls_back_to_exact_gram_when_range_is_too_wide():
         sw.close()
 
 
+@pytest.mark.parametrize("lists", ["stable", "reference"])
+@pytest.mark.parametrize("gram", ["expsum", "exact"])
+def test_sweep_second_random_effect(lists, gram):
+    """Z_2 / W (fast_BSFG_sampler.R:211-216, 248-250): the second sample_means_c call with W_prec and the rand2 list,
+    every residual that carries Z_2 W, and the W_prec Gamma draw."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k, r2 = 55, 41, 5, 9
+    rng = np.random.default_rng(77)
+    setup = I.make_synthetic(n, p, 3, pedigree="halfsib", seed=19)
+    Z2 = np.zeros((n, r2)); Z2[np.arange(n), rng.integers(0, r2, n)] = 1.0
+    setup["Z_2"] = Z2
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=4, lists=lists)
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, gram=gram)
+    try:
+        ora = cs
+        for it in (1, 2):
+            v = I.draw_variates(rng, n, p, k, n, 1 + n, pri, r2=r2)
+            sw.set_state(ora)
+            ora_next, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            _compare_states(dev, ora_next, 1)
+            assert rowwise_relerr(dev["W"].T, ora_next["W"].T) < TOL
+            assert relerr(dev["W_prec"], ora_next["W_prec"]) < TOL
+            a = sw.aux()
+            assert relerr(a["W_prec_rate"], aux["W_prec_rate"]) < TOL
+            assert relerr(a["resid_Y_prec_rate"], aux["resid_Y_prec_rate"]) < TOL
+            ora = ora_next
+        sw.set_state(cs)
+        sw.sweep(3)                      # device Philox path with W
+        out = sw.get_state()
+        assert np.all(np.isfinite(out["W"])) and np.all(out["W_prec"] > 0)
+    finally:
+        sw.close()
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
