@@ -161,7 +161,10 @@ typedef struct bsfg_priors {           /* model_setup.R:49-63, fast_BSFG_sampler
     double W_prec_shape, W_prec_rate;  /* second random effect (model_setup.R:53-54); used when r2 > 0 */
 } bsfg_priors;
 
-/* Constants of one chain (host pointers; Y and everything trait-indexed holds THIS RANK's columns):
+/* Constants of one chain (host pointers; Y and everything trait-indexed holds THIS RANK's columns).  NaN entries of
+ * Y are missing phenotypes (is.na(Y), fast_BSFG_sampler_init.R:69): they are re-imputed at the start of every
+ * iteration (fast_BSFG_sampler.R:180-184) and the rotated data are rebuilt, which costs two n x n x p products per
+ * iteration; set_state must then also supply Lambda and E_a (the imputation conditions on them).
  * Y n x p_local, X n x b, Z_1 n x r (NULL if identity), invert_aI_bZAZ {U n x n, s n},
  * invert_aPXA_bDesignDesignT {U br x br, s1, s2, Design_U n x br}, invert_aZZt_Ainv {U r x r, s1, s2},
  * Ainv r x r (used only by the "direct" E_a_prec form; may be NULL in "diag" mode).               */
@@ -210,6 +213,9 @@ typedef struct bsfg_variates {
     /* second random effect: z_W r2 x p_local (= randn(br,p) of the second sample_means_c call,
      * fast_BSFG_sampler.R:214), g_W p_local ~ Gamma(a + r2/2, 1) (R:249) */
     const double* z_W; const double* g_W;
+    /* missing phenotypes (NaN in Y): z_Y n x p_local N(0,1); element (i,j) is entry i*p + j of the reference's
+     * rnorm(p*n) stream, which it lays out byrow (fast_BSFG_sampler.R:182) */
+    const double* z_Y;
 } bsfg_variates;
 
 /* Gamma (shape, rate) parameters of the last iteration's precision draws, for parity checks. */
@@ -220,6 +226,7 @@ typedef struct bsfg_aux {
     double* delta_rate;         /* k (draw order) */
     double* h2_log_ps;          /* k x H */
     double* W_prec_rate;        /* p_local (r2 > 0) */
+    double* Y_imputed;          /* n x p_local: Y after the last iteration's imputation step (only with missing data) */
 } bsfg_aux;
 
 int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out);

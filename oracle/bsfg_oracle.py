@@ -331,7 +331,8 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     """One pass of the loop body of `fast_BSFG_sampler` with injected variates.
 
     data: dict Y, X, Z_1 and optionally Z_2 (n x r2; then rv has invert_aPXA_bDesignDesignT_rand2 / A_2_inv, the
-          state has W (r2 x p) / W_prec (p) and v has z_W (r2 x p) / g_W (p)); Y has no NaN
+          state has W (r2 x p) / W_prec (p) and v has z_W (r2 x p) / g_W (p)); NaN in Y = missing phenotype, imputed
+          every iteration from v["z_Y"] (n x p) like fast_BSFG_sampler.R:180-184
     rv  : run_variables (Ainv, invert_aI_bZAZ, invert_aPXA_bDesignDesignT, invert_aZZt_Ainv, n,p,r,b)
     st  : current_state dict (modified copy is returned)
     v   : variates dict: z_Lambda (k,p), z_means (br,p), u_h2 (k), z_Fa (r,k), z_F (n,k),
@@ -354,6 +355,16 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
         W, W_prec = np.zeros((0, p)), st.get("W_prec", np.zeros(p))
         ZW = 0.0
     aux = {}
+    # -- fill in missing phenotypes (R:180-184): conditioning on everything else.  `resids` is
+    #    matrix(rnorm(p*n, 0, sqrt(1/resid_Y_prec)), nr=n, nc=p, byrow=T): element (i,j) = z[i*p + j] / sqrt(rp_j);
+    #    v["z_Y"] is that N(0,1) stream already arranged as the (n, p) matrix.
+    Y_missing = np.isnan(Y)
+    if Y_missing.any():
+        meanTraits = X @ B + F @ st["Lambda"].T + Z_1 @ st["E_a"] + ZW
+        resids = v["z_Y"] * np.sqrt(1.0 / st["resid_Y_prec"])[None, :]
+        Y = Y.copy()
+        Y[Y_missing] = meanTraits[Y_missing] + resids[Y_missing]
+        aux["Y_imputed"] = Y
     # -- Lambda (R:189-191)
     Y_tilde = Y - X @ B - ZW
     Lambda = sample_Lambda_c(Y_tilde, F, st["resid_Y_prec"], st["E_a_prec"], st["Plam"],

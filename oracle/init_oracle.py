@@ -248,7 +248,7 @@ def make_synthetic(n, p, k_true, seed=20131, pedigree="random", b=1):
                 error_factor_Lambda=Lambda, n=n, p=p, r=n)
 
 
-def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0):
+def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0, missing=False):
     """One iteration's worth of injected variates in the layouts of oracle.bsfg_oracle.gibbs_iteration."""
     df = priors["Lambda_df"]
     v = dict(z_Lambda=rng.standard_normal((k, p)), z_means=rng.standard_normal((br, p)),
@@ -261,6 +261,8 @@ def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0):
     shapes = [priors["delta_1_shape"] + 0.5 * p * k]
     shapes += [priors["delta_2_shape"] + 0.5 * p * (k - h + 1) for h in delta_loop_indices(k)]
     v["g_delta"] = np.array([rng.gamma(s, 1.0) for s in shapes])
+    if missing:
+        v["z_Y"] = rng.standard_normal((n, p))
     if r2 > 0:
         v["z_W"] = rng.standard_normal((r2, p))
         v["g_W"] = rng.gamma(priors["W_prec_shape"] + r2 / 2.0, 1.0, size=p)

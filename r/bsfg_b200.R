@@ -35,7 +35,6 @@ sample_delta_c <- function(delta, tauh, Lambda_prec, delta_1_shape, delta_1_rate
 bsfg_sweep_loop <- function(BSFG_state, n_samples, k_max = NULL) {
   dm <- BSFG_state$data_matrices; rv <- BSFG_state$run_variables; pr <- BSFG_state$priors
   rp <- BSFG_state$run_parameters; cs <- BSFG_state$current_state
-  stopifnot(sum(dm$Y_missing) == 0)                              # imputation step not on the device path yet (DESIGN.md section 8)
   k <- ncol(cs$F); if (is.null(k_max)) k_max <- max(2 * k, k + 8)
   dims <- as.integer(c(rv$n, rv$p, k, k_max, rv$r, rv$b, rp$h2_divisions, rv$r2))
   pri <- c(pr$resid_Y_prec_shape, pr$resid_Y_prec_rate, pr$E_a_prec_shape, pr$E_a_prec_rate, pr$Lambda_df,

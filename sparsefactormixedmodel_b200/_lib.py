@@ -65,12 +65,12 @@ class bsfg_state(C.Structure):
 class bsfg_variates(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
-                 "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W")]
+                 "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y")]
 
 
 class bsfg_aux(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
-                ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate")]
+                ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate", "Y_imputed")]
 
 
 # every symbol include/bsfg_b200.h declares (tests/test_abi.py checks this list against the header)

@@ -794,6 +794,27 @@ __global__ void trait_reduce_kernel(TraitReduceArgs a, VarSrc g_resid, VarSrc g_
     }
 }
 
+// Missing phenotypes (fast_BSFG_sampler.R:180-184): Y[i,j] = fit[i,j] + z[i,j] / sqrt(rp_j) where Y0[i,j] is NaN, Y0 elsewhere.
+// fit = X B + F Lambda' + Z_1 E_a + Z_2 W.  One CTA per trait column.
+__global__ void impute_missing_kernel(const double* __restrict__ Y0, long ld0, int n, int p, const double* __restrict__ fit,
+                                      long ldf, const double* __restrict__ rp, VarSrc zsrc, double* __restrict__ Y, long ldy) {
+    const int j = blockIdx.x;
+    if (j >= p) return;
+    const double sd = sqrt(1.0 / rp[j]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double y0 = Y0[(long)j * ld0 + i];
+        Y[(long)j * ldy + i] = isnan(y0) ? fit[(long)j * ldf + i] + var_normal(zsrc, i, j) * sd : y0;
+    }
+}
+// dst += src (same shape), used to add Z_1 E_a when Z_1 is the identity
+__global__ void add_inplace_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src, long lds, long rows, long cols) {
+    const long total = rows * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % rows, j = idx / rows;
+        dst[j * ldd + i] += src[j * lds + i];
+    }
+}
+
 // yy[j] = sum_i Y[i,j]^2, one warp per column
 __global__ void colsumsq_kernel(const double* __restrict__ Y, long ld, int n, int p, double* __restrict__ out) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -57,6 +57,8 @@ struct bsfg_ctx {
     bool have_priors = false, have_consts = false, have_state = false;
     int n = 0, pl = 0, p_total = 0, p_off = 0, k = 0, kmax = 0, r = 0, b = 0, br = 0, H = 0;
     bool z1_identity = false;
+    bool has_missing = false;     // NaN in Y: impute + re-rotate every iteration (fast_BSFG_sampler.R:180-184)
+    bsfg::DMat Y0, Ycur, fit, Ft, Xt, v_zY;
     int r2 = 0;                   // second random effect (Z_2 / W), 0: none
     bsfg::DMat Z2, Z2t, Uw, Uwt, A2inv, UtZ2t, DtZ2, DtZ2t, Z2tY, Z2tZ2;          // constants
     bsfg::DVec s1w, s2w, wp;
@@ -153,11 +155,51 @@ static void allreduce(bsfg_ctx* c, double* buf, size_t count) {
 }
 
 struct IterVariates {   // device-side sources for one iteration
-    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD, zW, gW;
+    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD, zW, gW, zY;
 };
 
 static void phase_mark(bsfg_ctx* c, int idx) {
     if (c->phase_timing) BSFG_CUDA(cudaEventRecord(c->ev_phase[idx], c->dev.st));
+}
+
+// rotate the data: U'Y, (U'Y)', Design_U'Y, colSums(Y^2), Z_2'Y  (once at upload; every iteration with missing data)
+static void rotate_data(bsfg_ctx* c, const DMat& Y) {
+    Device& d = c->dev;
+    d.gemm(1.0, c->U1, Y, 0.0, c->UtY);
+    d.transpose(c->UtY, c->UtYt);
+    d.gemm(1.0, c->DU, Y, 0.0, c->DtY);
+    if (c->r2 > 0) d.gemm(1.0, c->Z2, Y, 0.0, c->Z2tY);
+    colsumsq_kernel<<<ceil_div((long)c->pl * 32, 256), 256, 0, d.st>>>(Y.p, Y.ld, c->n, c->pl, c->yy.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+}
+
+// step 0: Y[Y_missing] = (X B + F Lambda' + Z_1 E_a + Z_2 W + resids)[Y_missing]        R:180-184
+static void impute_missing(bsfg_ctx* c, const VarSrc& zY) {
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, k = c->k, r = c->r, b = c->b, r2 = c->r2;
+    if (c->theta_valid) {
+        d.gemm(1.0, c->DUt, c->theta, 0.0, c->fit);                       // Design_U theta = X B + Z_1 E_a
+    } else {                                                              // first iteration after set_state
+        if (!c->Ea_in.p) fail(BSFG_ESTATE, "Y has missing entries: bsfg_set_state must supply E_a");
+        if (b > 0) d.gemm(1.0, c->Xt, c->Bfix, 0.0, c->fit);
+        else c->fit.zero(d.st);
+        if (c->z1_identity) {
+            add_inplace_kernel<<<d.sms * 8, 256, 0, d.st>>>(c->fit.p, c->fit.ld, c->Ea_in.p, c->Ea_in.ld, n, pl);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        } else {
+            d.gemm(1.0, c->Z1t, c->Ea_in, 1.0, c->fit);
+        }
+    }
+    {
+        DMat F = view(c->F, n, k), Ft = view(c->Ft, k, n), Lt = view(c->Lt, k, pl);
+        d.transpose(F, Ft);
+        d.gemm(1.0, Ft, Lt, 1.0, c->fit);                                 // + F Lambda'
+    }
+    if (r2 > 0) d.gemm(1.0, c->Z2t, c->W, 1.0, c->fit);                   // + Z_2 W
+    impute_missing_kernel<<<pl, 256, 0, d.st>>>(c->Y0.p, c->Y0.ld, n, pl, c->fit.p, c->fit.ld, c->rp.p, zY, c->Ycur.p, c->Ycur.ld);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    rotate_data(c, c->Ycur);
+    (void)r;
 }
 
 // ---- one Gibbs iteration (everything but update_k), steps numbered as SURVEY.md section 3.1 ----
@@ -169,6 +211,8 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     DMat Lt = view(c->Lt, k, pl), Lam = view(c->Lam, pl, k), Lmsg = view(c->Lmsg, pl, k), LP = view(c->LP, pl, k);
     DMat Plamt = view(c->Plamt, k, pl);
 
+    // 0. missing phenotypes                                  R:180-184
+    if (c->has_missing) impute_missing(c, v.zY);
     // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
     phase_mark(c, 0);
     const int r2 = c->r2;
@@ -591,15 +635,29 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
         d.sync();
     }
     {   // rotate the data once: U'Y, (U'Y)', Design_U'Y, colSums(Y^2), U'X
-        DMat Y(n, pl);
-        Y.upload(k->Y, d.st);
+        c->has_missing = false;
+        const size_t total = (size_t)n * (size_t)pl;
+        for (size_t e = 0; e < total; e++)
+            if (k->Y[e] != k->Y[e]) { c->has_missing = true; break; }       // is.na(Y), fast_BSFG_sampler_init.R:69
         c->UtY.alloc(n, pl); c->UtYt.alloc(pl, n); c->DtY.alloc(br, pl);
-        d.gemm(1.0, c->U1, Y, 0.0, c->UtY);
-        d.transpose(c->UtY, c->UtYt);
-        d.gemm(1.0, c->DU, Y, 0.0, c->DtY);
-        if (c->r2 > 0) { c->Z2tY.alloc(c->r2, pl); d.gemm(1.0, c->Z2, Y, 0.0, c->Z2tY); }
-        colsumsq_kernel<<<ceil_div((long)pl * 32, 256), 256, 0, d.st>>>(Y.p, Y.ld, n, pl, c->yy.p);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (c->r2 > 0) c->Z2tY.alloc(c->r2, pl);
+        if (c->has_missing) {
+            // rotated data are rebuilt after every imputation; keep Y itself (NaN = missing) on the device
+            c->Y0.alloc(n, pl); c->Ycur.alloc(n, pl); c->fit.alloc(n, pl); c->Ft.alloc(c->kmax, n);
+            c->Y0.upload(k->Y, d.st);
+            if (b > 0) {
+                DMat X(n, b);
+                X.upload(k->X, d.st);
+                c->Xt.alloc(b, n);
+                d.transpose(X, c->Xt);
+                d.sync();
+            }
+        } else {
+            DMat Y(n, pl);
+            Y.upload(k->Y, d.st);
+            rotate_data(c, Y);
+            d.sync();
+        }
         if (b > 0) {
             DMat X(n, b);
             X.upload(k->X, d.st);
@@ -694,6 +752,7 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
     REQUIRE_PTR(st->F); REQUIRE_PTR(st->resid_Y_prec); REQUIRE_PTR(st->E_a_prec); REQUIRE_PTR(st->Plam);
     REQUIRE_PTR(st->delta); REQUIRE_PTR(st->tauh);
     if (c->b > 0) REQUIRE_PTR(st->B);
+    if (c->has_missing) { REQUIRE_PTR(st->Lambda); REQUIRE_PTR(st->E_a); }     // the imputation step conditions on them (R:181)
     const int k = st->k;
     if (k < 2 || k > c->kmax) fail(BSFG_ESHAPE, "bsfg_set_state: k = %d outside [2, k_max = %d]", k, c->kmax);
     Device& d = c->dev;
@@ -802,6 +861,7 @@ extern "C" int bsfg_get_aux(bsfg_ctx* c, bsfg_aux* a) {
     if (a->E_a_prec_rate) c->aux_re.download(a->E_a_prec_rate, d.st);
     if (a->delta_rate) BSFG_CUDA(cudaMemcpyAsync(a->delta_rate, c->delta_rates.p, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, d.st));
     if (a->W_prec_rate && c->r2 > 0) c->aux_rw.download(a->W_prec_rate, d.st);
+    if (a->Y_imputed && c->has_missing) c->Ycur.download(a->Y_imputed, d.st);
     if (a->h2_log_ps) BSFG_CUDA(cudaMemcpyAsync(a->h2_log_ps, c->aux_logps.p, sizeof(double) * (size_t)k * c->H, cudaMemcpyDeviceToHost, d.st));
     d.sync();
     BSFG_API_END
@@ -831,6 +891,7 @@ extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
         v.gD = make_var(nullptr, seed, SITE_G_DELTA, ii, 0, 1);
         v.zW = make_var(nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
         v.gW = make_var(nullptr, seed, SITE_G_W, ii, c->p_off, 1);
+        v.zY = make_var(nullptr, seed, SITE_Z_Y, ii, c->p_off, c->n);
         c->phase_timing = (it == n_iter - 1);
         gibbs_iteration(c, v);
         RngStream rs{seed, SITE_U_K, ii};
@@ -867,6 +928,7 @@ extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
     v.gE = make_var(stage(c->v_gE, hv->g_Ea, pl, 1), seed, SITE_G_EA, ii, c->p_off, 1);
     v.zW = make_var(c->r2 > 0 ? stage(c->v_zW, hv->z_W, c->r2, pl) : nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
     v.gW = make_var(c->r2 > 0 ? stage(c->v_gW, hv->g_W, pl, 1) : nullptr, seed, SITE_G_W, ii, c->p_off, 1);
+    v.zY = make_var(c->has_missing ? stage(c->v_zY, hv->z_Y, n, pl) : nullptr, seed, SITE_Z_Y, ii, c->p_off, n);
     {
         const DMat* gd = nullptr;
         if (hv->g_delta) {       // only as many entries as sample_delta draws: 1 + |2:(k-1)|

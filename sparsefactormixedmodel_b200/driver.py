@@ -26,7 +26,7 @@ from ._lib import as_f, check, ptr
 _STATE_FIELDS = ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
                  "E_a_prec", "delta", "tauh")
 _VARIATE_FIELDS = ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
-                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W")
+                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y")
 
 
 _GRAM_MODES = {"default": 0, "exact": 1, "expsum": 2}
@@ -59,8 +59,7 @@ class BSFGSweep:
                  seed=0, rank=0, world=1, mode="auto", nccl_id=None, gram="default", gram_terms=0, gram_step=0.0):
         self.lib = _lib.load()
         Y = np.asarray(data_matrices["Y"], dtype=np.float64)
-        if np.isnan(Y).any():
-            raise ValueError("missing phenotypes (NaN in Y) are not supported by the device sweep yet")
+        self.has_missing = bool(np.isnan(Y).any())      # re-imputed on the device every iteration (fast_BSFG_sampler.R:180-184)
         X = np.asarray(data_matrices["X"], dtype=np.float64)
         Z_1 = np.asarray(data_matrices["Z_1"], dtype=np.float64)
         Z_2 = data_matrices.get("Z_2")
@@ -205,7 +204,7 @@ class BSFGSweep:
 
         def conv(name, a):
             a = np.asarray(a, dtype=np.float64)
-            if name in ("z_Lambda", "z_means", "z_W"):
+            if name in ("z_Lambda", "z_means", "z_W", "z_Y"):
                 a = a[:, sl]
             elif name in ("g_Lambda_prec",):
                 a = a[sl, :]
@@ -226,9 +225,11 @@ class BSFGSweep:
         k = probe.k
         out = dict(Lambda_prec_rate=np.zeros((self.pl, k), order="F"), resid_Y_prec_rate=np.zeros(self.pl),
                    E_a_prec_rate=np.zeros(self.pl), delta_rate=np.zeros(k + 2), h2_log_ps=np.zeros((k, self.H), order="F"),
-                   W_prec_rate=np.zeros(self.pl))
-        a = _lib.bsfg_aux(*[ptr(out[nm]) for nm in ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate",
-                                                     "delta_rate", "h2_log_ps", "W_prec_rate")])
+                   W_prec_rate=np.zeros(self.pl),
+                   Y_imputed=np.zeros((self.n, self.pl) if self.has_missing else (0, 0), order="F"))
+        a = _lib.bsfg_aux(*[ptr(out[nm]) if out[nm].size else None
+                            for nm in ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps",
+                                       "W_prec_rate", "Y_imputed")])
         check(self.lib.bsfg_get_aux(self._ctx, C.byref(a)))
         return out
 

@@ -16,10 +16,9 @@ literals, state, variates) and the outputs, so
   * `-m gpu` tests push the same stored inputs through the C ABI and compare with the stored outputs.
 
 Fixtures are sub-sampled to stay small (whole half-sib families / whole lines are kept so A stays a valid
-relationship matrix); the Ayroles panel has missing phenotypes, which the device sweep does not handle yet
-(SURVEY.md section 8f-3): its NaNs are replaced by the trait mean here and the case serves as the
-rectangular-Z_1 (n=200 individuals, r=40 lines, b=2) fixture WITH the second random effect of the real data
-(Z_2 200 x 40, W, W_prec; fast_BSFG_sampler.R:211-216, 248-250).
+relationship matrix).  The Ayroles panel is used as it is: rectangular Z_1 (n=200 individuals, r=40 lines), b=2,
+the second random effect of the real data (Z_2 200 x 40, W, W_prec; fast_BSFG_sampler.R:211-216, 248-250) and its
+real missing phenotypes (NaN, re-imputed every iteration, fast_BSFG_sampler.R:180-184).
 """
 import os
 import sys
@@ -53,10 +52,7 @@ def load_setup(name, path, n_keep, p_keep):
         X = X.T
     A = np.asarray(m["A"], dtype=np.float64)
     if name == "ayroles":
-        mu = np.nanmean(Y, axis=0)
-        Y = np.where(np.isnan(Y), mu[None, :], Y)
-        # keep traits with the fewest imputed values first -> deterministic choice
-        keep = np.arange(p_keep)
+        keep = np.arange(p_keep)          # the real missing-data pattern (NaN) is kept: 20% of the panel
         Z_2 = np.asarray(m["Z_2"], dtype=np.float64)
         if Z_2.shape[0] != n:
             Z_2 = Z_2.T
@@ -95,15 +91,16 @@ def main():
         flatten("state0.", {kk: vv for kk, vv in cs.items() if kk not in skip}, out)
         cur = cs
         for it in (1, 2):
-            v = I.draw_variates(rng, n, p, k, r, b + r, pri, r2=r2)
+            v = I.draw_variates(rng, n, p, k, r, b + r, pri, r2=r2, missing=bool(np.isnan(d["Y"]).any()))
             nxt, aux = O.gibbs_iteration(d, rv, pri, rp, cur, it, v)
             flatten(f"variates{it}.", v, out)
             flatten(f"state{it}.", {kk: vv for kk, vv in nxt.items() if kk not in skip}, out)
-            flatten(f"aux{it}.", {kk: vv for kk, vv in aux.items() if kk.endswith("_rate")}, out)
+            flatten(f"aux{it}.", {kk: vv for kk, vv in aux.items() if kk.endswith("_rate") or kk == "Y_imputed"}, out)
             cur = nxt
         # the export that is off the active sweep (fast_BSFG_sampler.R:198-199): stored separately
         u = rng.uniform(size=p)
-        prec = O.sample_prec_discrete_conditional_c(d["Y"], rp["h2_divisions"], pri["h2_priors_factors"],
+        Yc = out.get("aux1.Y_imputed", d["Y"])
+        prec = O.sample_prec_discrete_conditional_c(Yc, rp["h2_divisions"], pri["h2_priors_factors"],
                                                     rv["invert_aI_bZAZ"], cs["resid_Y_prec"], u)
         out["prec_cond.u"] = u
         out["prec_cond.Prec"] = prec

@@ -43,6 +43,9 @@ def test_sweep_injected_matches_golden(name):
             for f, val in g[f"aux{it}"].items():
                 got = a[f][:len(val)] if f == "delta_rate" else a[f]
                 assert relerr(got, val) < TOL, f
+                if f == "Y_imputed":
+                    obs = ~np.isnan(d["Y"])
+                    assert np.array_equal(got[obs], d["Y"][obs])
     finally:
         sw.close()
 
@@ -52,7 +55,7 @@ def test_stateless_dropins_match_golden(name):
     """Each Rcpp-named entry point on the stored inputs of iteration 1, chained like fast_BSFG_sampler.R:189-232."""
     import sparsefactormixedmodel_b200 as B
     g, d, rv, pri, rp = golden_problem(name)
-    Y, X, Z = d["Y"], d["X"], d["Z_1"]
+    Y, X, Z = g["aux1"].get("Y_imputed", d["Y"]), d["X"], d["Z_1"]      # missing phenotypes: iteration 1's imputed Y
     st, v, want = g["state0"], g["variates1"], g["state1"]
     b, r = X.shape[1], Z.shape[1]
     H = rp["h2_divisions"]

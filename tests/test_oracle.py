@@ -69,7 +69,8 @@ def test_oracle_reproduces_golden(name):
         for f, val in g[f"aux{it}"].items():
             assert relerr(aux[f], val) < 1e-10, (name, it, f)
         cur = nxt
-    prec = O.sample_prec_discrete_conditional_c(d["Y"], rp["h2_divisions"], pri["h2_priors_factors"],
+    Yc = g["aux1"].get("Y_imputed", d["Y"])
+    prec = O.sample_prec_discrete_conditional_c(Yc, rp["h2_divisions"], pri["h2_priors_factors"],
                                                 rv["invert_aI_bZAZ"], g["state0"]["resid_Y_prec"], g["prec_cond"]["u"])
     fin = np.isfinite(g["prec_cond"]["Prec"])
     assert np.array_equal(fin, np.isfinite(prec))
@@ -112,7 +113,7 @@ def _twin_inputs(name):
 def test_twins_agree_on_reference_fixtures(name):
     from oracle import bsfg_oracle as O, bsfg_oracle_rtwin as R
     g, d, rv, pri, rp, st, v = _twin_inputs(name)
-    Y, X, Z = d["Y"], d["X"], d["Z_1"]
+    Y, X, Z = g["aux1"].get("Y_imputed", d["Y"]), d["X"], d["Z_1"]      # missing phenotypes: the imputed Y of iteration 1
     if "Z_2" in d:
         Y = Y - d["Z_2"] @ st["W"]           # the twins are per-function: feed them the W-free residual
     H = rp["h2_divisions"]

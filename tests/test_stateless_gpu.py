@@ -71,9 +71,11 @@ def test_sample_Lambda_c(pkg, small_problem, gram):
     assert np.array_equal(got, got2)
 
 
-@pytest.mark.parametrize("n,p,k", [(33, 17, 3), (100, 257, 20), (250, 100, 40), (64, 50, 70)])
+@pytest.mark.parametrize("n,p,k", [(33, 17, 3), (100, 257, 20), (250, 100, 40), (64, 50, 70), (96, 24, 128), (80, 21, 136),
+                                   (120, 19, 200), (72, 9, 232)])
 def test_sample_Lambda_c_shapes(pkg, n, p, k, gram):
-    """ragged sizes incl. odd n (padded leading dimensions), k in each solve bucket (KT=1,2,4)."""
+    """ragged sizes incl. odd n (padded leading dimensions); k across the 4-warp (k <= 128) and 8-warp (k <= 232, the
+    shared-memory limit) instantiations of the blocked Cholesky, incl. k not a multiple of 8."""
     from oracle import bsfg_oracle as O
     rng = np.random.default_rng(n + p + k)
     A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n) * 0.1

@@ -143,6 +143,44 @@ def test_sweep_second_random_effect(lists, gram):
         sw.close()
 
 
+@pytest.mark.parametrize("with_z2", [False, True])
+def test_sweep_missing_phenotypes(with_z2):
+    """NaN in Y (fast_BSFG_sampler.R:180-184): imputed from the current state + rnorm at the start of every iteration,
+    then every rotated quantity is rebuilt.  20% missing, like the Ayroles panel."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k, r2 = 45, 38, 4, (6 if with_z2 else 0)
+    rng = np.random.default_rng(99)
+    setup = I.make_synthetic(n, p, 2, pedigree="halfsib", seed=23)
+    Y = setup["Y"].copy(); Y[rng.uniform(size=Y.shape) < 0.2] = np.nan; Y[:, 3] = setup["Y"][:, 3]   # one complete trait
+    setup["Y"] = Y
+    if with_z2:
+        Z2 = np.zeros((n, r2)); Z2[np.arange(n), rng.integers(0, r2, n)] = 1.0
+        setup["Z_2"] = Z2
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=8, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8)
+    try:
+        sw.set_state(cs)
+        ora = cs
+        for it in (1, 2, 3):                       # free running: iteration 2+ imputes from the device's own theta
+            v = I.draw_variates(rng, n, p, k, n, 1 + n, pri, r2=r2, missing=True)
+            ora, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            a = sw.aux()
+            assert relerr(a["Y_imputed"], aux["Y_imputed"]) < 1e-8
+            assert np.array_equal(a["Y_imputed"][~np.isnan(Y)], Y[~np.isnan(Y)])      # observed entries untouched
+        dev = sw.get_state()
+        _compare_states(dev, ora, 1, tol=1e-7)
+        if with_z2:
+            assert rowwise_relerr(dev["W"].T, ora["W"].T) < 1e-7
+        sw.sweep(2)                                # device Philox path
+        assert np.all(np.isfinite(sw.get_state()["Lambda"]))
+    finally:
+        sw.close()
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
