@@ -291,7 +291,13 @@ def run_ours(args):
     nccl_id = None
     if world > 1:
         nccl_id = bcast_obj(BSFGSweep.nccl_unique_id() if rank == 0 else None)
-    sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k, seed=20131, rank=rank, world=world, nccl_id=nccl_id,
+    # C5 (BASELINE.json configs[4]) runs with update_k live: start at iteration 200 (the i > 200 gate of
+    # BSFG_functions.R:331 is open from the first timed iteration) and leave room for added factors
+    start_iter = args.start_iter if args.start_iter >= 0 else (200 if args.workload == "C5" else 0)
+    k_max = k if start_iter + args.warmup + args.steps + 8 <= 200 else min(k + 16, 232)
+    cs = dict(cs); cs["nrun"] = start_iter
+    live_k = start_iter + args.warmup + args.steps > 200
+    sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k_max, seed=20131, rank=rank, world=world, nccl_id=nccl_id,
                    gram=args.gram)
     sw.set_state(cs)
     mode, r1, r2 = sw.mode()
@@ -337,15 +343,28 @@ def run_ours(args):
         shape = tuple(shape)
         t = torch.empty(shape[::-1], dtype=torch.float64).pin_memory()
         return t.numpy().T if len(shape) > 1 else t.numpy()
-    host = sw.alloc_state(k, with_E_a=False, empty=pinned_empty)      # pinned result buffers, reused every step
+    k_now = sw.get_state(with_E_a=False)["F"].shape[1]                # update_k may have changed k (C5)
+    k_trace = [k, k_now]
+    host = sw.alloc_state(k_now, with_E_a=False, empty=pinned_empty)  # pinned result buffers, reused every step
     sw.get_state(with_E_a=False, out=host)
+    # e2e starts from the state the timed sweep left (same k); trait-indexed members of set_state are given for all p
+    # traits and sliced per rank, so gather this rank's shard back into full-width pinned arrays
     full = dict(cs)
-    # trait-indexed members of set_state are given for all p traits and sliced per rank; keep them pinned
+    if k_now != k or world > 1:
+        full = dict(cs)
+    cur = sw.get_state(with_E_a=False)
+    if k_now != k:
+        def widen(a, cols):
+            out = np.zeros((p, cols)); out[sw.lo:sw.hi] = a
+            return out
+        full.update(Lambda=widen(cur["Lambda"], k_now), Lambda_prec=widen(cur["Lambda_prec"], k_now), Plam=widen(cur["Plam"], k_now),
+                    F=cur["F"], F_a=cur["F_a"], F_h2=cur["F_h2"], delta=cur["delta"], tauh=cur["tauh"], nrun=cur["nrun"])
     for nm in ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "B"):
         full[nm] = pinned(full[nm])
     e2e_steps = max(2, min(args.steps, 5))
-    h2d = 8 * (3 * sw.pl * k + 2 * n * k + sw.b * sw.pl + 2 * sw.pl + 3 * k)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
-    d2h = 8 * (3 * sw.pl * k + n * k + n * k + k + sw.b * sw.pl + 2 * sw.pl + 2 * k)
+    kk_ = k_now
+    h2d = 8 * (3 * sw.pl * kk_ + 2 * n * kk_ + sw.b * sw.pl + 2 * sw.pl + 3 * kk_)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
+    d2h = 8 * (3 * sw.pl * kk_ + n * kk_ + n * kk_ + kk_ + sw.b * sw.pl + 2 * sw.pl + 2 * kk_)
     sw.set_state(full); sw.sweep(1); sw.get_state(with_E_a=False, out=host)         # warm the path
     barrier()
     t0 = time.perf_counter()
@@ -359,12 +378,15 @@ def run_ours(args):
         out = sw.get_state(with_E_a=False, out=host)
         td = time.perf_counter()
         e2e_parts[0] += tb - ta; e2e_parts[1] += tc - tb; e2e_parts[2] += td - tc
-        full.update({nm: out[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})   # replicated members carry over
+        if not live_k:
+            full.update({nm: out[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})   # replicated members carry over
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = e2e_steps / e2e_s
 
-    npairs = k * (k + 1) // 2
+    if live_k:
+        args.no_exact_leg = True          # k moves under update_k: the fixed-k roofline legs do not apply
+    npairs = k_now * (k_now + 1) // 2
     if gstats["mode"] == "expsum":
         # dominant tensor kernel: the trait product Q = (G'A)' E, M = k(k+1)/2, N = p_local, K = R nodes
         kern_flop = 2 * npairs * gstats["terms"] * sw.pl
@@ -372,7 +394,7 @@ def run_ours(args):
         kern_name = (f"dgemm_tn_kernel<128,128,6> (exponential-sum weighted Gram, trait product Q = (G'A)'E: "
                      f"M=k(k+1)/2={npairs}, N=p_local={sw.pl}, K=R={gstats['terms']})")
     else:
-        kern_flop = k * (k + 1) * n * sw.pl
+        kern_flop = k_now * (k_now + 1) * n * sw.pl
         kern_ms = phases["lambda"]
         kern_name = "dgemm_tn_kernel<128,128,6> (exact weighted Gram Q = G'W, M=k(k+1)/2, N=p_local, K=n)"
     achieved = kern_flop / (kern_ms * 1e-3) * 1e-12 if kern_ms > 0 else None
@@ -430,7 +452,9 @@ def run_ours(args):
                                f"random 3-generation pedigree, traits sharded over {world} rank(s)",
                    "parallelism": f"trait-shard x{world}", "l2": "inputs larger than L2 (rotated data 2.4 GB/rank-set, "
                    "Gram operands 1 GB) -- no explicit flush", "formulation": mode,
-                   "diag_identity_residuals": [r1, r2], "update_k": "gated off by i<=200 (uu still drawn)",
+                   "diag_identity_residuals": [r1, r2],
+                   "update_k": (f"LIVE: iterations {start_iter + 1}.. (i > 200), k {k} -> {k_now} after warm-up + timed steps, k_max {k_max}"
+                                if live_k else "gated off by i<=200 (uu still drawn)"),
                    "gram": {kk: gstats[kk] for kk in ("mode", "terms", "step", "fallbacks", "c_min", "c_max")},
                    "rng": "device Philox4x32-10", "setup_s": round(t_setup, 1), "wall_s_timed_region": round(wall, 3)},
         "clocks": clk,
@@ -495,6 +519,7 @@ def main():
     ap.add_argument("--gram", default="default", choices=["default", "expsum", "exact"],
                     help="weighted-Gram evaluation of the Lambda draw (DESIGN.md section 3a)")
     ap.add_argument("--no-exact-leg", action="store_true", help="skip the extra exact-Gram timing beside the default")
+    ap.add_argument("--start-iter", type=int, default=-1, help="current_state$nrun at entry (default 0; 200 for C5 so update_k is live)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
