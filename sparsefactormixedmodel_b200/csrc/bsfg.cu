@@ -6,6 +6,7 @@
 #include "chol_blocked.cuh"
 #include <algorithm>
 #include <map>
+#include <functional>
 
 namespace bsfg {
 static thread_local char g_err[1024] = "";

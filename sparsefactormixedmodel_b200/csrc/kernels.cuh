@@ -153,10 +153,11 @@ struct ExpSumPlan {
     int R, ok;
     double c_min, c_max;
 };
-__global__ void expsum_plan_kernel(const double* __restrict__ ep, const double* __restrict__ rp, int p,
-                                   double s_min, double s_max, double h, int R, int force_exact,
-                                   ExpSumPlan* __restrict__ plan, int* __restrict__ need_exact,
-                                   unsigned long long* __restrict__ fallback_count) {
+// range[0] = -min_j c_j, range[1] = max_j c_j, range[2] = 1 if some c_j is not a positive finite number (else 0):
+// three values that combine over ranks with ONE max-allreduce, so that every rank of a trait-sharded run places the
+// same node grid (the node product G'A is then common work that can be split over the ranks).
+__global__ void expsum_range_kernel(const double* __restrict__ ep, const double* __restrict__ rp, int p,
+                                    double* __restrict__ range) {
     __shared__ double red[32];
     double lo = INFINITY, hi = 0.0;
     bool bad = false;
@@ -165,7 +166,6 @@ __global__ void expsum_plan_kernel(const double* __restrict__ ep, const double* 
         if (!(c > 0.0) || !isfinite(c)) bad = true;
         lo = fmin(lo, c); hi = fmax(hi, c);
     }
-    // block min / max via the sum helper's scratch
     lo = -lo;
     lo = warp_max(lo); hi = warp_max(hi);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -174,7 +174,7 @@ __global__ void expsum_plan_kernel(const double* __restrict__ ep, const double* 
     __syncthreads();
     double t = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
     t = warp_max(t);
-    const double c_min = -__shfl_sync(0xffffffffu, t, 0);
+    const double neg_c_min = __shfl_sync(0xffffffffu, t, 0);
     __syncthreads();
     if (l == 0) red[w] = hi;
     __syncthreads();
@@ -182,18 +182,24 @@ __global__ void expsum_plan_kernel(const double* __restrict__ ep, const double* 
     t = warp_max(t);
     const double c_max = __shfl_sync(0xffffffffu, t, 0);
     const int any_bad = __syncthreads_or(bad ? 1 : 0);
-    if (threadIdx.x == 0) {
-        const double eps = 1e-16;
-        const double x_lo = s_min + c_min, x_hi = s_max + c_max;
-        const double t0 = log(eps / x_hi);
-        const double need = log(-log(eps) / x_lo);
-        const bool ok = !force_exact && !any_bad && x_lo > 0.0 && isfinite(x_hi) && isfinite(t0) && isfinite(need) &&
-                        (t0 + h * (double)(R - 1) >= need);
-        plan->t0 = t0; plan->h = h; plan->R = R; plan->ok = ok ? 1 : 0;
-        plan->c_min = c_min; plan->c_max = c_max;
-        *need_exact = ok ? 0 : 1;
-        if (!ok && !force_exact && fallback_count) *fallback_count += 1ull;
-    }
+    if (threadIdx.x == 0) { range[0] = neg_c_min; range[1] = c_max; range[2] = any_bad ? 1.0 : 0.0; }
+}
+__global__ void expsum_plan_kernel(const double* __restrict__ range, double s_min, double s_max, double h, int R,
+                                   int force_exact, ExpSumPlan* __restrict__ plan, int* __restrict__ need_exact,
+                                   unsigned long long* __restrict__ fallback_count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double c_min = -range[0], c_max = range[1];
+    const bool any_bad = range[2] != 0.0;
+    const double eps = 1e-16;
+    const double x_lo = s_min + c_min, x_hi = s_max + c_max;
+    const double t0 = log(eps / x_hi);
+    const double need = log(-log(eps) / x_lo);
+    const bool ok = !force_exact && !any_bad && x_lo > 0.0 && isfinite(x_hi) && isfinite(t0) && isfinite(need) &&
+                    (t0 + h * (double)(R - 1) >= need);
+    plan->t0 = t0; plan->h = h; plan->R = R; plan->ok = ok ? 1 : 0;
+    plan->c_min = c_min; plan->c_max = c_max;
+    *need_exact = ok ? 0 : 1;
+    if (!ok && !force_exact && fallback_count) *fallback_count += 1ull;
 }
 // A[i,m] = h e^{t_m} exp(-e^{t_m} s_i)            (n x R, column m contiguous over i)
 __global__ void expsum_nodes_kernel(const ExpSumPlan* __restrict__ plan, const double* __restrict__ s, int n,
@@ -241,7 +247,7 @@ __global__ void pack_lower_kernel(const double* __restrict__ A, long ld, int k, 
 template <int KT>
 __global__ void __launch_bounds__(256)
 factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __restrict__ YL, long ldy,
-                   const double* __restrict__ ZFa, long ldz, const double* __restrict__ tau_e, VarSrc zsrc,
+                   const double* __restrict__ ZFa, long ldz, const double* __restrict__ tau_e, VarSrc zsrc, int row0,
                    double* __restrict__ Fout, long ldf) {
     extern __shared__ double sm[];
     const int npairs = k * (k + 1) / 2;
@@ -279,7 +285,7 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 #pragma unroll
         for (int t = 0; t < KT; t++) {
             const int h = lane + 32 * t;
-            if (h < k) x[t] += var_normal(zsrc, row_i, h);      // z is n x k: element (i, h)
+            if (h < k) x[t] += var_normal(zsrc, row_i + row0, h);      // z is n x k: element (i, h); row0 = first row of this rank's block
         }
         for (int j = k - 1; j >= 0; j--) {
             const double* row = L + j * (j + 1) / 2;
@@ -514,8 +520,10 @@ __global__ void prec_from_h2_kernel(const double* __restrict__ res_prec, const d
 // (b3 = U3' Z_1' F; the column scaling by tau_e of cpp:311 commutes with the products)
 // columns with tau_e == 1 or tau_e > 10000 are zeroed here and patched by fa_fixup_kernel.
 // ------------------------------------------------------------------------------------
+// rows [row0, row0 + r) of the r_total-row problem (row0 > 0: one rank's block of a row-sharded draw); b3, v, s1, s2
+// are given already offset to row0, z is addressed with the global row.
 __global__ void fa_v_kernel(const double* __restrict__ b3, long ldb, int r, int k, const double* __restrict__ F_h2,
-                            const double* __restrict__ s1, const double* __restrict__ s2, VarSrc zsrc,
+                            const double* __restrict__ s1, const double* __restrict__ s2, VarSrc zsrc, int row0,
                             double* __restrict__ v, long ldv) {
     const int j = blockIdx.y;
     if (j >= k) return;
@@ -526,21 +534,44 @@ __global__ void fa_v_kernel(const double* __restrict__ b3, long ldb, int r, int 
         double out = 0.0;
         if (!special) {
             const double d = s2[i] * tau_u + s1[i] * tau_e;
-            out = (b3[(long)j * ldb + i] * tau_e) / d + var_normal(zsrc, i, j) / sqrt(d);
+            out = (b3[(long)j * ldb + i] * tau_e) / d + var_normal(zsrc, i + row0, j) / sqrt(d);
         }
         v[(long)j * ldv + i] = out;
     }
 }
-__global__ void fa_fixup_kernel(const double* __restrict__ F, long ldf, int n, int r, int k,
+// rows [row0, row0 + r) (F, Fa given un-offset)
+__global__ void fa_fixup_kernel(const double* __restrict__ F, long ldf, int n, int r, int row0, int k,
                                 const double* __restrict__ F_h2, double* __restrict__ Fa, long lda) {
     const int j = blockIdx.y;
     if (j >= k) return;
     const double tau_e = 1.0 / (1.0 - F_h2[j]);
     if (tau_e == 1.0) {
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x) Fa[(long)j * lda + i] = 0.0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x) Fa[(long)j * lda + row0 + i] = 0.0;
     } else if (tau_e > 10000.0) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r; i += gridDim.x * blockDim.x)
-            Fa[(long)j * lda + i] = (i < n) ? F[(long)j * ldf + i] : 0.0;
+            Fa[(long)j * lda + row0 + i] = (row0 + i < n) ? F[(long)j * ldf + row0 + i] : 0.0;
+    }
+}
+
+// row-block exchange for the row-sharded replicated draws: pack rows [lo, lo+cnt) of C (rows x cols, ldc) into a dense
+// chunk x cols block (zero padded), and scatter `world` such blocks back into C.
+__global__ void pack_rows_kernel(const double* __restrict__ C, long ldc, long lo, long cnt, long chunk, long cols,
+                                 double* __restrict__ block) {
+    const long total = chunk * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % chunk, j = idx / chunk;
+        block[idx] = (i < cnt) ? C[j * ldc + lo + i] : 0.0;
+    }
+}
+__global__ void unpack_rows_kernel(const double* __restrict__ stage, long chunk, long cols, int world, int skip_rank, long rows,
+                                   double* __restrict__ C, long ldc) {
+    const long per = chunk * cols, total = per * world;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(idx / per);
+        if (q == skip_rank) continue;
+        const long e = idx - (long)q * per;
+        const long i = e % chunk, j = e / chunk, row = (long)q * chunk + i;
+        if (row < rows) C[j * ldc + row] = stage[idx];
     }
 }
 

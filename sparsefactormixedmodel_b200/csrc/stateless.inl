@@ -125,14 +125,16 @@ static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int 
 }
 
 static void launch_factor_rows(Device& d, const double* Lp, int k, int n, const double* YL, long ldy,
-                               const double* ZFa, long ldz, const double* tau_e, const VarSrc& z, double* F, long ldf) {
+                               const double* ZFa, long ldz, const double* tau_e, const VarSrc& z, double* F, long ldf,
+                               int row0 = 0 /* data pointers are offset to row0; z is addressed with row0 + i */) {
+    if (n <= 0) return;
     const size_t smem = sizeof(double) * ((size_t)k * (k + 1) / 2);
     const int wpb = 8;
     int blocks = std::min(ceil_div(n, wpb), d.sms * 4);
 #define BSFG_LAUNCH_FR(KT)                                                                                     \
     do {                                                                                                       \
         BSFG_CUDA(cudaFuncSetAttribute(factor_rows_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        factor_rows_kernel<KT><<<blocks, wpb * 32, smem, d.st>>>(Lp, k, n, YL, ldy, ZFa, ldz, tau_e, z, F, ldf); \
+        factor_rows_kernel<KT><<<blocks, wpb * 32, smem, d.st>>>(Lp, k, n, YL, ldy, ZFa, ldz, tau_e, z, row0, F, ldf); \
     } while (0)
     switch (kt_for(k)) {
         case 1: BSFG_LAUNCH_FR(1); break;
@@ -177,10 +179,17 @@ struct LambdaScratch {
     unsigned long long* fallbacks = nullptr;
     cudaEvent_t ev_sub[2] = {nullptr, nullptr};   // after the node product G'A, after the trait product (before the no-op fallback)
     bool sub_timed = false;
+    // trait-sharded runs: the node product G'A does not depend on the traits, so its columns (factor pairs) are split
+    // over the ranks and all-gathered instead of being recomputed by every rank
+    int rank = 0, world = 1;
+    std::function<void(double*, size_t)> allgather;   // in place: this rank's chunk sits at buf + rank * chunk_doubles
+    std::function<void(double*, size_t)> allreduce_max;
+    double* range = nullptr;                          // [-c_min, c_max, bad] (expsum_range_kernel)
     ~LambdaScratch() {
         for (auto& e : ev_sub) if (e) cudaEventDestroy(e);
         if (plan) cudaFree(plan);
         if (need_exact) cudaFree(need_exact);
+        if (range) cudaFree(range);
         if (fallbacks) cudaFree(fallbacks);
     }
     void ensure(long n, long p, long k, long R) {
@@ -191,7 +200,8 @@ struct LambdaScratch {
         if (Mn.rows != k || Mn.cols != p) Mn.alloc(k, p);
         if (R > 0) {
             if (A.rows != n || A.cols != R) A.alloc(n, R);
-            if (Ht.rows != R || Ht.cols != np) Ht.alloc(R, np);
+            const long np_pad = (long)ceil_div(np, world) * world;
+            if (Ht.rows != R || Ht.cols != np_pad) Ht.alloc(R, np_pad);
             if (E.rows != R || E.cols != p) E.alloc(R, p);
         }
         if (!plan) {
@@ -199,6 +209,8 @@ struct LambdaScratch {
             memset_sync(plan, 0, sizeof(ExpSumPlan));
             BSFG_CUDA(cudaMalloc(&need_exact, sizeof(int)));
             memset_sync(need_exact, 0, sizeof(int));
+            BSFG_CUDA(cudaMalloc(&range, 4 * sizeof(double)));
+            memset_sync(range, 0, 4 * sizeof(double));
             BSFG_CUDA(cudaMalloc(&fallbacks, sizeof(unsigned long long)));
             memset_sync(fallbacks, 0, sizeof(unsigned long long));
             for (auto& e : ev_sub) BSFG_CUDA(cudaEventCreate(&e));
@@ -221,7 +233,10 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     if (expsum) {
-        expsum_plan_kernel<<<1, 1024, 0, d.st>>>(ep, rp, p, go.s_min, go.s_max, go.step, R, 0, sc.plan, sc.need_exact, sc.fallbacks);
+        expsum_range_kernel<<<1, 1024, 0, d.st>>>(ep, rp, p, sc.range);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (sc.world > 1 && sc.allreduce_max) sc.allreduce_max(sc.range, 3);   // one node grid for all ranks
+        expsum_plan_kernel<<<1, 32, 0, d.st>>>(sc.range, go.s_min, go.s_max, go.step, R, 0, sc.plan, sc.need_exact, sc.fallbacks);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     {
@@ -240,9 +255,22 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
     }
     if (ev) BSFG_CUDA(cudaEventRecord(ev[0], d.st));
     if (expsum) {
-        d.gemm(1.0, sc.A, sc.Gt, 0.0, sc.Ht);      // Ht[m, pair] = sum_i A[i,m] f_ia f_ib
+        // Ht[m, pair] = sum_i A[i,m] f_ia f_ib
+        if (sc.world > 1 && sc.allgather) {
+            const long chunk = ceil_div(np, sc.world), lo = (long)sc.rank * chunk;
+            const long cnt = std::max(0L, std::min(chunk, (long)np - lo));
+            if (cnt > 0)
+                dgemm_tn(d.st, d.sms, R, (int)cnt, n, 1.0, sc.A.p, sc.A.ld, sc.Gt.p + lo * sc.Gt.ld, sc.Gt.ld, 0.0, nullptr, 0,
+                         sc.Ht.p + lo * sc.Ht.ld, sc.Ht.ld, d.ws.p, Device::WS_DOUBLES);
+            sc.allgather(sc.Ht.p, (size_t)chunk * (size_t)sc.Ht.ld);
+        } else {
+            dgemm_tn(d.st, d.sms, R, np, n, 1.0, sc.A.p, sc.A.ld, sc.Gt.p, sc.Gt.ld, 0.0, nullptr, 0, sc.Ht.p, sc.Ht.ld,
+                     d.ws.p, Device::WS_DOUBLES);
+        }
         if (ev) BSFG_CUDA(cudaEventRecord(sc.ev_sub[0], d.st));
-        d.gemm(1.0, sc.Ht, sc.E, 0.0, sc.Q);       // Q[pair, j]  = sum_m Ht[m,pair] E[m,j]
+        // Q[pair, j]  = sum_m Ht[m,pair] E[m,j]
+        dgemm_tn(d.st, d.sms, np, p, R, 1.0, sc.Ht.p, sc.Ht.ld, sc.E.p, sc.E.ld, 0.0, nullptr, 0, sc.Q.p, sc.Q.ld,
+                 d.ws.p, Device::WS_DOUBLES);
         if (ev) { BSFG_CUDA(cudaEventRecord(sc.ev_sub[1], d.st)); sc.sub_timed = true; }
         // exact fallback: a no-op launch unless the plan kernel raised need_exact
         dgemm_tn(d.st, d.sms, np, p, n, 1.0, sc.Gt.p, sc.Gt.ld, sc.W.p, sc.W.ld, 0.0, nullptr, 0, sc.Q.p, sc.Q.ld,
@@ -517,24 +545,33 @@ extern "C" int bsfg_sample_prec_discrete_conditional_c(const double* Y, int n, i
 // ---- sample_F_a_c (cpp:293-339) ---------------------------------------------------------------
 namespace bsfg {
 // b3 = U3' Z_1' F (r x k), v = elementwise, F_a = U3 v, then branch fix-ups.  Z1 may be null (identity).
+// Rows [row0, row0 + cnt) of the draw (the whole draw when row0 = 0, cnt = r).  `gather(M)` (may be null) completes a
+// row-sharded r x k matrix on every rank; it is called on v before the back-rotation and on Fa at the end.
 static void fa_core(Device& d, const DMat& F, const DMat* Z1, const DMat& U3, const DMat& U3t, const double* s1,
-                    const double* s2, const double* F_h2, const VarSrc& z, DMat& T1, DMat& b3, DMat& v, DMat& Fa) {
+                    const double* s2, const double* F_h2, const VarSrc& z, DMat& T1, DMat& b3, DMat& v, DMat& Fa,
+                    long row0 = 0, long cnt = -1, const std::function<void(DMat&)>* gather = nullptr) {
     const int n = (int)F.rows, k = (int)F.cols, r = (int)U3.rows;
+    if (cnt < 0) cnt = r;
     const DMat* t1 = &F;
     if (Z1) { d.gemm(1.0, *Z1, F, 0.0, T1); t1 = &T1; }    // Z_1' F
     else if (r != n) fail(BSFG_ESHAPE, "Z_1 omitted (identity) but r != n");
-    d.gemm(1.0, U3, *t1, 0.0, b3);                          // U' (Z_1' F), cpp:311
-    {
-        dim3 grid(std::min(ceil_div(r, 256), 64), k);
-        fa_v_kernel<<<grid, 256, 0, d.st>>>(b3.p, b3.ld, r, k, F_h2, s1, s2, z, v.p, v.ld);
+    if (cnt > 0) {
+        // rows of U'(Z_1'F) <-> columns of U
+        dgemm_tn(d.st, d.sms, (int)cnt, k, r, 1.0, U3.p + row0 * U3.ld, U3.ld, t1->p, t1->ld, 0.0, nullptr, 0, b3.p + row0, b3.ld,
+                 d.ws.p, Device::WS_DOUBLES);               // U' (Z_1' F), cpp:311
+        dim3 grid(std::min(ceil_div(cnt, 256), 64), k);
+        fa_v_kernel<<<grid, 256, 0, d.st>>>(b3.p + row0, b3.ld, (int)cnt, k, F_h2, s1 + row0, s2 + row0, z, (int)row0, v.p + row0, v.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
-    d.gemm(1.0, U3t, v, 0.0, Fa);                           // U * (mlam + z/sqrt(d)), cpp:331
-    {
-        dim3 grid(std::min(ceil_div(r, 256), 64), k);
-        fa_fixup_kernel<<<grid, 256, 0, d.st>>>(F.p, F.ld, n, r, k, F_h2, Fa.p, Fa.ld);
+    if (gather) (*gather)(v);
+    if (cnt > 0) {
+        dgemm_tn(d.st, d.sms, (int)cnt, k, r, 1.0, U3t.p + row0 * U3t.ld, U3t.ld, v.p, v.ld, 0.0, nullptr, 0, Fa.p + row0, Fa.ld,
+                 d.ws.p, Device::WS_DOUBLES);               // U * (mlam + z/sqrt(d)), cpp:331
+        dim3 grid(std::min(ceil_div(cnt, 256), 64), k);
+        fa_fixup_kernel<<<grid, 256, 0, d.st>>>(F.p, F.ld, n, (int)cnt, (int)row0, k, F_h2, Fa.p, Fa.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
+    if (gather) (*gather)(Fa);
 }
 }  // namespace bsfg
 

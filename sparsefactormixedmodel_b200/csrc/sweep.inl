@@ -15,6 +15,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     void load() {
@@ -31,6 +32,7 @@ struct NcclApi {
         BSFG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
         BSFG_NCCL_SYM(CommInitRank, "ncclCommInitRank");
         BSFG_NCCL_SYM(AllReduce, "ncclAllReduce");
+        BSFG_NCCL_SYM(AllGather, "ncclAllGather");
         BSFG_NCCL_SYM(CommDestroy, "ncclCommDestroy");
         BSFG_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef BSFG_NCCL_SYM
@@ -92,6 +94,7 @@ struct bsfg_ctx {
     bool aux_on = false;
     // multi-GPU
     ncclComm_t comm = nullptr;
+    bsfg::DVec gstage;            // row-block exchange staging for the row-sharded replicated draws
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_phase;     // (N_PHASES + 1) per iteration slot, reused
@@ -132,26 +135,55 @@ static DMat view_at(double* p, long rows, long cols, long ld) {
     return v;
 }
 
-static void refresh_derived(bsfg_ctx* c) {
-    // UtF = U'F (t(FtU), cpp:107) and FtD = F' Design_U: depend only on F
-    Device& d = c->dev;
-    DMat F = view(c->F, c->n, c->k), UtF = view(c->UtF, c->n, c->k), FtD = view(c->FtD, c->k, c->br);
-    DMat DtF = view(c->DtF, c->br, c->k);
-    d.gemm(1.0, c->U1, F, 0.0, UtF);
-    d.gemm(1.0, F, c->DU, 0.0, FtD);
-    d.transpose(FtD, DtF);
-    if (c->r2 > 0) {
-        DMat FtZ2 = view(c->FtZ2, c->k, c->r2), Z2tF = view(c->Z2tF, c->r2, c->k);
-        d.gemm(1.0, F, c->Z2, 0.0, FtZ2);          // F' Z_2
-        d.transpose(FtZ2, Z2tF);
-    }
-    c->derived_valid = true;
-}
-
+static void refresh_derived(bsfg_ctx* c);
 static void allreduce(bsfg_ctx* c, double* buf, size_t count) {
     if (c->cfg.world <= 1) return;
     if (!c->comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
     BSFG_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->dev.st));
+}
+
+static void allgather_inplace(bsfg_ctx* c, double* buf, size_t chunk_doubles) {
+    if (c->cfg.world <= 1) return;
+    if (!c->comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
+    BSFG_NCCL(g_nccl.AllGather(buf + (size_t)c->cfg.rank * chunk_doubles, buf, chunk_doubles, ncclDouble, c->comm, c->dev.st));
+}
+
+// Row sharding of the REPLICATED work (everything that depends on F only): with `world` ranks each computes rows
+// [lo, lo+cnt) of an (rows x k) result -- rows of C = At'B are columns of At, a contiguous block -- and the blocks are
+// exchanged with one all-gather, so every rank ends with bit-identical copies without redoing the other ranks' rows.
+struct RowShard { long chunk, lo, cnt; };
+static bool shard_replicated_enabled(int what /* 1 rows, 2 node product */) {
+    // diagnostic switch: BSFG_SHARD_REPLICATED=0 none, 1 rows only, 2 node product only, 3 (default) both
+    static const int mask = [] { const char* e = getenv("BSFG_SHARD_REPLICATED"); return e ? atoi(e) : 3; }();
+    return (mask & what) != 0;
+}
+static RowShard row_shard(const bsfg_ctx* c, long rows) {
+    RowShard s;
+    if (c->cfg.world <= 1 || !shard_replicated_enabled(1)) { s.chunk = rows; s.lo = 0; s.cnt = rows; return s; }
+    s.chunk = round_up(ceil_div(rows, c->cfg.world), 2);
+    s.lo = (long)c->cfg.rank * s.chunk;
+    s.cnt = std::max(0L, std::min(s.chunk, rows - s.lo));
+    return s;
+}
+// C[lo:lo+cnt, :] (+)= alpha * At[:, lo:lo+cnt]' B
+static void gemm_rows(bsfg_ctx* c, const RowShard& sh, double alpha, const DMat& At, const DMat& B, double beta, DMat& C) {
+    if (sh.cnt <= 0) return;
+    Device& d = c->dev;
+    dgemm_tn(d.st, d.sms, (int)sh.cnt, (int)B.cols, (int)At.rows, alpha, At.p + sh.lo * At.ld, At.ld, B.p, B.ld, beta,
+             C.p + sh.lo, C.ld, C.p + sh.lo, C.ld, d.ws.p, Device::WS_DOUBLES);
+}
+static void gather_rows(bsfg_ctx* c, const RowShard& sh, DMat& C) {
+    if (c->cfg.world <= 1 || !shard_replicated_enabled(1)) return;
+    Device& d = c->dev;
+    const long cols = C.cols, per = sh.chunk * cols;
+    if ((long)c->gstage.n < per * c->cfg.world) c->gstage.alloc(per * c->cfg.world);
+    const int blocks = (int)std::min<long>((per + 255) / 256, (long)d.sms * 8);
+    pack_rows_kernel<<<std::max(blocks, 1), 256, 0, d.st>>>(C.p, C.ld, sh.lo, sh.cnt, sh.chunk, cols, c->gstage.p + (long)c->cfg.rank * per);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    allgather_inplace(c, c->gstage.p, (size_t)per);
+    const int blocks2 = (int)std::min<long>((per * c->cfg.world + 255) / 256, (long)d.sms * 8);
+    unpack_rows_kernel<<<std::max(blocks2, 1), 256, 0, d.st>>>(c->gstage.p, sh.chunk, cols, c->cfg.world, c->cfg.rank, C.rows, C.p, C.ld);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
 }
 
 struct IterVariates {   // device-side sources for one iteration
@@ -160,6 +192,25 @@ struct IterVariates {   // device-side sources for one iteration
 
 static void phase_mark(bsfg_ctx* c, int idx) {
     if (c->phase_timing) BSFG_CUDA(cudaEventRecord(c->ev_phase[idx], c->dev.st));
+}
+
+static void refresh_derived(bsfg_ctx* c) {
+    // UtF = U'F (t(FtU), cpp:107) and DtF = Design_U'F (+ F'Z_2): depend only on F -> row-sharded over the ranks
+    Device& d = c->dev;
+    DMat F = view(c->F, c->n, c->k), UtF = view(c->UtF, c->n, c->k), FtD = view(c->FtD, c->k, c->br);
+    DMat DtF = view(c->DtF, c->br, c->k);
+    const RowShard sn = row_shard(c, c->n), sb = row_shard(c, c->br);
+    gemm_rows(c, sn, 1.0, c->U1, F, 0.0, UtF);
+    gather_rows(c, sn, UtF);
+    gemm_rows(c, sb, 1.0, c->DU, F, 0.0, DtF);
+    gather_rows(c, sb, DtF);
+    d.transpose(DtF, FtD);
+    if (c->r2 > 0) {
+        DMat FtZ2 = view(c->FtZ2, c->k, c->r2), Z2tF = view(c->Z2tF, c->r2, c->k);
+        d.gemm(1.0, F, c->Z2, 0.0, FtZ2);          // F' Z_2
+        d.transpose(FtZ2, Z2tF);
+    }
+    c->derived_valid = true;
 }
 
 // rotate the data: U'Y, (U'Y)', Design_U'Y, colSums(Y^2), Z_2'Y  (once at upload; every iteration with missing data)
@@ -269,7 +320,10 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     // 5. F_a | F, F_h2                                        R:226 -> cpp:293-339
     {
         DMat T1 = view(c->T1, r, k), b3 = view(c->b3, r, k), vfa = view(c->vfa, r, k);
-        fa_core(d, F, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa);
+        const RowShard sr = row_shard(c, r);
+        std::function<void(DMat&)> gather = [&](DMat& M) { gather_rows(c, sr, M); };
+        fa_core(d, F, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa,
+                sr.lo, sr.cnt, (c->cfg.world > 1 && shard_replicated_enabled(1)) ? &gather : nullptr);
     }
     phase_mark(c, 6);
 
@@ -290,15 +344,18 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     allreduce(c, c->red1.p, (size_t)c->red1.ld * (size_t)k);
     phase_mark(c, 8);
     {
+        // rows of F are independent given the k x k factor: each rank forms and solves its own block of individuals,
+        // then the blocks are all-gathered (bit-identical F on every rank)
         DMat YL = view(c->YL, n, k);
-        d.gemm(1.0, c->U1t, P1, 0.0, YL);
-        d.gemm(-1.0, c->DUt, P2, 1.0, YL);
-        if (r2 > 0) d.gemm(-1.0, c->Z2t, P3, 1.0, YL);                                     // ... - Z_2 W Lmsg  (R:230)
+        const RowShard sn = row_shard(c, n);
+        gemm_rows(c, sn, 1.0, c->U1t, P1, 0.0, YL);
+        gemm_rows(c, sn, -1.0, c->DUt, P2, 1.0, YL);
+        if (r2 > 0) gemm_rows(c, sn, -1.0, c->Z2t, P3, 1.0, YL);                         // ... - Z_2 W Lmsg  (R:230)
         const double* zfa_p = nullptr; long zfa_ld = 0;
         if (c->z1_identity) { zfa_p = Fa.p; zfa_ld = Fa.ld; }
         else {
             DMat ZFa = view(c->ZFa, n, k);
-            d.gemm(1.0, c->Z1t, Fa, 0.0, ZFa);
+            gemm_rows(c, sn, 1.0, c->Z1t, Fa, 0.0, ZFa);
             zfa_p = ZFa.p; zfa_ld = ZFa.ld;
         }
         tau_e_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, k, c->tau_e.p);
@@ -307,7 +364,9 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         VarSrc none = make_var(nullptr, 0, 0, 0, 0, 1);
         launch_chol_solve(d, c->Lp.p, 0, k, 1, c->tau_e.p, 0, 1, nullptr, 0, none, nullptr, 0, c->Lfac.p);
-        launch_factor_rows(d, c->Lfac.p, k, n, YL.p, YL.ld, zfa_p, zfa_ld, c->tau_e.p, v.zF, F.p, F.ld);
+        launch_factor_rows(d, c->Lfac.p, k, (int)sn.cnt, YL.p + sn.lo, YL.ld, zfa_p + sn.lo, zfa_ld, c->tau_e.p, v.zF,
+                           F.p + sn.lo, F.ld, (int)sn.lo);
+        gather_rows(c, sn, F);
     }
     phase_mark(c, 9);
 
@@ -998,5 +1057,12 @@ extern "C" int bsfg_comm_init(bsfg_ctx* c, const char id_in[128]) {
     ncclUniqueId id;
     memcpy(&id, id_in, 128);
     BSFG_NCCL(g_nccl.CommInitRank(&c->comm, c->cfg.world, id, c->cfg.rank));
+    if (shard_replicated_enabled(2)) {
+        c->lsc.rank = c->cfg.rank; c->lsc.world = c->cfg.world;
+        c->lsc.allgather = [c](double* buf, size_t chunk) { allgather_inplace(c, buf, chunk); };
+        c->lsc.allreduce_max = [c](double* buf, size_t count) {
+            BSFG_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclMax, c->comm, c->dev.st));
+        };
+    }
     BSFG_API_END
 }
