@@ -240,6 +240,11 @@ int bsfg_get_aux(bsfg_ctx* ctx, bsfg_aux* aux);
 int bsfg_sweep(bsfg_ctx* ctx, int n_iter);
 /* exactly one iteration with injected variates (the parity path). */
 int bsfg_sweep_injected(bsfg_ctx* ctx, const bsfg_variates* v);
+/* one iteration of the fixed-Lambda sampler (fast_BSFG_sampler_fixedlambda.R:159-236): Lambda (p_local x k, k = the
+ * state's k) is a stored posterior draw; B/E_a, W, F_h2, F_a, F and the precisions are resampled, Lambda, Lambda_prec,
+ * delta and k are not.  The (B,E_a) step also removes X B like that driver does (its line 180).  variates may be NULL
+ * (device Philox) or carry the members used by those steps.                                                         */
+int bsfg_sweep_fixed_lambda(bsfg_ctx* ctx, const double* Lambda, int k, const bsfg_variates* variates);
 /* which residual / E_a_prec formulation the context selected (1 direct, 2 diag) and the measured
  * ||U2' P U2 - diag(s1)||_max, ||Design_U' Design_U - diag(s2)||_max that drove the choice.        */
 int bsfg_get_mode(bsfg_ctx* ctx, int* mode, double* resid_s1, double* resid_s2);

@@ -431,3 +431,54 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
         out.update(res)
     out["nrun"] = i
     return out, aux
+
+
+# --------------------------------------------------------------------------------------
+# One iteration of the fixed-Lambda sampler (fast_BSFG_sampler_fixedlambda.R:159-236)
+# --------------------------------------------------------------------------------------
+def gibbs_iteration_fixedlambda(data, rv, priors, rp, st, Lambda, v):
+    """Lambda (p, k) is a stored posterior draw (`matrix(BSFG_state$Lambda[,j], nr=p)`, :163-164); the loop resamples
+    B/E_a (after ALSO removing X B, :180), W, F_h2, F_a, F and the three precisions; Lambda, Lambda_prec, delta, k stay."""
+    Y, X, Z_1 = data["Y"], data["X"], data["Z_1"]
+    n, p = Y.shape
+    r = Z_1.shape[1]
+    b = X.shape[1]
+    Z_2 = data.get("Z_2")
+    r2 = 0 if Z_2 is None else np.asarray(Z_2).shape[1]
+    st = {k_: (np.array(v_, dtype=np.float64, copy=True) if isinstance(v_, np.ndarray) else v_) for k_, v_ in st.items()}
+    B, F = st["B"], st["F"]
+    Lambda = np.asarray(Lambda, dtype=np.float64)
+    W, W_prec = (st["W"], st["W_prec"]) if r2 > 0 else (np.zeros((0, p)), st.get("W_prec", np.zeros(p)))
+    ZW = (np.asarray(Z_2, dtype=np.float64) @ W) if r2 > 0 else 0.0
+    aux = {}
+    Y_missing = np.isnan(Y)
+    if Y_missing.any():                                                       # :170-174
+        meanTraits = X @ B + F @ Lambda.T + Z_1 @ st["E_a"] + ZW
+        Y = Y.copy()
+        Y[Y_missing] = (meanTraits + v["z_Y"] * np.sqrt(1.0 / st["resid_Y_prec"])[None, :])[Y_missing]
+        aux["Y_imputed"] = Y
+    Y_tilde = Y - F @ Lambda.T - ZW - X @ B                                   # :180 (X B removed too)
+    loc = sample_means_c(Y_tilde, st["resid_Y_prec"], st["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    B = loc[:b, :]
+    E_a = loc[b:b + r, :]
+    if r2 > 0:                                                                # :192-198
+        W = sample_means_c(Y - X @ B - Z_1 @ E_a - F @ Lambda.T, st["resid_Y_prec"], W_prec,
+                           rv["invert_aPXA_bDesignDesignT_rand2"], v["z_W"])
+        ZW = np.asarray(Z_2, dtype=np.float64) @ W
+    F_h2 = sample_h2s_discrete_c(F, rp["h2_divisions"], priors["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"])
+    F_a = sample_F_a_c(F, Z_1, F_h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
+    F = sample_factors_scores_c(Y - X @ B - Z_1 @ E_a - ZW, Z_1, Lambda, st["resid_Y_prec"], F_a, F_h2, v["z_F"])
+    Y_tilde = Y - X @ B - F @ Lambda.T - Z_1 @ E_a - ZW
+    ry_rate = priors["resid_Y_prec_rate"] + 0.5 * np.sum(Y_tilde ** 2, axis=0)
+    ea_rate = priors["E_a_prec_rate"] + 0.5 * np.einsum("ij,ij->j", E_a, rv["Ainv"] @ E_a)
+    out = dict(st)
+    out.update(Lambda=Lambda, B=B, E_a=E_a, F_h2=F_h2, F_a=F_a, F=F, resid_Y_prec=v["g_resid"] / ry_rate,
+               E_a_prec=v["g_Ea"] / ea_rate)
+    aux["resid_Y_prec_rate"], aux["E_a_prec_rate"] = ry_rate, ea_rate
+    if r2 > 0:
+        A2 = rv.get("A_2_inv")
+        A2 = np.eye(r2) if A2 is None else np.asarray(A2, dtype=np.float64)
+        w_rate = priors["W_prec_rate"] + 0.5 * np.einsum("ij,ij->j", W, A2 @ W)
+        out.update(W=W, W_prec=v["g_W"] / w_rate)
+        aux["W_prec_rate"] = w_rate
+    return out, aux

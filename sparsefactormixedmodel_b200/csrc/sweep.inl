@@ -60,7 +60,7 @@ struct bsfg_ctx {
     int n = 0, pl = 0, p_total = 0, p_off = 0, k = 0, kmax = 0, r = 0, b = 0, br = 0, H = 0;
     bool z1_identity = false;
     bool has_missing = false;     // NaN in Y: impute + re-rotate every iteration (fast_BSFG_sampler.R:180-184)
-    bsfg::DMat Y0, Ycur, fit, Ft, Xt, v_zY;
+    bsfg::DMat Y0, Ycur, fit, Ft, Xt, v_zY, DtXt;
     int r2 = 0;                   // second random effect (Z_2 / W), 0: none
     bsfg::DMat Z2, Z2t, Uw, Uwt, A2inv, UtZ2t, DtZ2, DtZ2t, Z2tY, Z2tZ2;          // constants
     bsfg::DVec s1w, s2w, wp;
@@ -254,7 +254,7 @@ static void impute_missing(bsfg_ctx* c, const VarSrc& zY) {
 }
 
 // ---- one Gibbs iteration (everything but update_k), steps numbered as SURVEY.md section 3.1 ----
-static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
+static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambda = false) {
     Device& d = c->dev;
     const int n = c->n, pl = c->pl, k = c->k, r = c->r, b = c->b, br = c->br, H = c->H;
     if (!c->derived_valid) refresh_derived(c);
@@ -267,11 +267,17 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
     phase_mark(c, 0);
     const int r2 = c->r2;
-    if (r2 > 0)        // U'(Y - Z_2 W): R:189 (the X B part is fused into the weight kernel)
-        dgemm_tn(d.st, d.sms, n, pl, r2, -1.0, c->UtZ2t.p, c->UtZ2t.ld, c->W.p, c->W.ld, 1.0, c->UtY.p, c->UtY.ld,
-                 c->UtYw.p, c->UtYw.ld, d.ws.p, Device::WS_DOUBLES);
-    lambda_core(d, c->lsc, c->gram, UtF, r2 > 0 ? c->UtYw : c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
-                Plamt.p, Plamt.ld, 1, v.zL, Lt, c->phase_timing ? &c->ev_phase[1] : nullptr);
+    if (!fixed_lambda) {
+        if (r2 > 0)        // U'(Y - Z_2 W): R:189 (the X B part is fused into the weight kernel)
+            dgemm_tn(d.st, d.sms, n, pl, r2, -1.0, c->UtZ2t.p, c->UtZ2t.ld, c->W.p, c->W.ld, 1.0, c->UtY.p, c->UtY.ld,
+                     c->UtYw.p, c->UtYw.ld, d.ws.p, Device::WS_DOUBLES);
+        lambda_core(d, c->lsc, c->gram, UtF, r2 > 0 ? c->UtYw : c->UtY, c->s.p, c->rp.p, c->ep.p, b > 0 ? &c->UtX : nullptr, b > 0 ? &c->Bfix : nullptr,
+                    Plamt.p, Plamt.ld, 1, v.zL, Lt, c->phase_timing ? &c->ev_phase[1] : nullptr);
+    } else if (c->phase_timing) {
+        // fixed-Lambda sweep (fast_BSFG_sampler_fixedlambda.R:159-236): Lambda is a stored posterior draw, not resampled
+        BSFG_CUDA(cudaEventRecord(c->ev_phase[1], d.st)); BSFG_CUDA(cudaEventRecord(c->ev_phase[2], d.st));
+        BSFG_CUDA(cudaEventRecord(c->ev_phase[3], d.st));
+    }
     {
         dim3 grid(ceil_div(k, 32), ceil_div(pl, 32)), block(32, 8);
         lt_to_lam_kernel<<<grid, block, 0, d.st>>>(Lt.p, Lt.ld, k, pl, c->rp.p, Lam.p, Lam.ld, Lmsg.p, Lmsg.ld);
@@ -283,6 +289,9 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
              c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
     if (r2 > 0)        // ... - Design_U' Z_2 W  (R:203)
         dgemm_tn(d.st, d.sms, br, pl, r2, -1.0, c->DtZ2t.p, c->DtZ2t.ld, c->W.p, c->W.ld, 1.0, c->tmp_brp.p, c->tmp_brp.ld,
+                 c->tmp_brp.p, c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
+    if (fixed_lambda && b > 0)   // the fixed-Lambda driver also removes X B (old B) here: fast_BSFG_sampler_fixedlambda.R:180
+        dgemm_tn(d.st, d.sms, br, pl, b, -1.0, c->DtXt.p, c->DtXt.ld, c->Bfix.p, c->Bfix.ld, 1.0, c->tmp_brp.p, c->tmp_brp.ld,
                  c->tmp_brp.p, c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
     {
         const bool fuse_b = b > 0 && b <= MEANS_BMAX;      // B = location_sample[1:b,] (R:206) reduced in the same pass
@@ -371,7 +380,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     phase_mark(c, 9);
 
     // 7. Lambda_prec | Lambda, tauh                           R:235-236
-    {
+    if (!fixed_lambda) {
         const long total = (long)pl * k;
         int blocks = (int)std::min<long>((total + 255) / 256, (long)d.sms * 8);
         lambda_prec_kernel<<<blocks, 256, 0, d.st>>>(Lam.p, Lam.ld, pl, k, c->tauh.p, c->pri.Lambda_df, v.gLP, LP.p, LP.ld,
@@ -421,6 +430,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v) {
     }
     phase_mark(c, 10);
 
+    if (fixed_lambda) { phase_mark(c, 11); return; }
     // 11-12. delta, tauh, Plam                                R:253-257 -> BSFG_functions.R:272-308
     factor_reduce_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, Lam.p, Lam.ld, pl, k, c->pri.epsilon, c->colsum_cnt.p,
                                               c->colsum_cnt.p + c->kmax);
@@ -718,10 +728,13 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
             d.sync();
         }
         if (b > 0) {
-            DMat X(n, b);
+            DMat X(n, b), DtX(br, b);
             X.upload(k->X, d.st);
             c->UtX.alloc(n, b);
             d.gemm(1.0, c->U1, X, 0.0, c->UtX);
+            c->DtXt.alloc(b, br);
+            d.gemm(1.0, c->DU, X, 0.0, DtX);                 // Design_U'X (fixed-Lambda sweep only)
+            d.transpose(DtX, c->DtXt);
             d.sync();
         }
         d.sync();
@@ -1024,6 +1037,53 @@ extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
         ka.g_delta = *hv->k_g_delta; ka.u_h2 = *hv->k_u_h2; ka.have_scalars = true;
     }
     update_k_step(c, i, uu, have_add ? &ka : nullptr);
+    c->iter = i;
+    finish_timing(c, launches_before, 1);
+    BSFG_API_END
+}
+
+extern "C" int bsfg_sweep_fixed_lambda(bsfg_ctx* c, const double* Lambda, int k, const bsfg_variates* hv) {
+    BSFG_API_BEGIN
+    require_ready(c);
+    REQUIRE_PTR(Lambda);
+    if (k != c->k) fail(BSFG_ESHAPE, "bsfg_sweep_fixed_lambda: Lambda has %d columns, the state has k = %d", k, c->k);
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, r = c->r, br = c->br;
+    const long i = c->iter + 1;
+    const uint64_t seed = c->cfg.seed;
+    const uint32_t ii = (uint32_t)i;
+    {   // Lambda = matrix(BSFG_state$Lambda[,j], nr = p)      fast_BSFG_sampler_fixedlambda.R:163-164
+        DMat Lam = view(c->Lam, pl, k), Lt = view(c->Lt, k, pl);
+        Lam.upload(Lambda, d.st);
+        d.transpose(Lam, Lt);
+    }
+    static const bsfg_variates none = {};
+    if (!hv) hv = &none;
+    auto stage = [&](DMat& buf, const double* host, long rows, long cols) -> const DMat* {
+        if (!host) return nullptr;
+        if (buf.rows != rows || buf.cols != cols) buf.alloc(rows, cols);
+        buf.upload(host, d.st);
+        return &buf;
+    };
+    IterVariates v;
+    v.zL = make_var(nullptr, seed, SITE_Z_LAMBDA, ii, c->p_off, k);
+    v.gLP = make_var(nullptr, seed, SITE_G_LAMBDA_PREC, ii, c->p_off, c->p_total);
+    v.gD = make_var(nullptr, seed, SITE_G_DELTA, ii, 0, 1);
+    v.zM = make_var(stage(c->v_zM, hv->z_means, br, pl), seed, SITE_Z_MEANS, ii, c->p_off, br);
+    v.uh2 = make_var(stage(c->v_uh2, hv->u_h2, k, 1), seed, SITE_U_H2, ii, 0, k);
+    v.zFa = make_var(stage(c->v_zFa, hv->z_Fa, r, k), seed, SITE_Z_FA, ii, 0, r);
+    v.zF = make_var(stage(c->v_zF, hv->z_F, n, k), seed, SITE_Z_F, ii, 0, n);
+    v.gR = make_var(stage(c->v_gR, hv->g_resid, pl, 1), seed, SITE_G_RESID, ii, c->p_off, 1);
+    v.gE = make_var(stage(c->v_gE, hv->g_Ea, pl, 1), seed, SITE_G_EA, ii, c->p_off, 1);
+    v.zW = make_var(c->r2 > 0 ? stage(c->v_zW, hv->z_W, c->r2, pl) : nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
+    v.gW = make_var(c->r2 > 0 ? stage(c->v_gW, hv->g_W, pl, 1) : nullptr, seed, SITE_G_W, ii, c->p_off, 1);
+    v.zY = make_var(c->has_missing ? stage(c->v_zY, hv->z_Y, n, pl) : nullptr, seed, SITE_Z_Y, ii, c->p_off, n);
+    d.sync();
+    c->aux_on = true;
+    c->phase_timing = true;
+    const long long launches_before = g_launch_counter;
+    BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
+    gibbs_iteration(c, v, /*fixed_lambda=*/true);
     c->iter = i;
     finish_timing(c, launches_before, 1);
     BSFG_API_END

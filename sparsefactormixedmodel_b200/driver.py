@@ -219,6 +219,29 @@ class BSFGSweep:
                 setattr(v, name, conv(name, variates[name]))
         check(self.lib.bsfg_sweep_injected(self._ctx, C.byref(v)))
 
+    def sweep_fixed_lambda(self, Lambda, variates=None):
+        """One iteration of the fixed-Lambda sampler (fast_BSFG_sampler_fixedlambda.R:159-236) with `Lambda` (p x k, all
+        traits; sliced to this rank's shard here) a stored posterior draw; `variates` as in sweep_injected, or None."""
+        L = as_f(np.asarray(Lambda, dtype=np.float64)[self.lo:self.hi, :])
+        hold, vptr = [], None
+        if variates is not None:
+            v = _lib.bsfg_variates()
+            sl = slice(self.lo, self.hi)
+            for name in ("z_means", "u_h2", "z_Fa", "z_F", "g_resid", "g_Ea", "z_W", "g_W", "z_Y"):
+                a = variates.get(name)
+                if a is None:
+                    continue
+                a = np.asarray(a, dtype=np.float64)
+                if name in ("z_means", "z_W", "z_Y"):
+                    a = a[:, sl]
+                elif name in ("g_resid", "g_Ea", "g_W"):
+                    a = a.ravel()[sl]
+                a = np.asfortranarray(a) if a.ndim == 2 else np.ascontiguousarray(a.ravel())
+                hold.append(a)
+                setattr(v, name, ptr(a))
+            vptr = C.byref(v)
+        check(self.lib.bsfg_sweep_fixed_lambda(self._ctx, ptr(L), int(L.shape[1]), vptr))
+
     def aux(self):
         probe = _lib.bsfg_state()
         check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))

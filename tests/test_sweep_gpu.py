@@ -181,6 +181,53 @@ def test_sweep_missing_phenotypes(with_z2):
         sw.close()
 
 
+@pytest.mark.parametrize("b,with_z2", [(2, False), (0, True), (1, False)])
+def test_sweep_fixed_lambda(b, with_z2):
+    """fast_BSFG_sampler_fixedlambda.R:159-236: Lambda supplied per iteration, everything else resampled; the (B,E_a)
+    step removes X B as that driver does."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k, r2 = 50, 33, 4, (5 if with_z2 else 0)
+    rng = np.random.default_rng(123)
+    setup = I.make_synthetic(n, p, 2, pedigree="halfsib", seed=29, b=max(b, 1))
+    if b == 0:
+        setup["X"] = np.zeros((n, 0))
+    if with_z2:
+        Z2 = np.zeros((n, r2)); Z2[np.arange(n), rng.integers(0, r2, n)] = 1.0
+        setup["Z_2"] = Z2
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=9, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=6)
+    try:
+        ora = cs
+        for it in (1, 2):
+            Lam = rng.standard_normal((p, k)) * 0.3                       # a "stored posterior draw"
+            v = I.draw_variates(rng, n, p, k, n, b + n, pri, r2=r2)
+            sw.set_state(ora)
+            ora_next, aux = O.gibbs_iteration_fixedlambda(d, rv, pri, rp, ora, Lam, v)
+            sw.sweep_fixed_lambda(Lam, v)
+            dev = sw.get_state()
+            assert np.array_equal(dev["Lambda"], Lam)
+            assert rowwise_relerr(dev["F"], ora_next["F"]) < TOL
+            assert rowwise_relerr(dev["F_a"].T, ora_next["F_a"].T) < TOL
+            assert np.array_equal(dev["F_h2"], np.asarray(ora_next["F_h2"]).ravel())
+            if b > 0:
+                assert relerr(dev["B"], ora_next["B"].reshape(dev["B"].shape)) < TOL
+            assert rowwise_relerr(dev["E_a"].T, ora_next["E_a"].T) < TOL
+            assert relerr(dev["resid_Y_prec"], ora_next["resid_Y_prec"]) < TOL
+            assert relerr(dev["E_a_prec"], ora_next["E_a_prec"]) < TOL
+            assert relerr(dev["delta"], ora["delta"]) == 0.0 and relerr(dev["Lambda_prec"], ora["Lambda_prec"]) == 0.0
+            if with_z2:
+                assert rowwise_relerr(dev["W"].T, ora_next["W"].T) < TOL
+                assert relerr(dev["W_prec"], ora_next["W_prec"]) < TOL
+            ora = ora_next
+        sw.sweep_fixed_lambda(Lam)                                        # device Philox draws
+        assert np.all(np.isfinite(sw.get_state()["F"]))
+    finally:
+        sw.close()
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
