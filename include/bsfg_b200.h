@@ -245,6 +245,28 @@ int bsfg_sweep_injected(bsfg_ctx* ctx, const bsfg_variates* v);
  * delta and k are not.  The (B,E_a) step also removes X B like that driver does (its line 180).  variates may be NULL
  * (device Philox) or carry the members used by those steps.                                                         */
 int bsfg_sweep_fixed_lambda(bsfg_ctx* ctx, const double* Lambda, int k, const bsfg_variates* variates);
+/* ---- posterior bookkeeping on the device: save_posterior_samples (BSFG_functions.R:375-408) without a device->host
+ * copy per saved sample.  bsfg_posterior_begin reserves `capacity` sample slots (and clears earlier ones);
+ * bsfg_sweep_collect runs n_iter iterations and, after every iteration i with (i - burn) %% thin == 0 && i > burn
+ * (fast_BSFG_sampler.R:272), stores sample sp_num = (i - burn)/thin: full traces of Lambda, F, F_a, delta, F_h2 and
+ * the precisions, running means of B, E_a, W.  bsfg_get_posterior copies out what was collected:
+ *   traces, one column per sample in slot order: Lambda (p_local*k_max), F (n*k_max), F_a (r*k_max), delta (k_max),
+ *   F_h2 (k_max) -- each sample is the column-major vec of the (rows x k) matrix, zero padded to k_max columns like the
+ *   reference pads when k grew (:384-391); resid_Y_prec, E_a_prec, W_prec (p_local);
+ *   means: B (b x p_local), E_a (r x p_local), W (r2 x p_local); sp_num[s] = the sample number of slot s, k[s] = the
+ *   number of factors it had.
+ * NULL members are skipped.                                                                                         */
+typedef struct bsfg_posterior {
+    double* Lambda; double* F; double* F_a; double* delta; double* F_h2;
+    double* resid_Y_prec; double* E_a_prec; double* W_prec;
+    double* B; double* E_a; double* W;
+    int* sp_num; int* k;
+} bsfg_posterior;
+int bsfg_posterior_begin(bsfg_ctx* ctx, int capacity);
+int bsfg_sweep_collect(bsfg_ctx* ctx, int n_iter, int burn, int thin);
+int bsfg_posterior_count(bsfg_ctx* ctx, int* n_samples, int* k_max);
+int bsfg_get_posterior(bsfg_ctx* ctx, bsfg_posterior* out);
+
 /* which residual / E_a_prec formulation the context selected (1 direct, 2 diag) and the measured
  * ||U2' P U2 - diag(s1)||_max, ||Design_U' Design_U - diag(s2)||_max that drove the choice.        */
 int bsfg_get_mode(bsfg_ctx* ctx, int* mode, double* resid_s1, double* resid_s2);

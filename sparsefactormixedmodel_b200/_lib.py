@@ -68,6 +68,12 @@ class bsfg_variates(C.Structure):
                  "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y")]
 
 
+class bsfg_posterior(C.Structure):
+    _fields_ = [(nm, c_double_p) for nm in
+                ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec", "W_prec", "B", "E_a", "W")] + \
+               [("sp_num", c_int_p), ("k", c_int_p)]
+
+
 class bsfg_aux(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate", "Y_imputed")]
@@ -81,7 +87,8 @@ EXPORTS = [
     "bsfg_sample_prec_discrete_conditional_c", "bsfg_sample_F_a_c", "bsfg_sample_delta_c",
     "bsfg_dgemm_tn_host", "bsfg_set_gram_default", "bsfg_get_gram_stats",
     "bsfg_create", "bsfg_destroy", "bsfg_set_priors", "bsfg_upload_constants", "bsfg_set_state",
-    "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda", "bsfg_get_mode",
+    "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda",
+    "bsfg_posterior_begin", "bsfg_sweep_collect", "bsfg_posterior_count", "bsfg_get_posterior", "bsfg_get_mode",
     "bsfg_get_timing", "bsfg_nccl_unique_id", "bsfg_comm_init", "bsfg_launch_count",
 ]
 

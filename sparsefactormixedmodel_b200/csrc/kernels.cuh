@@ -846,6 +846,26 @@ __global__ void add_inplace_kernel(double* __restrict__ dst, long ldd, const dou
     }
 }
 
+// ---- posterior bookkeeping on the device (save_posterior_samples, BSFG_functions.R:375-408) ------------------
+// trace slot (rows x kcap, dense) <- current (rows x k, ld), zero padded to kcap columns (the reference pads the sample
+// vector with zeros when k grew, :384-391)
+__global__ void trace_store_kernel(const double* __restrict__ cur, long ld, long rows, int k, int kcap, double* __restrict__ slot) {
+    const long total = rows * kcap;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % rows, h = idx / rows;
+        slot[idx] = (h < k) ? cur[h * ld + i] : 0.0;
+    }
+}
+// running mean exactly as the reference writes it: mean = (mean * (sp_num - 1) + x) / sp_num      (:403-405)
+__global__ void mean_update_kernel(double* __restrict__ mean, long ldm, const double* __restrict__ x, long ldx, long rows, long cols,
+                                   double sp_num) {
+    const long total = rows * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % rows, j = idx / rows;
+        mean[j * ldm + i] = (mean[j * ldm + i] * (sp_num - 1.0) + x[j * ldx + i]) / sp_num;
+    }
+}
+
 // yy[j] = sum_i Y[i,j]^2, one warp per column
 __global__ void colsumsq_kernel(const double* __restrict__ Y, long ld, int n, int p, double* __restrict__ out) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -92,6 +92,12 @@ struct bsfg_ctx {
     bsfg::DMat aux_lp_rate;
     bsfg::DVec aux_rr, aux_re, aux_logps;
     bool aux_on = false;
+    // device-side posterior (bsfg_posterior_begin / bsfg_sweep_collect)
+    int post_cap = 0, post_n = 0;
+    std::vector<int> post_spnum, post_k;
+    bsfg::DMat tr_Lambda, tr_F, tr_Fa, tr_delta, tr_h2, tr_rp, tr_ep, tr_wp;     // one column per sample slot
+    bsfg::DMat mean_theta, mean_W;                                                // running means (B, E_a through theta)
+    double post_mean_count = 0;
     // multi-GPU
     ncclComm_t comm = nullptr;
     bsfg::DVec gstage;            // row-block exchange staging for the row-sharded replicated draws
@@ -971,6 +977,117 @@ extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
         c->iter = i;
     }
     finish_timing(c, launches_before, n_iter);
+    BSFG_API_END
+}
+
+namespace bsfg {
+// one saved sample: save_posterior_samples(sp_num, ...)   BSFG_functions.R:375-408
+static void posterior_store(bsfg_ctx* c, int sp_num) {
+    if (c->post_n >= c->post_cap) fail(BSFG_ESTATE, "posterior capacity (%d samples) exhausted: call bsfg_posterior_begin with more", c->post_cap);
+    if (!c->theta_valid) fail(BSFG_ESTATE, "no sweep has run since set_state: nothing to store");
+    Device& d = c->dev;
+    const int n = c->n, pl = c->pl, r = c->r, k = c->k, km = c->kmax, s = c->post_n;
+    auto store = [&](const double* cur, long ld, long rows, DMat& tr) {
+        const long total = rows * km;
+        trace_store_kernel<<<(int)std::min<long>((total + 255) / 256, (long)d.sms * 8), 256, 0, d.st>>>(cur, ld, rows, k, km,
+                                                                                                 tr.p + (long)s * tr.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    };
+    store(c->Lam.p, c->Lam.ld, pl, c->tr_Lambda);
+    store(c->F.p, c->F.ld, n, c->tr_F);
+    store(c->Fa.p, c->Fa.ld, r, c->tr_Fa);
+    store(c->delta.p, 1, 1, c->tr_delta);
+    store(c->F_h2.p, 1, 1, c->tr_h2);
+    BSFG_CUDA(cudaMemcpyAsync(c->tr_rp.p + (long)s * c->tr_rp.ld, c->rp.p, sizeof(double) * pl, cudaMemcpyDeviceToDevice, d.st));
+    BSFG_CUDA(cudaMemcpyAsync(c->tr_ep.p + (long)s * c->tr_ep.ld, c->ep.p, sizeof(double) * pl, cudaMemcpyDeviceToDevice, d.st));
+    if (c->r2 > 0)
+        BSFG_CUDA(cudaMemcpyAsync(c->tr_wp.p + (long)s * c->tr_wp.ld, c->wp.p, sizeof(double) * pl, cudaMemcpyDeviceToDevice, d.st));
+    // B and E_a are linear in theta ([B;E_a] = U theta, cpp:78), so their running means are U * (running mean of theta)
+    {
+        const long total = (long)c->br * pl;
+        mean_update_kernel<<<(int)std::min<long>((total + 255) / 256, (long)d.sms * 8), 256, 0, d.st>>>(
+            c->mean_theta.p, c->mean_theta.ld, c->theta.p, c->theta.ld, c->br, pl, (double)sp_num);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (c->r2 > 0) {
+            const long tw = (long)c->r2 * pl;
+            mean_update_kernel<<<(int)std::min<long>((tw + 255) / 256, (long)d.sms * 8), 256, 0, d.st>>>(
+                c->mean_W.p, c->mean_W.ld, c->W.p, c->W.ld, c->r2, pl, (double)sp_num);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+    }
+    c->post_spnum.push_back(sp_num); c->post_k.push_back(k);
+    c->post_n++;
+}
+}  // namespace bsfg
+
+extern "C" int bsfg_posterior_begin(bsfg_ctx* c, int capacity) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c);
+    if (capacity <= 0) fail(BSFG_EARG, "capacity must be positive");
+    const int n = c->n, pl = c->pl, r = c->r, km = c->kmax;
+    c->tr_Lambda.alloc((long)pl * km, capacity); c->tr_F.alloc((long)n * km, capacity); c->tr_Fa.alloc((long)r * km, capacity);
+    c->tr_delta.alloc(km, capacity); c->tr_h2.alloc(km, capacity);
+    c->tr_rp.alloc(pl, capacity); c->tr_ep.alloc(pl, capacity);
+    if (c->r2 > 0) { c->tr_wp.alloc(pl, capacity); c->mean_W.alloc(c->r2, pl); }
+    c->mean_theta.alloc(c->br, pl);
+    c->post_cap = capacity; c->post_n = 0; c->post_spnum.clear(); c->post_k.clear();
+    BSFG_API_END
+}
+
+extern "C" int bsfg_posterior_count(bsfg_ctx* c, int* n_samples, int* k_max) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c);
+    if (n_samples) *n_samples = c->post_n;
+    if (k_max) *k_max = c->kmax;
+    BSFG_API_END
+}
+
+extern "C" int bsfg_get_posterior(bsfg_ctx* c, bsfg_posterior* o) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(c); REQUIRE_PTR(o);
+    Device& d = c->dev;
+    const int S = c->post_n, pl = c->pl, r = c->r, b = c->b, br = c->br;
+    auto dl = [&](const DMat& tr, double* host) {
+        if (!host || S == 0) return;
+        BSFG_CUDA(cudaMemcpy2DAsync(host, tr.rows * sizeof(double), tr.p, tr.ld * sizeof(double), tr.rows * sizeof(double), S,
+                                    cudaMemcpyDeviceToHost, d.st));
+    };
+    dl(c->tr_Lambda, o->Lambda); dl(c->tr_F, o->F); dl(c->tr_Fa, o->F_a); dl(c->tr_delta, o->delta); dl(c->tr_h2, o->F_h2);
+    dl(c->tr_rp, o->resid_Y_prec); dl(c->tr_ep, o->E_a_prec);
+    if (c->r2 > 0) { dl(c->tr_wp, o->W_prec); if (o->W && S > 0) c->mean_W.download(o->W, d.st); }
+    if (S > 0 && (o->B || o->E_a)) {
+        DMat loc = view(c->tmp_brp, br, pl);                    // scratch that is dead between iterations
+        d.gemm(1.0, c->U2t, c->mean_theta, 0.0, loc);           // mean([B;E_a]) = U mean(theta)
+        if (o->B && b > 0)
+            BSFG_CUDA(cudaMemcpy2DAsync(o->B, b * sizeof(double), loc.p, loc.ld * sizeof(double), b * sizeof(double), pl,
+                                        cudaMemcpyDeviceToHost, d.st));
+        if (o->E_a)
+            BSFG_CUDA(cudaMemcpy2DAsync(o->E_a, r * sizeof(double), loc.p + b, loc.ld * sizeof(double), r * sizeof(double), pl,
+                                        cudaMemcpyDeviceToHost, d.st));
+    }
+    if (o->sp_num) for (int s = 0; s < S; s++) o->sp_num[s] = c->post_spnum[s];
+    if (o->k) for (int s = 0; s < S; s++) o->k[s] = c->post_k[s];
+    d.sync();
+    BSFG_API_END
+}
+
+extern "C" int bsfg_sweep_collect(bsfg_ctx* c, int n_iter, int burn, int thin) {
+    BSFG_API_BEGIN
+    require_ready(c);
+    if (n_iter < 0 || thin <= 0 || burn < 0) fail(BSFG_EARG, "bsfg_sweep_collect: n_iter >= 0, burn >= 0, thin > 0 required");
+    if (c->post_cap <= 0) fail(BSFG_ESTATE, "call bsfg_posterior_begin first");
+    int done = 0;
+    while (done < n_iter) {
+        // run up to the next thinning boundary (fast_BSFG_sampler.R:272), store, continue
+        long i = c->iter, nxt = std::max<long>(i + 1, burn + 1);
+        while ((nxt - burn) % thin != 0) nxt++;
+        const int step = (int)std::min<long>(nxt - i, n_iter - done);
+        const int rc = bsfg_sweep(c, step);
+        if (rc != BSFG_OK) return rc;
+        done += step;
+        if (c->iter == nxt) posterior_store(c, (int)((nxt - burn) / thin));
+    }
+    c->dev.sync();
     BSFG_API_END
 }
 

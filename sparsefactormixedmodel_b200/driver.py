@@ -242,6 +242,39 @@ class BSFGSweep:
             vptr = C.byref(v)
         check(self.lib.bsfg_sweep_fixed_lambda(self._ctx, ptr(L), int(L.shape[1]), vptr))
 
+    # -- device-side posterior bookkeeping (save_posterior_samples, BSFG_functions.R:375-408) -------------
+    def posterior_begin(self, capacity):
+        check(self.lib.bsfg_posterior_begin(self._ctx, int(capacity)))
+
+    def collect(self, n_iter, burn, thin):
+        """n_iter iterations; samples on the reference's burn/thin schedule stay on the device."""
+        check(self.lib.bsfg_sweep_collect(self._ctx, int(n_iter), int(burn), int(thin)))
+
+    def posterior(self):
+        """Collected samples in the reference's Posterior layout (this rank's traits): traces are (rows*k_max) x S with
+        each column the column-major vec of the sample, zero padded to k_max factor columns; B, E_a, W running means."""
+        S = C.c_int(0); km = C.c_int(0)
+        check(self.lib.bsfg_posterior_count(self._ctx, C.byref(S), C.byref(km)))
+        S, km = S.value, km.value
+        out = dict(Lambda=np.zeros((self.pl * km, S), order="F"), F=np.zeros((self.n * km, S), order="F"),
+                   F_a=np.zeros((self.r * km, S), order="F"), delta=np.zeros((km, S), order="F"), F_h2=np.zeros((km, S), order="F"),
+                   resid_Y_prec=np.zeros((self.pl, S), order="F"), E_a_prec=np.zeros((self.pl, S), order="F"),
+                   W_prec=np.zeros((self.pl, S), order="F"), B=np.zeros((self.b, self.pl), order="F"),
+                   E_a=np.zeros((self.r, self.pl), order="F"), W=np.zeros((self.r2, self.pl), order="F"))
+        sp = np.zeros(max(S, 1), dtype=np.int32)
+        ks = np.zeros(max(S, 1), dtype=np.int32)
+        po = _lib.bsfg_posterior()
+        for name in ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec", "W_prec", "B", "E_a", "W"):
+            if out[name].size:
+                setattr(po, name, ptr(out[name]))
+        po.sp_num = sp.ctypes.data_as(_lib.c_int_p)
+        po.k = ks.ctypes.data_as(_lib.c_int_p)
+        check(self.lib.bsfg_get_posterior(self._ctx, C.byref(po)))
+        out["sp_num"] = sp[:S].copy()
+        out["k"] = ks[:S].copy()
+        out["k_max"] = km
+        return out
+
     def aux(self):
         probe = _lib.bsfg_state()
         check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))
@@ -292,7 +325,7 @@ class BSFGSweep:
 # ------------------------------------------------------------------------------------------
 # fast_BSFG_sampler (R_BSFG/fast_BSFG_sampler.R) -- same entry point, state dict in, state dict out
 # ------------------------------------------------------------------------------------------
-def _save_posterior_samples(sp_num, Posterior, cs):
+def _save_posterior_samples(sp_num, Posterior, cs, traces_only=False):
     """BSFG_functions.R:375-408: full traces for Lambda, F, F_a, delta, F_h2 and the precisions (rows grow
     when update_k adds factors), running means for B and E_a."""
     def put(name, vec):
@@ -308,7 +341,7 @@ def _save_posterior_samples(sp_num, Posterior, cs):
         Posterior[name] = M
     for name in ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec", "W_prec"):
         put(name, cs[name])
-    for name in ("B", "E_a", "W"):
+    for name in (() if traces_only else ("B", "E_a", "W")):
         prev = Posterior.get(name)
         cur = np.asarray(cs[name], dtype=np.float64)
         if prev is None or np.shape(prev) != cur.shape:
@@ -338,22 +371,35 @@ def fast_BSFG_sampler(BSFG_state, n_samples, *, seed=None, sweep=None):
                           k_init=np.asarray(cs["F"]).shape[1], seed=seed)
     try:
         sweep.set_state(cs)
-        i = start_i
         end = start_i + int(n_samples)
-        while i < end:
-            # run up to the next thinning boundary (fast_BSFG_sampler.R:272)
-            nxt = end
-            if thin > 0:
-                j = max(i + 1, burn + 1)
-                while (j - burn) % thin != 0:
-                    j += 1
-                if j <= end:
-                    nxt = j
-            sweep.sweep(nxt - i)
-            i = nxt
-            if (i - burn) % thin == 0 and i > burn:
-                sp_num = (i - burn) // thin
-                Posterior = _save_posterior_samples(sp_num, Posterior, sweep.get_state(with_E_a=True))
+        # samples that fall inside this call (fast_BSFG_sampler.R:272): kept on the device, read back once at the end
+        n_keep = sum(1 for i in range(start_i + 1, end + 1) if i > burn and (i - burn) % thin == 0) if thin > 0 else 0
+        if n_keep > 0:
+            sweep.posterior_begin(n_keep)
+            sweep.collect(int(n_samples), burn, thin)
+            post = sweep.posterior()
+            km = post["k_max"]
+            for s in range(len(post["sp_num"])):
+                kk = int(post["k"][s])
+                sample = dict(Lambda=post["Lambda"][:, s].reshape(sweep.pl, km, order="F")[:, :kk],
+                              F=post["F"][:, s].reshape(sweep.n, km, order="F")[:, :kk],
+                              F_a=post["F_a"][:, s].reshape(sweep.r, km, order="F")[:, :kk],
+                              delta=post["delta"][:kk, s], F_h2=post["F_h2"][:kk, s],
+                              resid_Y_prec=post["resid_Y_prec"][:, s], E_a_prec=post["E_a_prec"][:, s], W_prec=post["W_prec"][:, s])
+                Posterior = _save_posterior_samples(int(post["sp_num"][s]), Posterior, sample, traces_only=True)
+            # running means of B, E_a, W: combine the device means of this call's samples with what was there before
+            first, last = int(post["sp_num"][0]), int(post["sp_num"][-1])
+            for name in ("B", "E_a", "W"):
+                cur = post[name]
+                prev = Posterior.get(name)
+                if prev is None or np.shape(prev) != cur.shape or first == 1:
+                    Posterior[name] = cur if first == 1 else cur
+                else:
+                    # the device mean was started at sample `first` with the reference's recursion seeded by zero, i.e. it
+                    # equals (sum of this call's samples) / last; add the earlier samples' share
+                    Posterior[name] = prev * (first - 1) / last + cur
+        else:
+            sweep.sweep(int(n_samples))
         new_cs = sweep.get_state(with_E_a=True)
     finally:
         if own:

@@ -228,6 +228,48 @@ def test_sweep_fixed_lambda(b, with_z2):
         sw.close()
 
 
+def test_device_posterior_matches_host_bookkeeping():
+    """bsfg_sweep_collect keeps save_posterior_samples (BSFG_functions.R:375-408) on the device: same chain (same seed),
+    samples pulled with get_state at every thinning boundary on the host vs collected on the device must be identical
+    for the traces and agree to rounding for the running means (B, E_a go through the mean of theta)."""
+    from oracle import init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 40, 30, 5
+    st = _build(n, p, k, "stable", seed=17)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    burn, thin, iters = 3, 2, 11                    # samples at i = 5, 7, 9, 11
+    a = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, seed=5)
+    bsw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, seed=5)
+    try:
+        a.set_state(cs); bsw.set_state(cs)
+        host = []
+        a.sweep(burn + thin)
+        for s in range(4):
+            host.append(a.get_state())
+            if s < 3:
+                a.sweep(thin)
+        bsw.posterior_begin(8)
+        bsw.collect(iters, burn, thin)
+        post = bsw.posterior()
+        assert list(post["sp_num"]) == [1, 2, 3, 4] and post["k_max"] == 8
+        for s, hs in enumerate(host):
+            kk = hs["F"].shape[1]
+            for name, rows in (("Lambda", p), ("F", n), ("F_a", n)):
+                got = post[name][:, s].reshape(rows, 8, order="F")
+                assert np.array_equal(got[:, :kk], hs[name]) and not got[:, kk:].any()
+            assert np.array_equal(post["delta"][:kk, s], hs["delta"]) and np.array_equal(post["F_h2"][:kk, s], hs["F_h2"])
+            assert np.array_equal(post["resid_Y_prec"][:, s], hs["resid_Y_prec"])
+            assert np.array_equal(post["E_a_prec"][:, s], hs["E_a_prec"])
+        Bm = np.zeros_like(host[0]["B"]); Em = np.zeros_like(host[0]["E_a"])
+        for s, hs in enumerate(host, start=1):
+            Bm = (Bm * (s - 1) + hs["B"]) / s; Em = (Em * (s - 1) + hs["E_a"]) / s
+        assert relerr(post["B"], Bm) < 1e-12 and relerr(post["E_a"], Em) < 1e-12
+        # both chains ended in the same state
+        assert np.array_equal(bsw.get_state()["F"], a.get_state()["F"])
+    finally:
+        a.close(); bsw.close()
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
@@ -356,3 +398,9 @@ def test_fast_BSFG_sampler_contract():
     out2 = fast_BSFG_sampler(out, 4, seed=3)                       # continuation (README.md:33)
     assert out2["current_state"]["nrun"] == 14
     assert out2["Posterior"]["Lambda"].shape[1] == 5
+    # "should be the same as running one continuous chain" (README.md:33): 10 + 4 iterations == 14 in one call
+    one = fast_BSFG_sampler(st, 14, seed=3)
+    assert np.array_equal(one["Posterior"]["Lambda"], out2["Posterior"]["Lambda"])
+    assert np.array_equal(one["current_state"]["F"], out2["current_state"]["F"])
+    assert relerr(out2["Posterior"]["E_a"], one["Posterior"]["E_a"]) < 1e-12
+    assert relerr(out2["Posterior"]["B"], one["Posterior"]["B"]) < 1e-12
