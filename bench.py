@@ -101,26 +101,37 @@ def make_problem(n, p, k, seed=20131, device=None):
     del U_act, E_act
     X = torch.ones(n, 1, dtype=f64, device=dev)
     b = 1
-    # --- the three diagonalisations (same contract as fast_BSFG_sampler_init.R:263-325), eigen route
-    s, U = torch.linalg.eigh(A)
-    s = s.flip(0).clamp_min(0.0).contiguous(); U = U.flip(1).contiguous()
-    Ainv = torch.linalg.inv(A); Ainv = 0.5 * (Ainv + Ainv.T)
-    br = b + n
-    P = torch.zeros(br, br, dtype=f64, device=dev); P[0, 0] = 1e-10; P[b:, b:] = Ainv
-    D = torch.cat([X, torch.eye(n, dtype=f64, device=dev)], dim=1)
-    D2 = D.T @ D
-    Lc = torch.linalg.cholesky(P + D2)
-    Li = torch.linalg.solve_triangular(Lc, torch.eye(br, dtype=f64, device=dev), upper=False)
-    M = Li @ D2 @ Li.T; M = 0.5 * (M + M.T)
-    lam, V = torch.linalg.eigh(M)
-    lam = lam.clamp(0.0, 1.0)
-    U2 = Li.T @ V
-    s1_2, s2_2 = 1.0 - lam, lam
-    Design_U = D @ U2
-    del P, D, D2, Lc, Li, M, V
-    t2 = s / (1.0 + s)                      # Z_1 = I: U3 = U diag(t), U3'U3 = t^2 = s1, U3'Ainv U3 = t^2/s = s2
-    U3 = U * t2.sqrt()[None, :]
-    s1_3, s2_3 = t2, 1.0 - t2
+    # --- the three diagonalisations (contract of fast_BSFG_sampler_init.R:263-325): the library's own device init
+    #     (bsfg_init_lists, cuSOLVER) when a GPU is present, else the same eigen route through torch on the CPU
+    A_host = np.asfortranarray(A.cpu().numpy())
+    X_host = np.asfortranarray(X.cpu().numpy())
+    lists = None
+    if dev.type == "cuda":
+        del A, L_A
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+        import sparsefactormixedmodel_b200 as pkg
+        with torch.cuda.device(dev):
+            lists = pkg.init_lists(None, A_host, X_host, None, b_X_prec=1e-10)
+    else:
+        s, U = torch.linalg.eigh(A)
+        s = s.flip(0).clamp_min(0.0).contiguous(); U = U.flip(1).contiguous()
+        Ainv = torch.linalg.inv(A); Ainv = 0.5 * (Ainv + Ainv.T)
+        br = b + n
+        P = torch.zeros(br, br, dtype=f64, device=dev); P[0, 0] = 1e-10; P[b:, b:] = Ainv
+        D = torch.cat([X, torch.eye(n, dtype=f64, device=dev)], dim=1)
+        D2 = D.T @ D
+        Lc = torch.linalg.cholesky(P + D2)
+        Li = torch.linalg.solve_triangular(Lc, torch.eye(br, dtype=f64, device=dev), upper=False)
+        M = Li @ D2 @ Li.T; M = 0.5 * (M + M.T)
+        lam, V = torch.linalg.eigh(M)
+        lam = lam.clamp(0.0, 1.0)
+        U2 = Li.T @ V
+        t2 = s / (1.0 + s)                      # Z_1 = I: U3 = U diag(t), U3'U3 = t^2 = s1, U3'Ainv U3 = t^2/s = s2
+        cpu_ = lambda t: np.asfortranarray(t.cpu().numpy())
+        lists = dict(Ainv=cpu_(Ainv), invert_aI_bZAZ=dict(U=cpu_(U), s=s.cpu().numpy()),
+                     invert_aPXA_bDesignDesignT=dict(U=cpu_(U2), s1=(1.0 - lam).cpu().numpy(), s2=lam.cpu().numpy(),
+                                                     Design_U=cpu_(D @ U2)),
+                     invert_aZZt_Ainv=dict(U=cpu_(U * t2.sqrt()[None, :]), s1=t2.cpu().numpy(), s2=(1.0 - t2).cpu().numpy()))
     H = 50
     run_parameters = dict(b0=1.0, b1=0.0005, epsilon=1e-2, prop=1.00, h2_divisions=H, save_freq=100, burn=2000,
                           thin=400, draw_iter=200, simulation=True)
@@ -142,12 +153,9 @@ def make_problem(n, p, k, seed=20131, device=None):
     F = F_a + rng.standard_normal((n, k)) * np.sqrt(1 - F_h2)[None, :]
     B = rng.standard_normal((b, p))
     cpu = lambda t: np.asfortranarray(t.cpu().numpy())
-    data = dict(Y=cpu(Y), X=cpu(X), Z_1=np.eye(n), Z_2=np.zeros((n, 0)))
-    rv = dict(p=p, n=n, r=n, r2=0, b=b, Ainv=cpu(Ainv),
-              invert_aI_bZAZ=dict(U=cpu(U), s=s.cpu().numpy()),
-              invert_aPXA_bDesignDesignT=dict(U=cpu(U2), s1=s1_2.cpu().numpy(), s2=s2_2.cpu().numpy(),
-                                              Design_U=cpu(Design_U)),
-              invert_aZZt_Ainv=dict(U=cpu(U3), s1=s1_3.cpu().numpy(), s2=s2_3.cpu().numpy()))
+    data = dict(Y=cpu(Y), X=X_host, Z_1=np.eye(n), Z_2=np.zeros((n, 0)))
+    rv = dict(p=p, n=n, r=n, r2=0, b=b, Ainv=lists["Ainv"], invert_aI_bZAZ=lists["invert_aI_bZAZ"],
+              invert_aPXA_bDesignDesignT=lists["invert_aPXA_bDesignDesignT"], invert_aZZt_Ainv=lists["invert_aZZt_Ainv"])
     cs = dict(resid_Y_prec=resid_Y_prec, Lambda_prec=Lambda_prec, delta=delta, tauh=tauh, Plam=Plam, Lambda=Lambda,
               F_h2=F_h2, E_a_prec=E_a_prec, F_a=F_a, F=F, B=B, E_a=None, nrun=0)
     if dev.type == "cuda":

@@ -280,6 +280,25 @@ int bsfg_get_gram_stats(bsfg_ctx* ctx, int* mode, int* terms, double* step, long
 #define BSFG_N_PHASES 12
 int bsfg_get_timing(bsfg_ctx* ctx, double* total_ms, long long* launches, double* phase_ms);
 
+/* ------------------------------------------------------------------------------------------
+ * Device init: the precomputed lists of fast_BSFG_sampler_init.R:263-325 (Ainv, svd(Z_1 A Z_1'), the three GSVD
+ * diagonalisations and their Design_U), computed on the GPU with cuSOLVER/cuBLAS (loaded on first use).  Same list
+ * contract as the reference (inv(aP + bD'D) = U diag(1/(a s1 + b s2)) U'), obtained through symmetric
+ * eigen-decompositions instead of GSVD_2_c's svd(A inv(B)) (cpp:27-40); U is not unique, the contract is.
+ * Host pointers; Z_1 NULL = identity (r == n); X n x b; Z_2 n x r2 (r2 = 0: none); NULL outputs are skipped.
+ * Sizes: Ainv r x r; U1 n x n, s n; U2 br x br, s1_2, s2_2 br, Design_U n x br; U3 r x r, s1_3, s2_3 r;
+ * U4 r2 x r2, s1_4, s2_4 r2, Design_U4 n x r2.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bsfg_init_out {
+    double* Ainv;
+    double* U1; double* s;
+    double* U2; double* s1_2; double* s2_2; double* Design_U;
+    double* U3; double* s1_3; double* s2_3;
+    double* U4; double* s1_4; double* s2_4; double* Design_U4;
+} bsfg_init_out;
+int bsfg_init_lists(int n, int r, int b, int r2, const double* Z_1, const double* A, const double* X,
+                    const double* Z_2, double b_X_prec, bsfg_init_out* out);
+
 /* multi-GPU: rank 0 calls bsfg_nccl_unique_id, broadcasts the 128 bytes out of band (the Python host
  * uses torch.distributed), every rank calls bsfg_comm_init before bsfg_sweep.                    */
 int bsfg_nccl_unique_id(char id_out[128]);

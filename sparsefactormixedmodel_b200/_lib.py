@@ -74,6 +74,11 @@ class bsfg_posterior(C.Structure):
                [("sp_num", c_int_p), ("k", c_int_p)]
 
 
+class bsfg_init_out(C.Structure):
+    _fields_ = [(nm, c_double_p) for nm in
+                ("Ainv", "U1", "s", "U2", "s1_2", "s2_2", "Design_U", "U3", "s1_3", "s2_3", "U4", "s1_4", "s2_4", "Design_U4")]
+
+
 class bsfg_aux(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate", "Y_imputed")]
@@ -88,7 +93,7 @@ EXPORTS = [
     "bsfg_dgemm_tn_host", "bsfg_set_gram_default", "bsfg_get_gram_stats",
     "bsfg_create", "bsfg_destroy", "bsfg_set_priors", "bsfg_upload_constants", "bsfg_set_state",
     "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda",
-    "bsfg_posterior_begin", "bsfg_sweep_collect", "bsfg_posterior_count", "bsfg_get_posterior", "bsfg_get_mode",
+    "bsfg_init_lists", "bsfg_posterior_begin", "bsfg_sweep_collect", "bsfg_posterior_count", "bsfg_get_posterior", "bsfg_get_mode",
     "bsfg_get_timing", "bsfg_nccl_unique_id", "bsfg_comm_init", "bsfg_launch_count",
 ]
 

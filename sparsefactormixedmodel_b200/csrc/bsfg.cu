@@ -30,3 +30,4 @@ extern "C" int bsfg_device_count(void) {
 #include "gemm_host.inl"
 #include "stateless.inl"
 #include "sweep.inl"
+#include "init_device.inl"

@@ -39,6 +39,38 @@ def set_gram_default(gram="expsum", terms=0, step=0.0):
     check(_lib.load().bsfg_set_gram_default(_GRAM_MODES[gram], int(terms), C.c_double(step)))
 
 
+def init_lists(Z_1, A, X, Z_2=None, b_X_prec=1e-10):
+    """The precomputed members of `run_variables` (fast_BSFG_sampler_init.R:263-325) on the GPU: returns a dict with
+    Ainv, invert_aI_bZAZ, invert_aPXA_bDesignDesignT, invert_aZZt_Ainv (and invert_aPXA_bDesignDesignT_rand2 / A_2_inv when
+    Z_2 has columns) that can be passed as `run_variables` to BSFGSweep."""
+    lib = _lib.load()
+    A = as_f(A); X = as_f(X)
+    if Z_1 is None:                          # identity incidence matrix (one record per individual): r == n
+        n = r = A.shape[0]
+        ident = True
+    else:
+        Z_1 = np.asarray(Z_1, dtype=np.float64)
+        n, r = Z_1.shape
+        ident = _is_identity(Z_1)
+    b = X.shape[1]
+    Z_2 = np.zeros((n, 0)) if Z_2 is None else np.asarray(Z_2, dtype=np.float64)
+    r2 = Z_2.shape[1]
+    br = b + r
+    f = lambda *shape: np.zeros(shape, order="F")
+    o = dict(Ainv=f(r, r), U1=f(n, n), s=f(n), U2=f(br, br), s1_2=f(br), s2_2=f(br), Design_U=f(n, br), U3=f(r, r), s1_3=f(r),
+             s2_3=f(r), U4=f(r2, r2), s1_4=f(r2), s2_4=f(r2), Design_U4=f(n, r2))
+    out = _lib.bsfg_init_out(*[ptr(o[nm]) if o[nm].size else None for nm in
+                               ("Ainv", "U1", "s", "U2", "s1_2", "s2_2", "Design_U", "U3", "s1_3", "s2_3", "U4", "s1_4", "s2_4",
+                                "Design_U4")])
+    Z1f = None if ident else as_f(Z_1); Z2f = as_f(Z_2) if r2 > 0 else None
+    check(lib.bsfg_init_lists(n, r, b, r2, ptr(Z1f), ptr(A), ptr(X) if b > 0 else None, ptr(Z2f), C.c_double(b_X_prec), C.byref(out)))
+    rv = dict(n=n, r=r, b=b, r2=r2, Ainv=o["Ainv"], invert_aI_bZAZ=dict(U=o["U1"], s=o["s"]),
+              invert_aPXA_bDesignDesignT=dict(U=o["U2"], s1=o["s1_2"], s2=o["s2_2"], Design_U=o["Design_U"]),
+              invert_aZZt_Ainv=dict(U=o["U3"], s1=o["s1_3"], s2=o["s2_3"]), A_2_inv=np.eye(r2),
+              invert_aPXA_bDesignDesignT_rand2=(dict(U=o["U4"], s1=o["s1_4"], s2=o["s2_4"], Design_U=o["Design_U4"]) if r2 > 0 else {}))
+    return rv
+
+
 def shard_bounds(p, rank, world):
     """Contiguous, balanced split of the p trait columns: rank g owns [lo, hi)."""
     base, rem = divmod(p, world)
