@@ -6,6 +6,7 @@
 #include "chol_blocked.cuh"
 #include <algorithm>
 #include <map>
+#include <cmath>
 #include <functional>
 
 namespace bsfg {

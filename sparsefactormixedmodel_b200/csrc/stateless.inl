@@ -155,7 +155,20 @@ struct GramOpts {
     int terms = 256;             // R
     double step = 0.28;          // h: relative quadrature error ~1.2e-14
     double s_min = 0.0, s_max = 0.0;
+    // stateful sweeps created with gram_terms == 0: R is re-chosen at the start of every bsfg_sweep call from the range
+    // of c seen at the end of the previous one (widened 4x on both sides), between 64 and terms_max; the device guard
+    // still falls back to the exact GEMM if an iteration needs more
+    bool auto_terms = false;
+    int terms_max = 256;
 };
+// nodes needed to cover [s_min + c_min, s_max + c_max] with step h (same formulas as expsum_plan_kernel)
+static int expsum_terms_needed(double s_min, double s_max, double c_min, double c_max, double h) {
+    const double eps = 1e-16;
+    const double x_lo = s_min + c_min, x_hi = s_max + c_max;
+    if (!(x_lo > 0.0) || !std::isfinite(x_hi)) return 1 << 30;
+    const double t0 = std::log(eps / x_hi), need = std::log(-std::log(eps) / x_lo);
+    return (int)std::ceil((need - t0) / h) + 1;
+}
 static GramOpts g_gram_default;
 static GramOpts resolve_gram(int mode, int terms, double step) {
     GramOpts o = g_gram_default;

@@ -599,12 +599,14 @@ extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
         fail(BSFG_ESHAPE, "bsfg_create: inconsistent sizes");
     if (cfg->z1_is_identity && cfg->r != cfg->n) fail(BSFG_ESHAPE, "z1_is_identity requires r == n");
     kt_for(cfg->k_max);
-    GramOpts gram = resolve_gram(cfg->gram_mode, cfg->gram_terms, cfg->gram_step);
+    GramOpts gram = resolve_gram(cfg->gram_mode, cfg->gram_terms < 0 ? 0 : cfg->gram_terms, cfg->gram_step);
     bsfg_ctx* c = new bsfg_ctx();
     try {
         c->dev.init();
         c->cfg = *cfg;
         c->gram = gram;
+        c->gram.auto_terms = (cfg->gram_terms < 0 && gram.mode == GRAM_EXPSUM);   // opt-in: see bsfg_config
+        c->gram.terms_max = gram.terms;
         c->n = cfg->n; c->pl = cfg->p_local; c->p_total = cfg->p_total; c->p_off = cfg->p_offset;
         c->k = cfg->k; c->kmax = cfg->k_max; c->r = cfg->r; c->b = cfg->b; c->br = cfg->b + cfg->r; c->H = cfg->h2_divisions;
         c->z1_identity = cfg->z1_is_identity != 0;
@@ -951,6 +953,18 @@ extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
     if (n_iter < 0) fail(BSFG_EARG, "n_iter < 0");
     Device& d = c->dev;
     c->aux_on = false;
+    if (c->gram.auto_terms && c->lsc.plan) {
+        // re-choose the number of exponential-sum nodes from the last plan (identical on every rank: the c range is
+        // max-allreduced before the plan is made), with a 4x margin on both ends of the range
+        ExpSumPlan pl;
+        BSFG_CUDA(cudaMemcpyAsync(&pl, c->lsc.plan, sizeof pl, cudaMemcpyDeviceToHost, d.st));
+        d.sync();
+        if (pl.R > 0 && pl.c_min > 0.0 && std::isfinite(pl.c_max)) {
+            int need = expsum_terms_needed(c->gram.s_min, c->gram.s_max, pl.c_min / 4.0, pl.c_max * 4.0, c->gram.step);
+            need = (int)round_up(std::max(need, 64), 16);
+            c->gram.terms = std::min(need, c->gram.terms_max);
+        }
+    }
     const long long launches_before = g_launch_counter;
     BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
     for (int it = 0; it < n_iter; it++) {

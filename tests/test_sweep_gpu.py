@@ -270,6 +270,34 @@ def test_device_posterior_matches_host_bookkeeping():
         a.close(); bsw.close()
 
 
+def test_sweep_adaptive_expsum_terms():
+    """gram_terms = -1: the node count adapts between bsfg_sweep calls; parity with the oracle is unchanged."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 60, 45, 6
+    st = _build(n, p, k, "stable")
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, gram="expsum", gram_terms=-1)
+    try:
+        sw.set_state(cs)
+        sw.sweep(2)
+        assert sw.gram_stats()["terms"] == 256                   # first call: no range known yet
+        sw.sweep(1)
+        t = sw.gram_stats()["terms"]
+        assert 64 <= t < 256 and t % 16 == 0, t
+        rng = np.random.default_rng(3)
+        ora = sw.get_state()
+        ora["nrun"] = 3
+        v = I.draw_variates(rng, n, p, k, n, 1 + n, pri)
+        sw.set_state(ora)
+        want, _ = O.gibbs_iteration(d, rv, pri, rp, ora, 4, v)
+        sw.sweep_injected(v)
+        assert sw.gram_stats()["terms"] == t and sw.gram_stats()["fallbacks"] == 0
+        assert rowwise_relerr(sw.get_state()["Lambda"], want["Lambda"]) < TOL
+    finally:
+        sw.close()
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
