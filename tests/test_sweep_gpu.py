@@ -298,6 +298,74 @@ def test_sweep_adaptive_expsum_terms():
         sw.close()
 
 
+@pytest.mark.parametrize("n,p,k,b", [(10, 1, 2, 1), (15, 3, 2, 0), (5, 7, 3, 1), (20, 2, 9, 2)])
+def test_sweep_edge_sizes(n, p, k, b):
+    """Smallest shapes the reference's R code accepts: a single trait, k = 2 (where R's `2:(k-1)` loop of sample_delta
+    counts DOWN, BSFG_functions.R:296), no fixed effects (b = 0), more factors than traits, n not a multiple of anything."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    setup = I.make_synthetic(n, max(p, 2), 2, pedigree="halfsib", seed=n + p, b=max(b, 1))
+    setup["Y"] = setup["Y"][:, :p]
+    if b == 0:
+        setup["X"] = np.zeros((n, 0))
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=2, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=k + 2)
+    try:
+        rng = np.random.default_rng(1)
+        ora = cs
+        for it in (1, 2):
+            v = I.draw_variates(rng, n, p, k, n, b + n, pri)
+            sw.set_state(ora)
+            ora_next, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            assert rowwise_relerr(dev["Lambda"], ora_next["Lambda"]) < TOL
+            assert rowwise_relerr(dev["F"], ora_next["F"]) < TOL
+            assert rowwise_relerr(dev["F_a"].T, ora_next["F_a"].T) < TOL
+            assert np.array_equal(dev["F_h2"], np.asarray(ora_next["F_h2"]).ravel())
+            if b > 0:
+                assert relerr(dev["B"], ora_next["B"].reshape(dev["B"].shape)) < TOL
+            assert rowwise_relerr(dev["E_a"].T, ora_next["E_a"].T) < TOL
+            for f in ("Lambda_prec", "resid_Y_prec", "E_a_prec", "delta", "tauh"):
+                assert relerr(dev[f], ora_next[f]) < TOL, f
+            nd = len(aux["delta_rate"])
+            assert nd == (3 if k == 2 else k - 1)                      # k = 2: delta_1, then h = 2, 1 -> delta_1 is drawn twice
+            assert relerr(sw.aux()["delta_rate"][:nd], aux["delta_rate"]) < TOL
+            ora = ora_next
+        sw.sweep(3)
+        assert np.all(np.isfinite(sw.get_state()["Lambda"]))
+    finally:
+        sw.close()
+
+
+def test_sweep_rejects_inconsistent_calls():
+    """Errors are loud (negative status -> BSFGError), like Armadillo's exceptions through Rcpp: wrong call order, k out of
+    range, k_max beyond the shared-memory limit of the per-trait solver."""
+    from oracle import init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep, BSFGError, _lib
+    st = _build(20, 8, 3, "stable", seed=3)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    sw = BSFGSweep(d, rv, pri, rp, k_init=3, k_max=4)
+    try:
+        with pytest.raises(BSFGError) as ei:
+            sw.sweep(1)                                           # no state yet
+        assert ei.value.code == _lib.BSFG_ESTATE
+        big = dict(cs)
+        for nm in ("F", "F_a", "Lambda", "Lambda_prec", "Plam"):
+            big[nm] = np.column_stack([cs[nm]] * 2)               # 6 columns > k_max = 4
+        big["delta"] = np.tile(cs["delta"], 2); big["tauh"] = np.tile(cs["tauh"], 2); big["F_h2"] = np.tile(cs["F_h2"], 2)
+        with pytest.raises(BSFGError) as ei:
+            sw.set_state(big)
+        assert ei.value.code == _lib.BSFG_ESHAPE
+    finally:
+        sw.close()
+    with pytest.raises(BSFGError) as ei:
+        BSFGSweep(d, rv, pri, rp, k_init=3, k_max=400)
+    assert ei.value.code == _lib.BSFG_ESHAPE
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
