@@ -42,6 +42,8 @@ struct GemmArgs {
     int tiles_m, tiles_n;
     int group_n;           // rasterisation: tiles are walked m-fastest inside groups of `group_n` n-tiles
     const int* run_if;     // optional device flag: the whole launch is a no-op when *run_if == 0
+    int trans_out;         // 1: the product is stored transposed, element (m, n) at C[m * ldc + n] (and Cin likewise);
+                           // lets an N = k product run as the M = k product of the swapped operands (short row tile)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -101,12 +103,13 @@ struct GemmSmem {
 };
 
 // ---- the kernel -----------------------------------------------------------------------------
-// WM = warps along M (the other 8/WM along N).  WM = 2: 64 x 32 warp tiles, the only layout instantiated (gemm_host.inl
-// records why the all-rows / all-columns layouts for M = k or N = k products are not used).
+// WM = warps along M (the other 8/WM along N).  WM = 2: (BM/2) x 32 warp tiles, the only layout instantiated (gemm_host.inl
+// records why the all-rows / all-columns layouts for M = k or N = k products are not used).  BM < 128 serves products
+// whose M is a single short row tile (M = k factors): BM = 112 for k = 100 multiplies 12% of zero fill instead of 28%.
 template <int BM, int BN, int STAGES, int WM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
-    static_assert(BM == 128 && BN == 128, "warp layout below is written for 128x128 CTA tiles");
+    static_assert(BN == 128 && BM % 16 == 0 && BM >= 16 && BM <= 128, "128-column CTA tiles of 16..128 rows");
     static_assert(WM == 1 || WM == 2 || WM == 8, "supported warp layouts");
     constexpr int WN = GEMM_CONSUMERS / WM;
     constexpr int FM = (BM / 8) / WM;      // 8-row fragments per warp
@@ -241,7 +244,8 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c = 0; c < 2; c++) {
                     const int m = m0 + wm0 + 8 * i + gq;
                     const int n = n0 + wn0 + 8 * j + 2 * q + c;
-                    cin[i][c] = (m < g.M && n < g.N) ? g.Cin[(size_t)n * g.ldcin + m] : 0.0;
+                    cin[i][c] = (m < g.M && n < g.N)
+                                    ? g.Cin[g.trans_out ? (size_t)m * g.ldcin + n : (size_t)n * g.ldcin + m] : 0.0;
                 }
             }
         }
@@ -254,7 +258,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (m < g.M && n < g.N) {
                     double v = g.alpha * acc[i][j][c];
                     if (g.Cin) v += g.beta * cin[i][c];
-                    g.C[(size_t)n * g.ldc + m] = v;
+                    g.C[g.trans_out ? (size_t)m * g.ldc + n : (size_t)n * g.ldc + m] = v;
                 }
             }
         }
@@ -271,8 +275,8 @@ __global__ void splitk_reduce_kernel(GemmArgs g) {
         double acc = 0.0;
         for (int s = 0; s < g.splits; s++) acc += g.ws[(size_t)s * total + idx];   // fixed order
         double v = g.alpha * acc;
-        if (g.Cin) v += g.beta * g.Cin[(size_t)n * g.ldcin + m];
-        g.C[(size_t)n * g.ldc + m] = v;
+        if (g.Cin) v += g.beta * g.Cin[g.trans_out ? (size_t)m * g.ldcin + n : (size_t)n * g.ldcin + m];
+        g.C[g.trans_out ? (size_t)m * g.ldc + n : (size_t)n * g.ldc + m] = v;
     }
 }
 

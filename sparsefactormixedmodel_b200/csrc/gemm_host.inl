@@ -34,22 +34,31 @@ static void make_operand_map(CUtensorMap* tm, const double* base, long K, long r
 }
 
 constexpr int GEMM_STAGES = 6;
-using GemmCfg = GemmSmem<128, 128, GEMM_STAGES>;
 
 static long long g_launch_counter = 0;   // kernels launched by this library (bench.py's gpu_launches)
 
-void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
-              const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
-              double* ws, size_t ws_doubles, const int* run_if) {
-    if (M <= 0 || N <= 0) return;
-    if (K <= 0) fail(BSFG_ESHAPE, "dgemm_tn: K must be positive");
+template <int BM>
+static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, dim3 grid) {
+    using Cfg = GemmSmem<BM, 128, GEMM_STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<128, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg::TOTAL));
+        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
         attr_set = true;
     }
+    // WM = 2 ((BM/2) x 32 warp tiles) for every shape: the all-rows / all-columns layouts (WM = 1 / 8) that skip the empty
+    // fragments of M = k or N = k products evenly were measured SLOWER on B200 (sweep 13.3 -> 14.0 ms at C4: 18 instead
+    // of 12 fragment loads per 32 DMMAs and a predicated DMMA sequence), so they are not instantiated.
+    dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
+}
+
+static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
+                          const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
+                          double* ws, size_t ws_doubles, const int* run_if, int trans_out) {
+    // row-tile height: the smallest instantiated BM that holds a single short row tile, else 128
+    int BM = 128;
+    if (M <= 112) BM = M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 96 ? 96 : 112));
     CUtensorMap tmA, tmB;
-    make_operand_map(&tmA, At, K, M, lda, 128);
+    make_operand_map(&tmA, At, K, M, lda, BM);
     make_operand_map(&tmB, Bm, K, N, ldb, 128);
     GemmArgs g;
     g.M = M; g.N = N; g.K = K;
@@ -57,20 +66,21 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     g.Cin = (beta != 0.0) ? Cin : nullptr; g.ldcin = ldcin;
     g.alpha = alpha; g.beta = beta;
     g.run_if = run_if;
-    g.tiles_m = ceil_div(M, 128);
+    g.trans_out = trans_out;
+    g.tiles_m = ceil_div(M, BM);
     g.tiles_n = ceil_div(N, 128);
     g.group_n = 8;
     const int tiles = g.tiles_m * g.tiles_n;
     const int ktiles = ceil_div(K, GEMM_BK);
     // split-K, chosen by a small cost model (microseconds): waves of one CTA per SM, 2.1 us per 128x128x16 k-tile at
-    // the DMMA rate of one SM, ~8 us of pipeline fill + epilogue per CTA, and for s > 1 the extra pass over the
-    // s x M x N partials plus the reduce launch.  E.g. M=k=100, N=p=20000, K=5000 (157 tiles = 2 waves at 53%):
-    // s=7 -> 870 us instead of 1330; Lambda'Lmsg (1 tile, K=20000): s=148.  Partials are summed in a fixed order by
+    // the DMMA rate of one SM (scaled by BM/128), ~8 us of pipeline fill + epilogue per CTA, and for s > 1 the extra pass
+    // over the s x M x N partials plus the reduce launch.  E.g. M=k=100, N=p=20000, K=5000 (157 tiles = 2 waves at 53%):
+    // s=5 -> ~750 us instead of 1330; Lambda'Lmsg (1 tile, K=20000): s=148.  Partials are summed in a fixed order by
     // splitk_reduce_kernel, so results stay bit-reproducible.
     int splits = 1;
     if (ws) {
         const double per = (double)M * (double)N;
-        const double kt_us = 2.1;
+        const double kt_us = 2.1 * BM / 128.0;
         auto cost = [&](int s) {
             const long ctas = (long)tiles * s;
             const double waves = (double)((ctas + sm_count - 1) / sm_count);
@@ -90,10 +100,13 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
     g.splits = splits;
     g.ws = ws;
     dim3 grid(tiles, splits);
-    // WM = 2 (64 x 32 warp tiles) for every shape: the all-rows / all-columns layouts (WM = 1 / 8) that skip the empty
-    // fragments of M = k or N = k products evenly were measured SLOWER on B200 (sweep 13.3 -> 14.0 ms at C4: 18 instead
-    // of 12 fragment loads per 32 DMMAs and a predicated DMMA sequence), so they are not instantiated.
-    dgemm_tn_kernel<128, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, GemmCfg::TOTAL, st>>>(tmA, tmB, g);
+    switch (BM) {
+        case 32: launch_gemm<32>(st, tmA, tmB, g, grid); break;
+        case 64: launch_gemm<64>(st, tmA, tmB, g, grid); break;
+        case 96: launch_gemm<96>(st, tmA, tmB, g, grid); break;
+        case 112: launch_gemm<112>(st, tmA, tmB, g, grid); break;
+        default: launch_gemm<128>(st, tmA, tmB, g, grid); break;
+    }
     BSFG_CHECK_LAUNCH();
     g_launch_counter++;
     if (splits > 1) {
@@ -104,6 +117,19 @@ void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, 
         BSFG_CHECK_LAUNCH();
         g_launch_counter++;
     }
+}
+
+void dgemm_tn(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
+              const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
+              double* ws, size_t ws_doubles, const int* run_if) {
+    if (M <= 0 || N <= 0) return;
+    if (K <= 0) fail(BSFG_ESHAPE, "dgemm_tn: K must be positive");
+    // C = At'Bm with a short N (N = k factors) and a long M: run the transposed product Bm'At, whose short dimension is
+    // the row tile, and store it transposed
+    if (N <= 112 && M > 128)
+        dgemm_tn_impl(st, sm_count, N, M, K, alpha, Bm, ldb, At, lda, beta, Cin, ldcin, C, ldc, ws, ws_doubles, run_if, 1);
+    else
+        dgemm_tn_impl(st, sm_count, M, N, K, alpha, At, lda, Bm, ldb, beta, Cin, ldcin, C, ldc, ws, ws_doubles, run_if, 0);
 }
 
 }  // namespace bsfg
