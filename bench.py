@@ -302,7 +302,7 @@ def run_ours(args):
     # C5 (BASELINE.json configs[4]) runs with update_k live: start at iteration 200 (the i > 200 gate of
     # BSFG_functions.R:331 is open from the first timed iteration) and leave room for added factors
     start_iter = args.start_iter if args.start_iter >= 0 else (200 if args.workload == "C5" else 0)
-    k_max = k if start_iter + args.warmup + args.steps + 8 <= 200 else min(k + 16, 232)
+    k_max = k if start_iter + args.warmup + args.steps + 8 <= 200 else min(k + 16, 216)
     cs = dict(cs); cs["nrun"] = start_iter
     live_k = start_iter + args.warmup + args.steps > 200
     sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k_max, seed=20131, rank=rank, world=world, nccl_id=nccl_id,

@@ -15,12 +15,17 @@
 //   phase 1 (all warps, tensor pipe): tile(I,J) -= sum_{m<J} L(I,m) L(J,m)'  for I = J..NB-1.  A warp owns up
 //           to 4 tiles (I = J + warp + NW t) and keeps their 8x8 accumulators in the DMMA C fragment (2 doubles
 //           per lane per tile); both operands are K-contiguous tile rows, so A and B fragments load identically.
-//   phase 2 (one thread per matrix row): every thread factors the updated 8x8 diagonal tile redundantly in
-//           registers (36 values; no shuffles, no extra barrier) and applies the 8-step forward substitution to
-//           its own row of the panel below.
-// Then forward solve, + z, backward solve with one thread per row, 8-wide in-warp substitution on the diagonal
-// tile and an 8-FMA panel update per block.  3 barriers per block column in the factorisation, 1 per block in
-// each solve.  The per-element map packed-index -> tile offset is a uint16 table built once per k on the host.
+//           The updated diagonal tile is also written to a scratch tile, so that
+//   phase 2 (one thread per matrix row) can read it while its owners overwrite the real one: every thread factors
+//           the 8x8 diagonal tile redundantly in registers (36 values; no shuffles, no extra barrier) and applies the
+//           8-step forward substitution to its own row of the panel below; the 8 owners also store the INVERSE of the
+//           factored diagonal block (used by the backward solve).
+// 2 barriers per block column.  The right-hand side m rides along as an extra matrix row k (with a huge diagonal), so
+// the forward solve v = L^-1 m costs nothing: v' is row k of the factor.  The backward solve L'x = v + z runs on ONE
+// warp without block barriers: x_J = inv(L_JJ)' w_J is an 8x8 mat-vec (no 8-step dependency chain), followed by an
+// 8-FMA update of the earlier rows.  (ncu on the first version: ~40% of the stall samples sat on the barriers of the
+// two per-row solves, where three of four warps waited for the in-warp substitution of the fourth.)
+// The per-element map packed-index -> tile offset is a uint16 table built once per k on the host.
 #pragma once
 #include "kernels.cuh"
 
@@ -35,10 +40,11 @@ __device__ __forceinline__ void cb_dmma(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// shared-memory doubles needed for a k x k system
-inline size_t cb_smem_bytes(int k) {
-    const int NB = (k + 7) / 8;
-    return sizeof(double) * ((size_t)NB * (NB + 1) / 2 * 64 + 2 * (size_t)NB * 8) + 16;
+// shared-memory bytes needed for a k x k system (+1 row when a right-hand side rides along)
+inline size_t cb_smem_bytes(int k, bool with_rhs) {
+    const int NB = (k + (with_rhs ? 1 : 0) + 7) / 8;
+    // tiles + scratch diagonal tile + inverted diagonal blocks + solve vector + flag
+    return sizeof(double) * ((size_t)NB * (NB + 1) / 2 * 64 + 64 + (size_t)NB * 64 + (size_t)NB * 8) + 16;
 }
 
 template <int NW>
@@ -49,13 +55,16 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
                     double* __restrict__ Lout, int* __restrict__ fail_flag) {
     extern __shared__ __align__(16) double sm[];
     constexpr int T_ = NW * 32;
-    const int NB = (k + 7) >> 3;
+    const bool aug = rhs != nullptr;               // right-hand side stored as matrix row k
+    const int kk = k + (aug ? 1 : 0);
+    const int NB = (kk + 7) >> 3;
     const int ntile = NB * (NB + 1) / 2;
     const int npairs = k * (k + 1) / 2;
     double* T = sm;                       // ntile * 64
-    double* xv = sm + ntile * 64;         // 8 NB : block-solution exchange
-    double* invd = xv + 8 * NB;           // 8 NB : 1 / L[i][i]
-    int* s_bad = (int*)(invd + 8 * NB);
+    double* Dtmp = T + ntile * 64;        // 64 : copy of the diagonal tile being factored
+    double* Dinv = Dtmp + 64;             // NB * 64 : inverse of each factored diagonal block (row-major r*8+c, c <= r)
+    double* xv = Dinv + NB * 64;          // 8 NB : backward-solve vector
+    int* s_bad = (int*)(xv + 8 * NB);
     const int sys = blockIdx.x;
     if (sys >= nsys) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -71,13 +80,20 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
         const double* q = Qp + (long)sys * ldq;
 #pragma unroll 8
         for (int idx = tid; idx < npairs; idx += T_) T[tile_off[idx]] = q[idx];
-        for (int a = k + tid; a < 8 * NB; a += T_) T[cb_tile_id(a >> 3, a >> 3) * 64 + cb_swz(a & 7, a & 7)] = 1.0;
+        for (int a = kk + tid; a < 8 * NB; a += T_) T[cb_tile_id(a >> 3, a >> 3) * 64 + cb_swz(a & 7, a & 7)] = 1.0;
+        if (aug) {
+            const int Ik = k >> 3, rk = k & 7;
+            for (int j = tid; j < k; j += T_) T[cb_tile_id(Ik, j >> 3) * 64 + cb_swz(rk, j & 7)] = rhs[(long)sys * ldr + j];
+            if (tid == 0) T[cb_tile_id(Ik, Ik) * 64 + cb_swz(rk, rk)] = 1e300;   // keeps the pivot of row k positive; its factor is never used
+        }
     }
     __syncthreads();
     if (dadd) {
         for (int a = tid; a < k; a += T_)
             T[cb_tile_id(a >> 3, a >> 3) * 64 + cb_swz(a & 7, a & 7)] += dadd[(long)sys * dadd_sys_stride + (long)a * dadd_elem_stride];
     }
+    __syncthreads();
+    if (tid < 64) Dtmp[tid] = T[tid];     // tile (0,0): nothing to update before its factorisation
     __syncthreads();
 
     // ---- blocked left-looking Cholesky ------------------------------------------------------------
@@ -115,23 +131,19 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
                     double2 v = *c;
                     v.x -= acc[t][0]; v.y -= acc[t][1];
                     *c = v;
+                    if (t == 0 && warp == 0) *reinterpret_cast<double2*>(Dtmp + fc) = v;   // I == J: the diagonal tile
                 }
             }
             __syncthreads();
         }
         {
             const int row = 8 * J + tid;
-            const bool has_row = row < 8 * NB;
-            double L[8][8];
-            if (has_row) {
-                const double* D = T + cb_tile_id(J, J) * 64;
+            if (row < 8 * NB) {
+                double L[8][8];
 #pragma unroll
                 for (int r = 0; r < 8; r++)
 #pragma unroll
-                    for (int c = 0; c <= r; c++) L[r][c] = D[cb_swz(r, c)];
-            }
-            __syncthreads();      // every thread holds the diagonal tile before its owners overwrite it
-            if (has_row) {
+                    for (int c = 0; c <= r; c++) L[r][c] = Dtmp[cb_swz(r, c)];
                 double inv[8];
                 bool bad = false;
 #pragma unroll
@@ -151,12 +163,30 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
                 double* mine = T + cb_tile_id(I, J) * 64;
                 if (I == J) {
                     if (bad && r == 0) *s_bad = 1;
+                    // inverse of the factored block, X = L^-1 (lower), one column at a time (8 live values):
+                    // X[c][c] = 1/L[c][c], X[rr][c] = -(1/L[rr][rr]) sum_{m=c}^{rr-1} L[rr][m] X[m][c]; this thread keeps row r
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        double xc[8];
+                        xc[c] = inv[c];
+#pragma unroll
+                        for (int rr = c + 1; rr < 8; rr++) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int m = c; m < rr; m++) acc += L[rr][m] * xc[m];
+                            xc[rr] = -inv[rr] * acc;
+                        }
+                        double mine_x = 0.0;
+#pragma unroll
+                        for (int rr = c; rr < 8; rr++)
+                            if (rr == r) mine_x = xc[rr];
+                        Dinv[J * 64 + r * 8 + c] = mine_x;               // zero above the diagonal (c > r)
+                    }
 #pragma unroll
                     for (int rr = 0; rr < 8; rr++) {
                         if (rr == r) {
 #pragma unroll
                             for (int c = 0; c < 8; c++) mine[cb_swz(rr, c)] = (c <= rr) ? L[rr][c] : 0.0;
-                            invd[8 * J + rr] = inv[rr];
                         }
                     }
                 } else {
@@ -183,70 +213,40 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
     if (Lout) {
         for (int idx = tid; idx < npairs; idx += T_) Lout[(long)sys * npairs + idx] = T[tile_off[idx]];
     }
-    if (!out) return;
+    if (!out || !aug) return;
 
-    // ---- solves: one thread per row ------------------------------------------------------------------
-    const int I = tid >> 3, r = tid & 7;
-    const bool live = tid < 8 * NB;
-    double bval = (tid < k) ? rhs[(long)sys * ldr + tid] : 0.0;
-    // forward: L v = m
-    for (int J = 0; J < NB; J++) {
-        if (warp == (J >> 2)) {
-            const int base = (8 * J) & 31;
-            const bool mineb = live && I == J;
-            const double* D = T + cb_tile_id(J, J) * 64;
-            double Lr[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) Lr[c] = (mineb && c < r) ? D[cb_swz(r, c)] : 0.0;
-            const double idg = mineb ? invd[8 * J + r] : 0.0;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                if (mineb && r == c) bval *= idg;
-                const double xc = __shfl_sync(0xffffffffu, bval, base + c);
-                if (mineb && r > c) bval -= Lr[c] * xc;
-            }
-            if (mineb) xv[tid] = bval;
-        }
-        __syncthreads();
-        if (live && I > J) {
-            const double* Tt = T + cb_tile_id(I, J) * 64;
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < 8; c++) acc += Tt[cb_swz(r, c)] * xv[8 * J + c];
-            bval -= acc;
-        }
+    // ---- w = v + z with v' = row k of the factor (cpp:125, 128: mlam and ylam share one back-substitution) ---------
+    {
+        const int Ik = k >> 3, rk = k & 7;
+        for (int j = tid; j < 8 * NB; j += T_)
+            xv[j] = (j < k) ? T[cb_tile_id(Ik, j >> 3) * 64 + cb_swz(rk, j & 7)] + var_normal(zsrc, j, sys) : 0.0;
     }
-    // w = v + z   (cpp:128: ylam solves against Zcol; the two back-substitutions share one pass)
-    if (tid < k) bval += var_normal(zsrc, tid, sys);
     __syncthreads();
-    // backward: L' x = w
+    if (warp != 0) return;
+    // ---- backward solve L' x = w on one warp ------------------------------------------------------------------------
     for (int J = NB - 1; J >= 0; J--) {
-        if (warp == (J >> 2)) {
-            const int base = (8 * J) & 31;
-            const bool mineb = live && I == J;
-            const double* D = T + cb_tile_id(J, J) * 64;
-            double Lc[8];
+        double xr = 0.0;
+        if (lane < 8) {
+            // x_r = sum_{c >= r} inv(L_JJ)[c][r] w_c
+            const double* Xb = Dinv + J * 64;
 #pragma unroll
-            for (int c = 0; c < 8; c++) Lc[c] = (mineb && c > r) ? D[cb_swz(c, r)] : 0.0;   // column r of the diagonal tile
-            const double idg = mineb ? invd[8 * J + r] : 0.0;
-#pragma unroll
-            for (int c = 7; c >= 0; c--) {
-                if (mineb && r == c) bval *= idg;
-                const double xc = __shfl_sync(0xffffffffu, bval, base + c);
-                if (mineb && r < c) bval -= Lc[c] * xc;
-            }
-            if (mineb) xv[tid] = bval;
+            for (int c = 0; c < 8; c++) xr += Xb[c * 8 + lane] * xv[8 * J + c];     // entries with c < r are stored zeros
         }
-        __syncthreads();
-        if (live && I < J) {
-            const double* Tt = T + cb_tile_id(J, I) * 64;
+        __syncwarp();
+        if (lane < 8) xv[8 * J + lane] = xr;
+        __syncwarp();
+        // w_i -= sum_c L[8J + c][i] x_c for every earlier row i < 8J
+        for (int i = lane; i < 8 * J; i += 32) {
+            const double* Tt = T + cb_tile_id(J, i >> 3) * 64;
+            const int ri = i & 7;
             double acc = 0.0;
 #pragma unroll
-            for (int c = 0; c < 8; c++) acc += Tt[cb_swz(c, r)] * xv[8 * J + c];
-            bval -= acc;
+            for (int c = 0; c < 8; c++) acc += Tt[cb_swz(c, ri)] * xv[8 * J + c];
+            xv[i] -= acc;
         }
+        __syncwarp();
     }
-    if (tid < k) out[(long)sys * ldo + tid] = bval;
+    for (int i = lane; i < k; i += 32) out[(long)sys * ldo + i] = xv[i];
 }
 
 }  // namespace bsfg

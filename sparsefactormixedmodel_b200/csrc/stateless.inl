@@ -95,7 +95,7 @@ static VarSrc make_var(const DMat* injected, uint64_t seed, uint32_t site, uint3
 }
 
 // ---- reusable device-level pieces (also used by the sweep) -----------------------------------
-constexpr int BSFG_K_LIMIT = 232;   // 29 x 29 tiles of 8 x 8 doubles = 222.7 KB of the 227 KB shared memory per CTA
+constexpr int BSFG_K_LIMIT = 216;   // (k + 1 rows) -> 28 block rows: 406 tiles + 28 inverted diagonal blocks of 8 x 8 doubles fit 227 KB
 static int kt_for(int k) {
     if (k > BSFG_K_LIMIT) fail(BSFG_ESHAPE, "k = %d exceeds the supported maximum of %d factors", k, BSFG_K_LIMIT);
     if (k <= 32) return 1;
@@ -110,9 +110,10 @@ static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int 
                               const VarSrc& z, double* out, long ldo, double* Lout) {
     if (nsys <= 0) return;
     kt_for(k);
-    const size_t smem = cb_smem_bytes(k);
+    const size_t smem = cb_smem_bytes(k, rhs != nullptr);
+    if (smem > 227 * 1024) fail(BSFG_ESHAPE, "k = %d: the tiled Cholesky needs %zu B of shared memory", k, smem);
     const uint16_t* map = d.chol_map(k);
-    if (k <= 128) {
+    if (k + (rhs ? 1 : 0) <= 128) {      // one thread per matrix row (incl. the right-hand-side row): 4 warps cover 128 rows
         BSFG_CUDA(cudaFuncSetAttribute(chol_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chol_blocked_kernel<4><<<nsys, 128, smem, d.st>>>(Qp, ldq, k, nsys, map, dadd, dadd_sys_stride, dadd_elem_stride,
                                                           rhs, ldr, z, out, ldo, Lout, d.d_flag);

@@ -72,9 +72,9 @@ def test_sample_Lambda_c(pkg, small_problem, gram):
 
 
 @pytest.mark.parametrize("n,p,k", [(33, 17, 3), (100, 257, 20), (250, 100, 40), (64, 50, 70), (96, 24, 128), (80, 21, 136),
-                                   (120, 19, 200), (72, 9, 232)])
+                                   (120, 19, 200), (72, 9, 216)])
 def test_sample_Lambda_c_shapes(pkg, n, p, k, gram):
-    """ragged sizes incl. odd n (padded leading dimensions); k across the 4-warp (k <= 128) and 8-warp (k <= 232, the
+    """ragged sizes incl. odd n (padded leading dimensions); k across the 4-warp (k <= 128) and 8-warp (k <= 216, the
     shared-memory limit) instantiations of the blocked Cholesky, incl. k not a multiple of 8."""
     from oracle import bsfg_oracle as O
     rng = np.random.default_rng(n + p + k)
