@@ -92,9 +92,13 @@ __global__ void scale_kernel(const double* __restrict__ in, long ldi, long rows,
 // Khatri-Rao ("Gram feature") build: Gt[i, pair(a,b)] = UtF[i,a] * UtF[i,b], a >= b,
 // pair = a(a+1)/2 + b.  The weighted Gram Qlam_j = sum_i w_ij f_i f_i' (cpp:120-122) then is the
 // plain GEMM  Q = Gt' W.
+// Trait-sharded runs only need this rank's block of pairs [pair_lo, pair_hi) for the node product; the rest is built
+// only when the exact fallback will consume the whole of G (*need_all != 0).
 __global__ void gram_features_kernel(const double* __restrict__ UtF, long ldf, int n, int k,
-                                     double* __restrict__ Gt, long ldg) {
+                                     double* __restrict__ Gt, long ldg, int pair_lo, int pair_hi,
+                                     const int* __restrict__ need_all) {
     const int pair = blockIdx.y;
+    if ((pair < pair_lo || pair >= pair_hi) && !(need_all && *need_all != 0)) return;
     int a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);
     while ((a + 1) * (a + 2) / 2 <= pair) a++;
     while (a * (a + 1) / 2 > pair) a--;
@@ -602,15 +606,34 @@ __global__ void delta_colsum_kernel(const double* __restrict__ LP, long ldp, con
 // is what the lanes apply (relative rounding difference <= k ulp, far inside the 1e-9 contract); the tauh written
 // out at the end is the plain sequential cumprod of the final delta.  The draws stay sequential.
 // Loop order = R's 2:(k-1) (counts down when k == 2).  Shared memory: 3k doubles.
+// The Gamma shapes do not depend on the data (a_1 + pk/2, a_2 + p(k-h+1)/2), so all standard-Gamma variates of the
+// recursion are drawn up front by the whole block in parallel (shared memory gdraw[]); the sequential part then only
+// divides by the rates.  Shared memory: 4k + 2 doubles.
 __global__ void delta_recursion_kernel(double* __restrict__ delta_g, int k, const double* __restrict__ colsum_g,
                                        double n_genes, double d1s, double d1r, double d2s, double d2r,
                                        VarSrc gsrc, double* __restrict__ tauh_out, double* __restrict__ shapes,
                                        double* __restrict__ rates, int* __restrict__ ndraws) {
-    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    if (blockIdx.x != 0) return;
     extern __shared__ double dsm[];
     double* tauh = dsm;
     double* delta = dsm + k;
     double* colsum = dsm + 2 * k;
+    double* gdraw = dsm + 3 * k;                 // k + 2 entries, in draw order
+    {
+        const int hi0 = k - 1, step0 = (hi0 >= 2) ? 1 : -1;
+        const int n_loop = (step0 > 0) ? (hi0 - 1) : (2 - hi0 + 1);      // |2:(k-1)| in R's sense
+        for (int dr = threadIdx.x; dr < 1 + n_loop; dr += blockDim.x) {
+            double shape;
+            if (dr == 0) shape = d1s + 0.5 * n_genes * k;
+            else {
+                const int h = 2 + step0 * (dr - 1);                          // 1-based h of this draw
+                shape = d2s + 0.5 * n_genes * (k - h + 1);
+            }
+            gdraw[dr] = var_gamma(gsrc, dr, 0, shape);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     for (int h = lane; h < k; h += 32) { delta[h] = delta_g[h]; colsum[h] = colsum_g[h]; }
     __syncwarp();
@@ -628,7 +651,7 @@ __global__ void delta_recursion_kernel(double* __restrict__ delta_g, int k, cons
         const double ts = tail_sum(h0);
         const double old = delta[h0];
         const double rate = prior_rate + 0.5 * (1.0 / old) * ts;
-        const double dnew = var_gamma(gsrc, draw, 0, shape) / rate;          // same value on every lane
+        const double dnew = gdraw[draw] / rate;                              // same value on every lane
         const double ratio = dnew / old;
         __syncwarp();
         for (int l = h0 + lane; l < k; l += 32) tauh[l] *= ratio;

@@ -241,16 +241,25 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
     const bool expsum = go.mode == GRAM_EXPSUM;
     const int R = expsum ? go.terms : 0;
     sc.ensure(n, p, k, R);
-    {
-        dim3 grid(std::min(ceil_div(n, 256), 64), np);
-        gram_features_kernel<<<grid, 256, 0, d.st>>>(UtF.p, UtF.ld, n, k, sc.Gt.p, sc.Gt.ld);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-    }
     if (expsum) {
         expsum_range_kernel<<<1, 1024, 0, d.st>>>(ep, rp, p, sc.range);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         if (sc.world > 1 && sc.allreduce_max) sc.allreduce_max(sc.range, 3);   // one node grid for all ranks
         expsum_plan_kernel<<<1, 32, 0, d.st>>>(sc.range, go.s_min, go.s_max, go.step, R, 0, sc.plan, sc.need_exact, sc.fallbacks);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    {
+        // Gram features; a rank of a sharded expsum run builds only its own block of pairs unless the fallback needs all
+        int pair_lo = 0, pair_hi = np;
+        const bool shard_pairs = expsum && sc.world > 1 && sc.allgather;
+        if (shard_pairs) {
+            const long chunk = ceil_div(np, sc.world);
+            pair_lo = (int)std::min<long>(np, (long)sc.rank * chunk);
+            pair_hi = (int)std::min<long>(np, pair_lo + chunk);
+        }
+        dim3 grid(std::min(ceil_div(n, 256), 64), np);
+        gram_features_kernel<<<grid, 256, 0, d.st>>>(UtF.p, UtF.ld, n, k, sc.Gt.p, sc.Gt.ld, pair_lo, pair_hi,
+                                                     shard_pairs ? sc.need_exact : nullptr);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     {
@@ -633,7 +642,7 @@ extern "C" int bsfg_sample_delta_c(const double* delta, const double* tauh, int 
     delta_colsum_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, L2.p, L2.ld, p, k, 0, colsum.p);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     VarSrc gs = make_var(g ? &dG : nullptr, seed, SITE_G_DELTA, 0, 0, k);
-    delta_recursion_kernel<<<1, 32, 3 * sizeof(double) * k, d.st>>>(dd.p, k, colsum.p, (double)p, delta_1_shape, delta_1_rate,
+    delta_recursion_kernel<<<1, 128, (4 * k + 2) * sizeof(double), d.st>>>(dd.p, k, colsum.p, (double)p, delta_1_shape, delta_1_rate,
                                                                delta_2_shape, delta_2_rate, gs, nullptr, shapes.p, rates.p, d_nd);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     dd.download(delta_out, d.st);

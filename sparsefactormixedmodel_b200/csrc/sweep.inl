@@ -442,7 +442,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
                                               c->colsum_cnt.p + c->kmax);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     allreduce(c, c->colsum_cnt.p, (size_t)2 * c->kmax);
-    delta_recursion_kernel<<<1, 32, 3 * sizeof(double) * k, d.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
+    delta_recursion_kernel<<<1, 128, (4 * k + 2) * sizeof(double), d.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
                                                                c->pri.delta_1_shape, c->pri.delta_1_rate,
                                                                c->pri.delta_2_shape, c->pri.delta_2_rate, v.gD, c->tauh.p,
                                                                c->delta_shapes.p, c->delta_rates.p, c->d_ndraws);

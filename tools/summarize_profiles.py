@@ -105,9 +105,11 @@ def main():
         d = st[0]
         summ["dram_bytes_per_launch_expsum"] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
     ncu_summary(f"prof_{tag}_chol.ncu-rep", "ncu full: chol_blocked_kernel<4> (20000 systems of k = 100)",
-                lambda s: ["Latency / barrier bound as designed: 4 CTAs (16 warps) per SM limited by 48 KB shared memory and 128 registers;",
-                           "barrier stalls 4.3 per issued instruction; DRAM at 5% (reads the 808 MB of Q once).  Shared-memory bank conflicts",
-                           "come from the one-thread-per-row phases (8-double row stride), not from the DMMA fragment loads."])
+                lambda s: ["Version 2 of the kernel (right-hand side as an extra matrix row, scratch diagonal tile, single-warp backward solve).",
+                           "Latency / barrier bound: 4 CTAs (16 warps) per SM limited by 55 KB shared memory and 128 registers; DRAM at ~6%",
+                           "(reads the 808 MB of Q once).  Shared-memory bank conflicts come from the one-thread-per-row phases (8-double row",
+                           "stride), not from the DMMA fragment loads.  The first version spent ~40% of its stall samples on the barriers of the",
+                           "two per-row solves (profiles kept in git history: 2.13 ms, 4.3 barrier stalls per issue)."])
     ncu_summary(f"prof_{tag}_gemm.ncu-rep", "ncu full: skinny products (k x p_local over K = n, split-K 5; G'A node product)",
                 lambda s: ["These captures were taken with the fragment-skipping experiment compiled in (later reverted, see gemm_host.inl);",
                            "kept for the wave / occupancy numbers: 157 x 5 CTAs = 5.3 waves, 80 x 5 = 2.7 waves."])
