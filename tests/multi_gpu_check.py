@@ -95,6 +95,36 @@ def main():
             assert relerr(got[nm], ref[nm]) < 1e-10, (nm, relerr(got[nm], ref[nm]))
         assert np.array_equal(got["F_h2"], ref["F_h2"])
         print(f"multi_gpu_check ok world={world}", flush=True)
+    # ---- second scenario: second random effect (Z_2 / W) + missing phenotypes under trait sharding ------------------
+    n, p, k, r2 = 70, 53, 5, 6
+    rs = np.random.default_rng(101)
+    setup = I.make_synthetic(n, p, 3, pedigree="halfsib", seed=23)
+    Y = setup["Y"].copy(); Y[rs.uniform(size=Y.shape) < 0.15] = np.nan
+    setup["Y"] = Y
+    Z2 = np.zeros((n, r2)); Z2[np.arange(n), rs.integers(0, r2, n)] = 1.0
+    setup["Z_2"] = Z2
+    pri = I.default_priors(k_init=k)
+    st = I.sampler_init(setup, pri, rp, seed=9, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    nccl_id = bcast(BSFGSweep.nccl_unique_id() if rank == 0 else None)
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, seed=7, rank=rank, world=world, nccl_id=nccl_id)
+    lo, hi = sw.lo, sw.hi
+    sw.set_state(cs)
+    ora = cs
+    for it in range(1, 4):                       # free running: iterations 2, 3 impute from the device's own theta
+        v = I.draw_variates(rs, n, p, k, n, 1 + n, pri, r2=r2, missing=True)
+        ora, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+        sw.sweep_injected(v)
+        assert relerr(sw.aux()["Y_imputed"], aux["Y_imputed"][:, lo:hi]) < 1e-8
+    dev = sw.get_state()
+    assert rowwise_relerr(dev["Lambda"], ora["Lambda"][lo:hi]) < 1e-7
+    assert rowwise_relerr(dev["F"], ora["F"]) < 1e-7
+    assert rowwise_relerr(dev["W"].T, ora["W"][:, lo:hi].T) < 1e-7
+    assert relerr(dev["W_prec"], ora["W_prec"][lo:hi]) < 1e-7
+    assert relerr(dev["resid_Y_prec"], ora["resid_Y_prec"][lo:hi]) < 1e-7
+    sw.close()
+    if rank == 0:
+        print(f"multi_gpu_check ok (Z_2 + missing data) world={world}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
