@@ -1,0 +1,60 @@
+"""Injected-variate parity at the sizes BASELINE.json names as configs (C2, C3; C1 = the Sim_1 golden
+fixture in test_golden_gpu.py; C4/C5 are the bench workloads, covered here through size-independent properties)."""
+import numpy as np
+import pytest
+
+from conftest import relerr, rowwise_relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _parity(n, p, k, pedigree, seed, iters=1, gram="default"):
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    setup = I.make_synthetic(n, p, max(2, k // 2), pedigree=pedigree, seed=seed)
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=seed + 1, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=k + 8, gram=gram)
+    try:
+        rng = np.random.default_rng(seed + 2)
+        ora = cs
+        for it in range(1, iters + 1):
+            v = I.draw_variates(rng, n, p, k, n, 1 + n, pri)
+            sw.set_state(ora)
+            ora, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            assert rowwise_relerr(dev["Lambda"], ora["Lambda"]) < TOL
+            assert rowwise_relerr(dev["F"], ora["F"]) < TOL
+            assert rowwise_relerr(dev["F_a"].T, ora["F_a"].T) < TOL
+            assert np.array_equal(dev["F_h2"], np.asarray(ora["F_h2"]).ravel())
+            assert relerr(dev["B"], ora["B"].reshape(dev["B"].shape)) < TOL
+            assert rowwise_relerr(dev["E_a"].T, ora["E_a"].T) < TOL
+            for f in ("Lambda_prec", "resid_Y_prec", "E_a_prec", "delta", "tauh"):
+                assert relerr(dev[f], ora[f]) < TOL, f
+            a = sw.aux()
+            assert relerr(a["resid_Y_prec_rate"], aux["resid_Y_prec_rate"]) < TOL
+            assert relerr(a["E_a_prec_rate"], aux["E_a_prec_rate"]) < TOL
+        assert sw.gram_stats()["fallbacks"] == 0
+    finally:
+        sw.close()
+
+
+def test_C2_synthetic_n1000_p1000_k20():
+    """BASELINE.json configs[1]: 'synthetic n=1000 individuals, p=1000 traits, k=20 factors, 1 GPU, injected-variate
+    equivalence vs Rcpp' (half-sib A with 2 distinct eigenvalues, like Sim_1)."""
+    _parity(1000, 1000, 20, "halfsib", 201, iters=2)
+
+
+def test_C3_ayroles_shaped_n200_p10000_k50():
+    """BASELINE.json configs[2]: 'n=200 lines, p=10000 genes, k=50, random pedigree A, 1 GPU'."""
+    _parity(200, 10000, 50, "random", 301)
+
+
+def test_C4_shape_properties_k100():
+    """C4's factor count (k = 100, the 4-warp Cholesky with the right-hand-side row in the 13th block) at a size the
+    oracle finishes in seconds, both Gram evaluations."""
+    _parity(300, 400, 100, "random", 401, gram="expsum")
+    _parity(300, 400, 100, "random", 401, gram="exact")
