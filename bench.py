@@ -355,31 +355,23 @@ def run_ours(args):
     k_trace = [k, k_now]
     host = sw.alloc_state(k_now, with_E_a=False, empty=pinned_empty)  # pinned result buffers, reused every step
     sw.get_state(with_E_a=False, out=host)
-    # e2e starts from the state the timed sweep left (same k); trait-indexed members of set_state are given for all p
-    # traits and sliced per rank, so gather this rank's shard back into full-width pinned arrays
-    full = dict(cs)
-    if k_now != k or world > 1:
-        full = dict(cs)
+    # e2e starts from the state the timed sweep left: every rank keeps ITS shard of the trait-indexed members in pinned
+    # host memory (set_state(local=True)), exactly what a chain driver holding per-rank state would pass back
     cur = sw.get_state(with_E_a=False)
-    if k_now != k:
-        def widen(a, cols):
-            out = np.zeros((p, cols)); out[sw.lo:sw.hi] = a
-            return out
-        full.update(Lambda=widen(cur["Lambda"], k_now), Lambda_prec=widen(cur["Lambda_prec"], k_now), Plam=widen(cur["Plam"], k_now),
-                    F=cur["F"], F_a=cur["F_a"], F_h2=cur["F_h2"], delta=cur["delta"], tauh=cur["tauh"], nrun=cur["nrun"])
+    full = dict(cur)
     for nm in ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "B"):
         full[nm] = pinned(full[nm])
     e2e_steps = max(2, min(args.steps, 5))
     kk_ = k_now
     h2d = 8 * (3 * sw.pl * kk_ + 2 * n * kk_ + sw.b * sw.pl + 2 * sw.pl + 3 * kk_)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
     d2h = 8 * (3 * sw.pl * kk_ + n * kk_ + n * kk_ + kk_ + sw.b * sw.pl + 2 * sw.pl + 2 * kk_)
-    sw.set_state(full); sw.sweep(1); sw.get_state(with_E_a=False, out=host)         # warm the path
+    sw.set_state(full, local=True); sw.sweep(1); sw.get_state(with_E_a=False, out=host)         # warm the path
     barrier()
     t0 = time.perf_counter()
     e2e_parts = [0.0, 0.0, 0.0]
     for _ in range(e2e_steps):
         ta = time.perf_counter()
-        sw.set_state(full)
+        sw.set_state(full, local=True)
         tb = time.perf_counter()
         sw.sweep(1)
         tc = time.perf_counter()

@@ -162,12 +162,13 @@ class BSFGSweep:
         return buf.raw
 
     # -- state -----------------------------------------------------------------------------
-    def set_state(self, current_state):
+    def set_state(self, current_state, local=False):
         """Upload `current_state` (fast_BSFG_sampler_init.R:238-254 field names); trait-indexed members
-        are given for ALL traits and sliced to this rank's shard here."""
+        are given for ALL traits and sliced to this rank's shard here, or -- `local=True` -- already hold this
+        rank's shard (what get_state returns), which avoids a host copy per call."""
         cs = current_state
         k = int(np.asarray(cs["F"]).shape[1])
-        sl = slice(self.lo, self.hi)
+        sl = slice(None) if local else slice(self.lo, self.hi)
         arrs = {}
 
         def put(name, a):
@@ -181,7 +182,7 @@ class BSFGSweep:
         st.F = put("F", as_f(cs["F"]))
         st.F_a = put("F_a", as_f(cs["F_a"])) if cs.get("F_a") is not None else None
         st.F_h2 = put("F_h2", np.ascontiguousarray(np.asarray(cs["F_h2"], dtype=np.float64).ravel())) if cs.get("F_h2") is not None else None
-        st.B = put("B", as_f(np.asarray(cs["B"]).reshape(self.b, self.p_total)[:, sl])) if self.b > 0 else None
+        st.B = put("B", as_f(np.asarray(cs["B"]).reshape(self.b, -1)[:, sl])) if self.b > 0 else None
         st.E_a = put("E_a", as_f(np.asarray(cs["E_a"])[:, sl])) if cs.get("E_a") is not None else None
         st.resid_Y_prec = put("rp", np.ascontiguousarray(np.asarray(cs["resid_Y_prec"], dtype=np.float64).ravel()[sl]))
         st.E_a_prec = put("ep", np.ascontiguousarray(np.asarray(cs["E_a_prec"], dtype=np.float64).ravel()[sl]))
