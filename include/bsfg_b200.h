@@ -163,6 +163,7 @@ typedef struct bsfg_priors {           /* model_setup.R:49-63, fast_BSFG_sampler
     const double* h2_priors_factors;   /* h2_divisions entries */
     double b0, b1, epsilon, prop;      /* run_parameters used by update_k */
     double W_prec_shape, W_prec_rate;  /* second random effect (model_setup.R:53-54); used when r2 > 0 */
+    double px_shape, px_rate;          /* parameter-expanded sampler (model_setup_px.R:55-56); used by bsfg_sweep_px */
 } bsfg_priors;
 
 /* Constants of one chain (host pointers; Y and everything trait-indexed holds THIS RANK's columns).  NaN entries of
@@ -201,6 +202,9 @@ typedef struct bsfg_state {
     int k;       /* in: number of factor columns supplied; out: current k */
     int nrun;    /* iteration counter i (current_state$nrun) */
     double* W; double* W_prec;   /* r2 x p_local, p_local (required on set_state when r2 > 0) */
+    /* parameter-expanded sampler (fast_BSFG_sampler_px.R): px_factor k, F_px n x k.  Supplying both on set_state puts
+     * the context in px mode (F is then ignored: F = F_px / sqrt(px_factor)); get_state returns them when non-NULL. */
+    double* px_factor; double* F_px;
 } bsfg_state;
 
 /* One iteration's injected variates (NULL members fall back to device Philox).
@@ -220,6 +224,9 @@ typedef struct bsfg_variates {
     /* missing phenotypes (NaN in Y): z_Y n x p_local N(0,1); element (i,j) is entry i*p + j of the reference's
      * rnorm(p*n) stream, which it lays out byrow (fast_BSFG_sampler.R:182) */
     const double* z_Y;
+    /* parameter-expanded sampler: g_px k ~ Gamma(px_shape + n/2, 1) (fast_BSFG_sampler_px.R:263); k_g_px scalar
+     * ~ Gamma(px_shape, 1) for the add-a-factor arm (BSFG_functions_px.R:333) */
+    const double* g_px; const double* k_g_px;
 } bsfg_variates;
 
 /* Gamma (shape, rate) parameters of the last iteration's precision draws, for parity checks. */
@@ -231,6 +238,7 @@ typedef struct bsfg_aux {
     double* h2_log_ps;          /* k x H */
     double* W_prec_rate;        /* p_local (r2 > 0) */
     double* Y_imputed;          /* n x p_local: Y after the last iteration's imputation step (only with missing data) */
+    double* px_rate;            /* k: rate of the px_factor draw (px mode) */
 } bsfg_aux;
 
 int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out);
@@ -244,6 +252,12 @@ int bsfg_get_aux(bsfg_ctx* ctx, bsfg_aux* aux);
 int bsfg_sweep(bsfg_ctx* ctx, int n_iter);
 /* exactly one iteration with injected variates (the parity path). */
 int bsfg_sweep_injected(bsfg_ctx* ctx, const bsfg_variates* v);
+/* Parameter-expanded sampler: the loop body of fast_BSFG_sampler_px.R:196-311 (F Lambda' = F_px Lambda_px' with a
+ * redundant per-factor scale px_factor that is resampled every iteration; update_k of BSFG_functions_px.R:301-369).
+ * The state must have been set with px_factor and F_px.  bsfg_sweep_px: n_iter iterations with device Philox draws;
+ * bsfg_sweep_px_injected: one iteration with injected variates.                                                      */
+int bsfg_sweep_px(bsfg_ctx* ctx, int n_iter);
+int bsfg_sweep_px_injected(bsfg_ctx* ctx, const bsfg_variates* v);
 /* one iteration of the fixed-Lambda sampler (fast_BSFG_sampler_fixedlambda.R:159-236): Lambda (p_local x k, k = the
  * state's k) is a stored posterior draw; B/E_a, W, F_h2, F_a, F and the precisions are resampled, Lambda, Lambda_prec,
  * delta and k are not.  The (B,E_a) step also removes X B like that driver does (its line 180).  variates may be NULL

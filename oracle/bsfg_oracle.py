@@ -482,3 +482,78 @@ def gibbs_iteration_fixedlambda(data, rv, priors, rp, st, Lambda, v):
         out.update(W=W, W_prec=v["g_W"] / w_rate)
         aux["W_prec_rate"] = w_rate
     return out, aux
+
+
+# --------------------------------------------------------------------------------------
+# Parameter-expanded sampler (fast_BSFG_sampler_px.R:196-311, update_k of BSFG_functions_px.R:301-369)
+# --------------------------------------------------------------------------------------
+def update_k_px(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, px_factor, F_px, Z_W, Lambda_df, delta_2_shape,
+                delta_2_rate, px_shape, px_rate, b0, b1, i, epsilon, prop, variates):
+    """As `update_k` plus px_factor / F_px; draw order of the add arm: k_g_lp, k_g_delta, k_z_lambda, k_u_h2, k_z_Fa,
+    k_z_F, k_g_px (BSFG_functions_px.R:325-334).  Plam is recomputed WITHOUT the px division in both arms (:328, :348)."""
+    res = update_k(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, Z_W, Lambda_df, delta_2_shape, delta_2_rate,
+                   b0, b1, i, epsilon, prop, variates)
+    px_factor = np.asarray(px_factor, dtype=np.float64).ravel().copy()
+    k_old, k_new = F.shape[1], res["F"].shape[1]
+    if k_new == k_old + 1:
+        px_factor = np.append(px_factor, variates["k_g_px"] / px_rate)
+        F_px = np.column_stack([F_px, res["F"][:, k_new - 1] * np.sqrt(px_factor[k_new - 1])])
+    elif k_new < k_old:
+        lind = np.mean(np.abs(Lambda) < epsilon, axis=0)
+        nonred = np.where(~(lind >= prop))[0]
+        px_factor = px_factor[nonred]
+        F_px = F_px[:, nonred]
+    res.update(px_factor=px_factor, F_px=F_px)
+    return res
+
+
+def gibbs_iteration_px(data, rv, priors, rp, st, i, v, with_update_k=True):
+    """One pass of the loop body of fast_BSFG_sampler_px.R (:196-311).  State additionally holds px_factor (k) and F_px
+    (n, k); variates additionally g_px (k) ~ Gamma(px_shape + n/2, 1) and, for the add arm, k_g_px ~ Gamma(px_shape, 1)."""
+    Y, X, Z_1 = data["Y"], data["X"], data["Z_1"]
+    n, p = Y.shape
+    r = Z_1.shape[1]
+    b = X.shape[1]
+    st = {k_: (np.array(v_, dtype=np.float64, copy=True) if isinstance(v_, np.ndarray) else v_) for k_, v_ in st.items()}
+    B, F_px, px = st["B"], st["F_px"], st["px_factor"]
+    aux = {}
+    Lambda_px = sample_Lambda_c(Y - X @ B, F_px, st["resid_Y_prec"], st["E_a_prec"], st["Plam"], rv["invert_aI_bZAZ"], v["z_Lambda"])
+    loc = sample_means_c(Y - F_px @ Lambda_px.T, st["resid_Y_prec"], st["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    B = loc[:b, :]
+    E_a = loc[b:b + r, :]
+    F_temp = sweep_times(F_px, 2, 1.0 / np.sqrt(px))                                            # :232
+    F_h2 = sample_h2s_discrete_c(F_temp, rp["h2_divisions"], priors["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"])
+    F_a = sample_F_a_c(F_temp, Z_1, F_h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
+    F_a_px = sweep_times(F_a, 2, np.sqrt(px))                                                    # :249
+    tau_e = 1.0 / (px * (1.0 - F_h2))                                                            # :250
+    F_px = sample_px_factors_scores_c(Y - X @ B - Z_1 @ E_a, Z_1, Lambda_px, st["resid_Y_prec"], F_a_px, tau_e, px, v["z_F"])
+    F_px_resid = F_px - Z_1 @ F_a_px                                                             # :260
+    px_rate_post = priors["px_rate"] + 0.5 * np.sum(F_px_resid ** 2, axis=0) / (1.0 - F_h2)
+    px = 1.0 / (v["g_px"] / px_rate_post)                                                        # :263
+    aux["px_shape"], aux["px_rate"] = priors["px_shape"] + n / 2.0, px_rate_post
+    Lambda = sweep_times(Lambda_px, 2, np.sqrt(px))                                              # :267
+    Lambda2 = Lambda ** 2
+    df = priors["Lambda_df"]
+    lp_rate = (df + sweep_times(Lambda2, 2, st["tauh"])) / 2.0
+    Lambda_prec = v["g_Lambda_prec"] / lp_rate
+    aux["Lambda_prec_rate"] = lp_rate
+    Y_tilde = Y - X @ B - F_px @ Lambda_px.T - Z_1 @ E_a
+    ry_rate = priors["resid_Y_prec_rate"] + 0.5 * np.sum(Y_tilde ** 2, axis=0)
+    ea_rate = priors["E_a_prec_rate"] + 0.5 * np.einsum("ij,ij->j", E_a, rv["Ainv"] @ E_a)
+    aux["resid_Y_prec_rate"], aux["E_a_prec_rate"] = ry_rate, ea_rate
+    delta, d_shapes, d_rates = sample_delta(st["delta"], st["tauh"], Lambda_prec, priors["delta_1_shape"], priors["delta_1_rate"],
+                                            priors["delta_2_shape"], priors["delta_2_rate"], Lambda2, v["g_delta"])
+    aux["delta_rate"] = d_rates
+    tauh = np.cumprod(delta)
+    Plam = sweep_times(sweep_times(Lambda_prec, 2, tauh), 2, 1.0 / px)                           # :289-290
+    F = sweep_times(F_px, 2, 1.0 / np.sqrt(px))                                                  # :294
+    out = dict(st)
+    out.update(Lambda=Lambda, B=B, E_a=E_a, F_h2=F_h2, F_a=F_a, F=F, F_px=F_px, px_factor=px, Lambda_prec=Lambda_prec,
+               resid_Y_prec=v["g_resid"] / ry_rate, E_a_prec=v["g_Ea"] / ea_rate, delta=delta, tauh=tauh, Plam=Plam)
+    if with_update_k:
+        res = update_k_px(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, px, F_px, Z_1, df, priors["delta_2_shape"],
+                          priors["delta_2_rate"], priors["px_shape"], priors["px_rate"], rp["b0"], rp["b1"], i, rp["epsilon"],
+                          rp["prop"], v)
+        out.update(res)
+    out["nrun"] = i
+    return out, aux

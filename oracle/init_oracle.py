@@ -30,7 +30,8 @@ def default_priors(k_init=20, h2_divisions=50):
     return dict(k_init=k_init, resid_Y_prec_shape=2.0, resid_Y_prec_rate=1 / 10, E_a_prec_shape=2.0,
                 E_a_prec_rate=1 / 10, W_prec_shape=2.0, W_prec_rate=1 / 10, Lambda_df=3.0,
                 delta_1_shape=2.1, delta_1_rate=1 / 20, delta_2_shape=4.5, delta_2_rate=1.0,
-                h2_priors_factors=np.concatenate([[H - 1.0], np.ones(H - 1)]) / (2.0 * (H - 1)))
+                h2_priors_factors=np.concatenate([[H - 1.0], np.ones(H - 1)]) / (2.0 * (H - 1)),
+                px_shape=0.5, px_rate=0.5)                               # model_setup_px.R:55-56
 
 
 def cholcov(X):
@@ -248,7 +249,7 @@ def make_synthetic(n, p, k_true, seed=20131, pedigree="random", b=1):
                 error_factor_Lambda=Lambda, n=n, p=p, r=n)
 
 
-def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0, missing=False):
+def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0, missing=False, px=False):
     """One iteration's worth of injected variates in the layouts of oracle.bsfg_oracle.gibbs_iteration."""
     df = priors["Lambda_df"]
     v = dict(z_Lambda=rng.standard_normal((k, p)), z_means=rng.standard_normal((br, p)),
@@ -263,6 +264,10 @@ def draw_variates(rng, n, p, k, r, br, priors, add_arm=False, r2=0, missing=Fals
     v["g_delta"] = np.array([rng.gamma(s, 1.0) for s in shapes])
     if missing:
         v["z_Y"] = rng.standard_normal((n, p))
+    if px:
+        v["g_px"] = rng.gamma(priors["px_shape"] + n / 2.0, 1.0, size=k)
+        if add_arm:
+            v["k_g_px"] = float(rng.gamma(priors["px_shape"], 1.0))
     if r2 > 0:
         v["z_W"] = rng.standard_normal((r2, p))
         v["g_W"] = rng.gamma(priors["W_prec_shape"] + r2 / 2.0, 1.0, size=p)

@@ -46,7 +46,8 @@ class bsfg_priors(C.Structure):
                 ("delta_2_shape", C.c_double), ("delta_2_rate", C.c_double),
                 ("b_X_prec", C.c_double), ("h2_priors_factors", c_double_p),
                 ("b0", C.c_double), ("b1", C.c_double), ("epsilon", C.c_double), ("prop", C.c_double),
-                ("W_prec_shape", C.c_double), ("W_prec_rate", C.c_double)]
+                ("W_prec_shape", C.c_double), ("W_prec_rate", C.c_double),
+                ("px_shape", C.c_double), ("px_rate", C.c_double)]
 
 
 class bsfg_constants(C.Structure):
@@ -59,13 +60,13 @@ class bsfg_state(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
                  "E_a_prec", "delta", "tauh")] + [("k", C.c_int), ("nrun", C.c_int)] + \
-               [("W", c_double_p), ("W_prec", c_double_p)]
+               [("W", c_double_p), ("W_prec", c_double_p), ("px_factor", c_double_p), ("F_px", c_double_p)]
 
 
 class bsfg_variates(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
-                 "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y")]
+                 "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y", "g_px", "k_g_px")]
 
 
 class bsfg_posterior(C.Structure):
@@ -81,7 +82,7 @@ class bsfg_init_out(C.Structure):
 
 class bsfg_aux(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
-                ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate", "Y_imputed")]
+                ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps", "W_prec_rate", "Y_imputed", "px_rate")]
 
 
 # every symbol include/bsfg_b200.h declares (tests/test_abi.py checks this list against the header)
@@ -92,7 +93,7 @@ EXPORTS = [
     "bsfg_sample_prec_discrete_conditional_c", "bsfg_sample_F_a_c", "bsfg_sample_delta_c",
     "bsfg_dgemm_tn_host", "bsfg_set_gram_default", "bsfg_get_gram_stats",
     "bsfg_create", "bsfg_destroy", "bsfg_set_priors", "bsfg_upload_constants", "bsfg_set_state",
-    "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda",
+    "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda", "bsfg_sweep_px", "bsfg_sweep_px_injected",
     "bsfg_init_lists", "bsfg_posterior_begin", "bsfg_sweep_collect", "bsfg_posterior_count", "bsfg_get_posterior", "bsfg_get_mode",
     "bsfg_get_timing", "bsfg_nccl_unique_id", "bsfg_comm_init", "bsfg_launch_count",
 ]

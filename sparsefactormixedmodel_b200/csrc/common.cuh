@@ -184,7 +184,8 @@ enum Site : uint32_t {
     SITE_U_PREC = 12,      // randu(1) per trait    BSFG_functions_c.cpp:282
     SITE_Z_MEANS_W = 13,   // randn(r2,p)           :68 (second call, fast_BSFG_sampler.R:214)
     SITE_G_W = 14,         // rgamma(p)             fast_BSFG_sampler.R:249
-    SITE_Z_Y = 15          // rnorm(p*n)            fast_BSFG_sampler.R:182 (missing phenotypes)
+    SITE_Z_Y = 15,         // rnorm(p*n)            fast_BSFG_sampler.R:182 (missing phenotypes)
+    SITE_G_PX = 16         // rgamma(k)             fast_BSFG_sampler_px.R:263
 };
 
 struct RngStream {

@@ -869,6 +869,36 @@ __global__ void add_inplace_kernel(double* __restrict__ dst, long ldd, const dou
     }
 }
 
+// ---- parameter-expanded sampler (fast_BSFG_sampler_px.R) ---------------------------------------------------------
+// sq[h] = sqrt(px[h]), isq[h] = 1/sqrt(px[h]), ipx[h] = 1/px[h]
+__global__ void px_vectors_kernel(const double* __restrict__ px, int k, double* __restrict__ sq, double* __restrict__ isq,
+                                  double* __restrict__ ipx) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < k) { const double s = sqrt(px[h]); sq[h] = s; isq[h] = 1.0 / s; ipx[h] = 1.0 / px[h]; }
+}
+// tau_e = 1 / (px_factor * (1 - F_h2))                                     fast_BSFG_sampler_px.R:250
+__global__ void tau_e_px_kernel(const double* __restrict__ F_h2, const double* __restrict__ px, int k, double* __restrict__ tau_e) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) tau_e[j] = 1.0 / (px[j] * (1.0 - F_h2[j]));
+}
+// px_factor[h] = 1 / rgamma(shape = a + n/2, rate = b + colSums((F_px - Z_1 F_a_px)^2)[h] / 2 / (1 - F_h2[h]))   (:260-263)
+// one CTA per factor; ZFa = Z_1 F_a_px (n x k)
+__global__ void px_factor_kernel(const double* __restrict__ Fpx, long ldf, const double* __restrict__ ZFa, long ldz, int n, int k,
+                                 const double* __restrict__ F_h2, double shape, double prior_rate, VarSrc gsrc,
+                                 double* __restrict__ px, double* __restrict__ rate_out) {
+    __shared__ double red[32];
+    const int h = blockIdx.x;
+    if (h >= k) return;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double e = Fpx[(long)h * ldf + i] - ZFa[(long)h * ldz + i]; acc += e * e; }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        const double rate = prior_rate + 0.5 * acc / (1.0 - F_h2[h]);
+        px[h] = 1.0 / (var_gamma(gsrc, h, 0, shape) / rate);
+        if (rate_out) rate_out[h] = rate;
+    }
+}
+
 // ---- posterior bookkeeping on the device (save_posterior_samples, BSFG_functions.R:375-408) ------------------
 // trace slot (rows x kcap, dense) <- current (rows x k, ld), zero padded to kcap columns (the reference pads the sample
 // vector with zeros when k grew, :384-391)
@@ -933,11 +963,12 @@ __global__ void build_prior_prec_kernel(const double* __restrict__ Ainv, long ld
 // add arm, trait-indexed part: new column h = k (0-based) of Lambda_prec, Plam, Lambda
 __global__ void addk_traits_kernel(int p, int h, double df, double tauh_new, VarSrc g_lp, VarSrc z_lam,
                                    double* __restrict__ LP, long ldp, double* __restrict__ Lam, long ldl,
-                                   double* __restrict__ Lt, long ldlt, double* __restrict__ Plamt, long ldpt) {
+                                   double* __restrict__ Lt, long ldlt, double* __restrict__ Plamt, long ldpt,
+                                   double lam_mult /* 1, or 1/sqrt(px_new): the px sweep stores Lambda_px */) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
         const double lp = var_gamma(g_lp, j, 0, df / 2.0) / (df / 2.0);     // R:334
         const double plam = lp * tauh_new;                                 // R:337
-        const double l = var_normal(z_lam, j, 0) * sqrt(1.0 / plam);        // R:338
+        const double l = var_normal(z_lam, j, 0) * sqrt(1.0 / plam) * lam_mult;   // R:338
         LP[(long)h * ldp + j] = lp;
         Lam[(long)h * ldl + j] = l;
         Lt[(long)j * ldlt + h] = l;
@@ -950,7 +981,8 @@ __global__ void addk_fa_kernel(int r, int h, double h2, VarSrc z_fa, double* __r
         Fa[(long)h * lda + i] = var_normal(z_fa, i, 0) * sqrt(h2);
 }
 __global__ void addk_f_kernel(int n, int r, int h, double h2, const double* __restrict__ Z1, long ldz,
-                              const double* __restrict__ Fa, long lda, VarSrc z_f, double* __restrict__ F, long ldf) {
+                              const double* __restrict__ Fa, long lda, VarSrc z_f, double* __restrict__ F, long ldf,
+                              double f_mult /* 1, or sqrt(px_new): the px sweep stores F_px */) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double m;
         if (Z1) {
@@ -959,7 +991,7 @@ __global__ void addk_f_kernel(int n, int r, int h, double h2, const double* __re
         } else {
             m = Fa[(long)h * lda + i];
         }
-        F[(long)h * ldf + i] = m + var_normal(z_f, i, 0) * sqrt(1.0 - h2);
+        F[(long)h * ldf + i] = (m + var_normal(z_f, i, 0) * sqrt(1.0 - h2)) * f_mult;
     }
 }
 // drop arm: keep columns map[0..knew) (ascending) of a column-major matrix, in place

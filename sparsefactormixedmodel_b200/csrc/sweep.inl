@@ -59,6 +59,9 @@ struct bsfg_ctx {
     bool have_priors = false, have_consts = false, have_state = false;
     int n = 0, pl = 0, p_total = 0, p_off = 0, k = 0, kmax = 0, r = 0, b = 0, br = 0, H = 0;
     bool z1_identity = false;
+    bool px_mode = false;         // parameter-expanded sampler: c->F holds F_px, c->Lam / c->Lt hold Lambda_px
+    bsfg::DVec px, px_sq, px_isq, px_ipx, aux_px_rate;
+    bsfg::DMat v_gpx;
     bool has_missing = false;     // NaN in Y: impute + re-rotate every iteration (fast_BSFG_sampler.R:180-184)
     bsfg::DMat Y0, Ycur, fit, Ft, Xt, v_zY, DtXt;
     int r2 = 0;                   // second random effect (Z_2 / W), 0: none
@@ -117,6 +120,7 @@ static void ctx_alloc_factor_storage(bsfg_ctx* c) {
     c->Lt.alloc(km, pl); c->Lam.alloc(pl, km); c->Lmsg.alloc(pl, km); c->LP.alloc(pl, km); c->Plamt.alloc(km, pl); c->Ptmp.alloc(pl, km);
     c->F.alloc(n, km); c->Fa.alloc(r, km); c->UtF.alloc(n, km); c->FtD.alloc(km, br); c->DtF.alloc(br, km);
     c->F_h2.alloc(km); c->delta.alloc(km); c->tauh.alloc(km); c->tau_e.alloc(km);
+    c->px.alloc(km); c->px_sq.alloc(km); c->px_isq.alloc(km); c->px_ipx.alloc(km); c->aux_px_rate.alloc(km);
     c->YL.alloc(n, km); c->ZFa.alloc(n, km); c->T1.alloc(r, km); c->b3.alloc(r, km); c->vfa.alloc(r, km);
     c->FtF.alloc(km, km); c->FtY.alloc(km, pl); c->G2.alloc(km, pl); c->FDth.alloc(km, pl);
     c->Lp.alloc((long)km * (km + 1) / 2); c->Lfac.alloc((long)km * (km + 1) / 2);
@@ -193,7 +197,7 @@ static void gather_rows(bsfg_ctx* c, const RowShard& sh, DMat& C) {
 }
 
 struct IterVariates {   // device-side sources for one iteration
-    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD, zW, gW, zY;
+    VarSrc zL, zM, uh2, zFa, zF, gLP, gR, gE, gD, zW, gW, zY, gPX;
 };
 
 static void phase_mark(bsfg_ctx* c, int idx) {
@@ -260,7 +264,7 @@ static void impute_missing(bsfg_ctx* c, const VarSrc& zY) {
 }
 
 // ---- one Gibbs iteration (everything but update_k), steps numbered as SURVEY.md section 3.1 ----
-static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambda = false) {
+static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambda = false, bool px = false) {
     Device& d = c->dev;
     const int n = c->n, pl = c->pl, k = c->k, r = c->r, b = c->b, br = c->br, H = c->H;
     if (!c->derived_valid) refresh_derived(c);
@@ -330,14 +334,23 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     phase_mark(c, 4);
 
     // 4. F_h2 | F (marginal over F_a)                         R:221 -> cpp:196-238
-    h2s_core(d, UtF, F, c->s.p, H, c->h2_prior.p, v.uh2, c->F_h2.p, c->aux_on ? c->aux_logps.p : nullptr, c->det, c->ll);
+    //    px sweep: both draws see F_temp = F_px / sqrt(px_factor)  (fast_BSFG_sampler_px.R:232-238); YL / ZFa are free here
+    DMat Fh = px ? view(c->YL, n, k) : view(c->F, n, k);
+    DMat UtFh = px ? view(c->ZFa, n, k) : view(c->UtF, n, k);
+    if (px) {
+        px_vectors_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        d.scale(F, nullptr, c->px_isq.p, Fh);
+        d.scale(UtF, nullptr, c->px_isq.p, UtFh);
+    }
+    h2s_core(d, UtFh, Fh, c->s.p, H, c->h2_prior.p, v.uh2, c->F_h2.p, c->aux_on ? c->aux_logps.p : nullptr, c->det, c->ll);
     phase_mark(c, 5);
     // 5. F_a | F, F_h2                                        R:226 -> cpp:293-339
     {
         DMat T1 = view(c->T1, r, k), b3 = view(c->b3, r, k), vfa = view(c->vfa, r, k);
         const RowShard sr = row_shard(c, r);
         std::function<void(DMat&)> gather = [&](DMat& M) { gather_rows(c, sr, M); };
-        fa_core(d, F, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa,
+        fa_core(d, Fh, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa,
                 sr.lo, sr.cnt, (c->cfg.world > 1 && shard_replicated_enabled(1)) ? &gather : nullptr);
     }
     phase_mark(c, 6);
@@ -366,14 +379,19 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
         gemm_rows(c, sn, 1.0, c->U1t, P1, 0.0, YL);
         gemm_rows(c, sn, -1.0, c->DUt, P2, 1.0, YL);
         if (r2 > 0) gemm_rows(c, sn, -1.0, c->Z2t, P3, 1.0, YL);                         // ... - Z_2 W Lmsg  (R:230)
+        // px sweep: F_a_px = F_a * sqrt(px), tau_e = 1 / (px (1 - F_h2))          fast_BSFG_sampler_px.R:249-250
+        DMat Fa_use = px ? view(c->T1, r, k) : view(c->Fa, r, k);
+        if (px) d.scale(Fa, nullptr, c->px_sq.p, Fa_use);
         const double* zfa_p = nullptr; long zfa_ld = 0;
-        if (c->z1_identity) { zfa_p = Fa.p; zfa_ld = Fa.ld; }
+        if (c->z1_identity) { zfa_p = Fa_use.p; zfa_ld = Fa_use.ld; }
         else {
             DMat ZFa = view(c->ZFa, n, k);
-            gemm_rows(c, sn, 1.0, c->Z1t, Fa, 0.0, ZFa);
+            if (px) d.gemm(1.0, c->Z1t, Fa_use, 0.0, ZFa);       // all rows: the px_factor draw needs Z_1 F_a_px in full
+            else gemm_rows(c, sn, 1.0, c->Z1t, Fa_use, 0.0, ZFa);
             zfa_p = ZFa.p; zfa_ld = ZFa.ld;
         }
-        tau_e_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, k, c->tau_e.p);
+        if (px) tau_e_px_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, c->px.p, k, c->tau_e.p);
+        else tau_e_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, k, c->tau_e.p);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         pack_lower_kernel<<<ceil_div((long)k * (k + 1) / 2, 256), 256, 0, d.st>>>(LtL.p, LtL.ld, k, c->Lp.p);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
@@ -382,14 +400,25 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
         launch_factor_rows(d, c->Lfac.p, k, (int)sn.cnt, YL.p + sn.lo, YL.ld, zfa_p + sn.lo, zfa_ld, c->tau_e.p, v.zF,
                            F.p + sn.lo, F.ld, (int)sn.lo);
         gather_rows(c, sn, F);
+        if (px) {
+            // px_factor | F_px, F_a_px, F_h2                      fast_BSFG_sampler_px.R:260-263 (replicated on every rank)
+            px_factor_kernel<<<k, 256, 0, d.st>>>(F.p, F.ld, zfa_p, zfa_ld, n, k, c->F_h2.p, c->pri.px_shape + n / 2.0, c->pri.px_rate,
+                                                  v.gPX, c->px.p, c->aux_on ? c->aux_px_rate.p : nullptr);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            px_vectors_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
     }
     phase_mark(c, 9);
+    // px sweep: Lambda = Lambda_px * sqrt(px) feeds Lambda_prec, delta and update_k (:267); Lmsg is free from here on
+    DMat LamS = px ? view(c->Lmsg, pl, k) : view(c->Lam, pl, k);
+    if (px) d.scale(Lam, nullptr, c->px_sq.p, LamS);
 
     // 7. Lambda_prec | Lambda, tauh                           R:235-236
     if (!fixed_lambda) {
         const long total = (long)pl * k;
         int blocks = (int)std::min<long>((total + 255) / 256, (long)d.sms * 8);
-        lambda_prec_kernel<<<blocks, 256, 0, d.st>>>(Lam.p, Lam.ld, pl, k, c->tauh.p, c->pri.Lambda_df, v.gLP, LP.p, LP.ld,
+        lambda_prec_kernel<<<blocks, 256, 0, d.st>>>(LamS.p, LamS.ld, pl, k, c->tauh.p, c->pri.Lambda_df, v.gLP, LP.p, LP.ld,
                                                      c->aux_on ? c->aux_lp_rate.p : nullptr);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
@@ -438,7 +467,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
 
     if (fixed_lambda) { phase_mark(c, 11); return; }
     // 11-12. delta, tauh, Plam                                R:253-257 -> BSFG_functions.R:272-308
-    factor_reduce_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, Lam.p, Lam.ld, pl, k, c->pri.epsilon, c->colsum_cnt.p,
+    factor_reduce_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, LamS.p, LamS.ld, pl, k, c->pri.epsilon, c->colsum_cnt.p,
                                               c->colsum_cnt.p + c->kmax);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
     allreduce(c, c->colsum_cnt.p, (size_t)2 * c->kmax);
@@ -451,12 +480,13 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
         dim3 grid(ceil_div(pl, 32), ceil_div(k, 32)), block(32, 8);
         plam_kernel<<<grid, block, 0, d.st>>>(LP.p, LP.ld, pl, k, c->tauh.p, Plamt.p, Plamt.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (px) d.scale(Plamt, c->px_ipx.p, nullptr, Plamt);      // Plam = Plam / px_factor (:290); rows of Plamt are factors
     }
     phase_mark(c, 11);
 }
 
 // ---- update_k (BSFG_functions.R:311-372); host decides, device applies -----------------------
-struct KAddVariates { VarSrc g_lp, z_lam, z_fa, z_f; double g_delta, u_h2; bool have_scalars; };
+struct KAddVariates { VarSrc g_lp, z_lam, z_fa, z_f; double g_delta, u_h2, g_px; bool have_scalars; };
 
 static void update_k_step(bsfg_ctx* c, long i, double uu, const KAddVariates* inj) {
     Device& d = c->dev;
@@ -479,12 +509,14 @@ static void update_k_step(bsfg_ctx* c, long i, double uu, const KAddVariates* in
         if (k + 1 > c->kmax) fail(BSFG_ESHAPE, "update_k wants factor %d but k_max = %d", k + 1, c->kmax);
         const int h = k;
         RngStream rs{c->cfg.seed, SITE_K_ADD, (uint32_t)i};
-        double g_delta, u_h2;
-        if (inj && inj->have_scalars) { g_delta = inj->g_delta; u_h2 = inj->u_h2; }
+        double g_delta, u_h2, g_px = 1.0;
+        if (inj && inj->have_scalars) { g_delta = inj->g_delta; u_h2 = inj->u_h2; g_px = inj->g_px; }
         else {
             g_delta = philox_gamma(rs, 0, c->pri.delta_2_shape);
             u_h2 = philox_uniform(rs, 1);
+            if (c->px_mode) g_px = philox_gamma(rs, (uint64_t)1 << 40, c->pri.px_shape);
         }
+        const double px_new = c->px_mode ? g_px / c->pri.px_rate : 1.0;         // BSFG_functions_px.R:333
         std::vector<double> delta(k + 1);
         BSFG_CUDA(cudaMemcpyAsync(delta.data(), c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
         d.sync();
@@ -507,13 +539,22 @@ static void update_k_step(bsfg_ctx* c, long i, double uu, const KAddVariates* in
         }
         addk_traits_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(
             pl, h, c->pri.Lambda_df, tauh[k], g_lp, z_lam, c->LP.p, c->LP.ld, c->Lam.p, c->Lam.ld, c->Lt.p, c->Lt.ld,
-            c->Plamt.p, c->Plamt.ld);
+            c->Plamt.p, c->Plamt.ld, c->px_mode ? 1.0 / sqrt(px_new) : 1.0);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         addk_fa_kernel<<<std::min(ceil_div(r, 256), d.sms * 4), 256, 0, d.st>>>(r, h, u_h2, z_fa, c->Fa.p, c->Fa.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         addk_f_kernel<<<std::min(ceil_div(n, 256), d.sms * 4), 256, 0, d.st>>>(
-            n, r, h, u_h2, c->z1_identity ? nullptr : c->Z1.p, c->Z1.ld, c->Fa.p, c->Fa.ld, z_f, c->F.p, c->F.ld);
+            n, r, h, u_h2, c->z1_identity ? nullptr : c->Z1.p, c->Z1.ld, c->Fa.p, c->Fa.ld, z_f, c->F.p, c->F.ld,
+            c->px_mode ? sqrt(px_new) : 1.0);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (c->px_mode) {
+            // px_factor[k] and, as BSFG_functions_px.R:328 does, Plam = Lambda_prec * tauh for ALL columns (no px division)
+            BSFG_CUDA(cudaMemcpyAsync(c->px.p + k, &px_new, sizeof(double), cudaMemcpyHostToDevice, d.st));
+            d.sync();
+            dim3 grid(ceil_div(pl, 32), ceil_div(k + 1, 32)), block(32, 8);
+            plam_kernel<<<grid, block, 0, d.st>>>(c->LP.p, c->LP.ld, pl, k + 1, c->tauh.p, c->Plamt.p, c->Plamt.ld);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
         c->k = k + 1;
         c->derived_valid = false;
     } else if (num > 0) {                                                    // drop redundant columns, R:342-359
@@ -545,6 +586,10 @@ static void update_k_step(bsfg_ctx* c, long i, double uu, const KAddVariates* in
             DMat h2v = view_at(c->F_h2.p, 1, k, 1);
             compact_cols_kernel<<<1, 32, 0, d.st>>>(h2v.p, 1, 1, knew, c->d_map);
             BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            if (c->px_mode) {
+                compact_cols_kernel<<<1, 32, 0, d.st>>>(c->px.p, 1, 1, knew, c->d_map);     // px_factor[nonred], :351
+                BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            }
         }
         compact_rows_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(c->Lt.p, c->Lt.ld, pl, knew, c->d_map);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
@@ -839,7 +884,14 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
     const int n = c->n, pl = c->pl, r = c->r, b = c->b;
     c->k = k;
     c->iter = st->nrun;
-    DMat F = view(c->F, n, k); F.upload(st->F, d.st);
+    c->px_mode = st->px_factor != nullptr && st->F_px != nullptr;
+    DMat F = view(c->F, n, k);
+    if (c->px_mode) {      // parameter-expanded state: the device keeps F_px (F = F_px / sqrt(px_factor) is derived on get_state)
+        F.upload(st->F_px, d.st);
+        BSFG_CUDA(cudaMemcpyAsync(c->px.p, st->px_factor, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    } else {
+        F.upload(st->F, d.st);
+    }
     c->rp.upload(st->resid_Y_prec, d.st); c->ep.upload(st->E_a_prec, d.st);
     BSFG_CUDA(cudaMemcpyAsync(c->delta.p, st->delta, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
     BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, st->tauh, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
@@ -852,6 +904,11 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
     if (st->Lambda) {
         DMat Lam = view(c->Lam, pl, k), Lt = view(c->Lt, k, pl);
         Lam.upload(st->Lambda, d.st);
+        if (c->px_mode) {   // the device keeps Lambda_px = Lambda / sqrt(px_factor)
+            px_vectors_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            d.scale(Lam, nullptr, c->px_isq.p, Lam);
+        }
         d.transpose(Lam, Lt);
     }
     if (st->Lambda_prec) { DMat LP = view(c->LP, pl, k); LP.upload(st->Lambda_prec, d.st); }
@@ -890,7 +947,19 @@ extern "C" int bsfg_get_state(bsfg_ctx* c, bsfg_state* st) {
         fprintf(stderr, "[bsfg_get_state] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
         t_prev = t;
     };
-    if (st->Lambda) { DMat Lam = view(c->Lam, pl, k); Lam.download(st->Lambda, d.st); }
+    if (c->px_mode) {
+        px_vectors_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    if (st->Lambda) {
+        DMat Lam = view(c->Lam, pl, k);
+        if (c->px_mode) {   // Lambda = Lambda_px * sqrt(px_factor), fast_BSFG_sampler_px.R:267
+            DMat tmp = view(c->Ptmp, pl, k);
+            d.scale(Lam, nullptr, c->px_sq.p, tmp);
+            tmp.download(st->Lambda, d.st);
+            d.sync();
+        } else Lam.download(st->Lambda, d.st);
+    }
     lap("Lambda");
     if (st->Lambda_prec) { DMat LP = view(c->LP, pl, k); LP.download(st->Lambda_prec, d.st); }
     lap("Lambda_prec");
@@ -900,7 +969,19 @@ extern "C" int bsfg_get_state(bsfg_ctx* c, bsfg_state* st) {
         Plam.download(st->Plam, d.st);
     }
     lap("Plam");
-    if (st->F) { DMat F = view(c->F, n, k); F.download(st->F, d.st); }
+    if (st->F) {
+        DMat F = view(c->F, n, k);
+        if (c->px_mode) {   // F = F_px / sqrt(px_factor), fast_BSFG_sampler_px.R:294
+            DMat tmp = view(c->YL, n, k);
+            d.scale(F, nullptr, c->px_isq.p, tmp);
+            tmp.download(st->F, d.st);
+            d.sync();
+        } else F.download(st->F, d.st);
+    }
+    if (c->px_mode) {
+        if (st->F_px) { DMat F = view(c->F, n, k); F.download(st->F_px, d.st); }
+        if (st->px_factor) BSFG_CUDA(cudaMemcpyAsync(st->px_factor, c->px.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+    }
     if (st->F_a) { DMat Fa = view(c->Fa, r, k); Fa.download(st->F_a, d.st); }
     if (st->F_h2) BSFG_CUDA(cudaMemcpyAsync(st->F_h2, c->F_h2.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
     if (st->B && b > 0) c->Bfix.download(st->B, d.st);
@@ -942,15 +1023,19 @@ extern "C" int bsfg_get_aux(bsfg_ctx* c, bsfg_aux* a) {
     if (a->delta_rate) BSFG_CUDA(cudaMemcpyAsync(a->delta_rate, c->delta_rates.p, sizeof(double) * (k + 2), cudaMemcpyDeviceToHost, d.st));
     if (a->W_prec_rate && c->r2 > 0) c->aux_rw.download(a->W_prec_rate, d.st);
     if (a->Y_imputed && c->has_missing) c->Ycur.download(a->Y_imputed, d.st);
+    if (a->px_rate && c->px_mode) BSFG_CUDA(cudaMemcpyAsync(a->px_rate, c->aux_px_rate.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
     if (a->h2_log_ps) BSFG_CUDA(cudaMemcpyAsync(a->h2_log_ps, c->aux_logps.p, sizeof(double) * (size_t)k * c->H, cudaMemcpyDeviceToHost, d.st));
     d.sync();
     BSFG_API_END
 }
 
-extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
+static int sweep_impl(bsfg_ctx* c, int n_iter, bool px) {
     BSFG_API_BEGIN
     require_ready(c);
     if (n_iter < 0) fail(BSFG_EARG, "n_iter < 0");
+    if (px != c->px_mode)
+        fail(BSFG_ESTATE, px ? "bsfg_sweep_px: the state was set without px_factor / F_px"
+                             : "bsfg_sweep: the state is parameter-expanded (px_factor / F_px were set); use bsfg_sweep_px");
     Device& d = c->dev;
     c->aux_on = false;
     if (c->gram.auto_terms && c->lsc.plan) {
@@ -984,8 +1069,9 @@ extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
         v.zW = make_var(nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
         v.gW = make_var(nullptr, seed, SITE_G_W, ii, c->p_off, 1);
         v.zY = make_var(nullptr, seed, SITE_Z_Y, ii, c->p_off, c->n);
+        v.gPX = make_var(nullptr, seed, SITE_G_PX, ii, 0, 1);
         c->phase_timing = (it == n_iter - 1);
-        gibbs_iteration(c, v);
+        gibbs_iteration(c, v, false, px);
         RngStream rs{seed, SITE_U_K, ii};
         update_k_step(c, i, philox_uniform(rs, 0), nullptr);               // uu = runif(1) every iteration, R:325
         c->iter = i;
@@ -993,6 +1079,8 @@ extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) {
     finish_timing(c, launches_before, n_iter);
     BSFG_API_END
 }
+extern "C" int bsfg_sweep(bsfg_ctx* c, int n_iter) { return sweep_impl(c, n_iter, false); }
+extern "C" int bsfg_sweep_px(bsfg_ctx* c, int n_iter) { return sweep_impl(c, n_iter, true); }
 
 namespace bsfg {
 // one saved sample: save_posterior_samples(sp_num, ...)   BSFG_functions.R:375-408
@@ -1105,10 +1193,11 @@ extern "C" int bsfg_sweep_collect(bsfg_ctx* c, int n_iter, int burn, int thin) {
     BSFG_API_END
 }
 
-extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
+static int sweep_injected_impl(bsfg_ctx* c, const bsfg_variates* hv, bool px) {
     BSFG_API_BEGIN
     require_ready(c);
     REQUIRE_PTR(hv);
+    if (px != c->px_mode) fail(BSFG_ESTATE, "sweep_injected: px mode of the call and of the state differ");
     Device& d = c->dev;
     const int n = c->n, pl = c->pl, k = c->k, r = c->r, br = c->br;
     const long i = c->iter + 1;
@@ -1132,6 +1221,7 @@ extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
     v.zW = make_var(c->r2 > 0 ? stage(c->v_zW, hv->z_W, c->r2, pl) : nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
     v.gW = make_var(c->r2 > 0 ? stage(c->v_gW, hv->g_W, pl, 1) : nullptr, seed, SITE_G_W, ii, c->p_off, 1);
     v.zY = make_var(c->has_missing ? stage(c->v_zY, hv->z_Y, n, pl) : nullptr, seed, SITE_Z_Y, ii, c->p_off, n);
+    v.gPX = make_var(px ? stage(c->v_gpx, hv->g_px, k, 1) : nullptr, seed, SITE_G_PX, ii, 0, 1);
     {
         const DMat* gd = nullptr;
         if (hv->g_delta) {       // only as many entries as sample_delta draws: 1 + |2:(k-1)|
@@ -1147,12 +1237,12 @@ extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
     c->phase_timing = true;
     const long long launches_before = g_launch_counter;
     BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
-    gibbs_iteration(c, v);
+    gibbs_iteration(c, v, false, px);
     double uu;
     if (hv->u_k) uu = *hv->u_k;
     else { RngStream rs{seed, SITE_U_K, ii}; uu = philox_uniform(rs, 0); }
     KAddVariates ka;
-    bool have_add = hv->k_g_lp && hv->k_g_delta && hv->k_z_lambda && hv->k_u_h2 && hv->k_z_Fa && hv->k_z_F;
+    bool have_add = hv->k_g_lp && hv->k_g_delta && hv->k_z_lambda && hv->k_u_h2 && hv->k_z_Fa && hv->k_z_F && (!px || hv->k_g_px);
     if (have_add) {
         // staged as one buffer: [g_lp (pl) | z_lambda (pl) | z_Fa (r) | z_F (n)]
         const long tot = 2L * pl + r + n;
@@ -1165,13 +1255,15 @@ extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) {
         auto mk = [&](double* p) { VarSrc s = make_var(nullptr, 0, 0, 0, 0, 1); s.ptr = p; s.ld = 0; return s; };
         ka.g_lp = mk(c->v_kadd.p); ka.z_lam = mk(c->v_kadd.p + pl); ka.z_fa = mk(c->v_kadd.p + 2L * pl);
         ka.z_f = mk(c->v_kadd.p + 2L * pl + r);
-        ka.g_delta = *hv->k_g_delta; ka.u_h2 = *hv->k_u_h2; ka.have_scalars = true;
+        ka.g_delta = *hv->k_g_delta; ka.u_h2 = *hv->k_u_h2; ka.g_px = px ? *hv->k_g_px : 1.0; ka.have_scalars = true;
     }
     update_k_step(c, i, uu, have_add ? &ka : nullptr);
     c->iter = i;
     finish_timing(c, launches_before, 1);
     BSFG_API_END
 }
+extern "C" int bsfg_sweep_injected(bsfg_ctx* c, const bsfg_variates* hv) { return sweep_injected_impl(c, hv, false); }
+extern "C" int bsfg_sweep_px_injected(bsfg_ctx* c, const bsfg_variates* hv) { return sweep_injected_impl(c, hv, true); }
 
 extern "C" int bsfg_sweep_fixed_lambda(bsfg_ctx* c, const double* Lambda, int k, const bsfg_variates* hv) {
     BSFG_API_BEGIN

@@ -26,7 +26,7 @@ from ._lib import as_f, check, ptr
 _STATE_FIELDS = ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
                  "E_a_prec", "delta", "tauh")
 _VARIATE_FIELDS = ("z_Lambda", "z_means", "u_h2", "z_Fa", "z_F", "g_Lambda_prec", "g_resid", "g_Ea",
-                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y")
+                   "g_delta", "u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "z_W", "g_W", "z_Y", "g_px", "k_g_px")
 
 
 _GRAM_MODES = {"default": 0, "exact": 1, "expsum": 2}
@@ -125,7 +125,8 @@ class BSFGSweep:
                               priors["delta_1_rate"], priors["delta_2_shape"], priors["delta_2_rate"], bx,
                               ptr(self._h2p), run_parameters["b0"], run_parameters["b1"],
                               run_parameters["epsilon"], run_parameters["prop"],
-                              priors.get("W_prec_shape", 2.0), priors.get("W_prec_rate", 0.1))
+                              priors.get("W_prec_shape", 2.0), priors.get("W_prec_rate", 0.1),
+                              priors.get("px_shape", 0.5), priors.get("px_rate", 0.5))
         check(self.lib.bsfg_set_priors(self._ctx, C.byref(pr)))
         # constants (this rank's trait columns of Y)
         l1 = run_variables["invert_aI_bZAZ"]; l2 = run_variables["invert_aPXA_bDesignDesignT"]
@@ -190,6 +191,10 @@ class BSFGSweep:
         st.tauh = put("tauh", np.ascontiguousarray(np.asarray(cs["tauh"], dtype=np.float64).ravel()))
         st.k = k
         st.nrun = int(cs.get("nrun", 0))
+        self.px_mode = cs.get("px_factor") is not None and cs.get("F_px") is not None
+        if self.px_mode:      # parameter-expanded state (fast_BSFG_sampler_init_px.R:221-222)
+            st.px_factor = put("px_factor", np.ascontiguousarray(np.asarray(cs["px_factor"], dtype=np.float64).ravel()))
+            st.F_px = put("F_px", as_f(cs["F_px"]))
         if self.r2 > 0:
             st.W = put("W", as_f(np.asarray(cs["W"])[:, sl]))
             st.W_prec = put("W_prec", np.ascontiguousarray(np.asarray(cs["W_prec"], dtype=np.float64).ravel()[sl]))
@@ -205,7 +210,9 @@ class BSFGSweep:
         if out is None or out["F"].shape[1] != k:
             out = self.alloc_state(k, with_E_a)
         st = _lib.bsfg_state()
-        for name in _STATE_FIELDS + ("W", "W_prec"):
+        if getattr(self, "px_mode", False) and "px_factor" not in out:
+            out["px_factor"] = np.zeros(k); out["F_px"] = np.zeros((self.n, k), order="F")
+        for name in _STATE_FIELDS + ("W", "W_prec", "px_factor", "F_px"):
             if name in out and out[name] is not None and out[name].size:
                 setattr(st, name, ptr(out[name]))
         check(self.lib.bsfg_get_state(self._ctx, C.byref(st)))
@@ -225,8 +232,10 @@ class BSFGSweep:
 
     # -- sweeping --------------------------------------------------------------------------
     def sweep(self, n_iter):
-        """`n_iter` Gibbs iterations with device Philox draws."""
-        check(self.lib.bsfg_sweep(self._ctx, int(n_iter)))
+        """`n_iter` Gibbs iterations with device Philox draws (the parameter-expanded loop when the state was set with
+        px_factor / F_px, fast_BSFG_sampler_px.R)."""
+        fn = self.lib.bsfg_sweep_px if getattr(self, "px_mode", False) else self.lib.bsfg_sweep
+        check(fn(self._ctx, int(n_iter)))
 
     def sweep_injected(self, variates):
         """One iteration with injected variates (dict in the layout of oracle gibbs_iteration; trait-indexed
@@ -250,7 +259,8 @@ class BSFGSweep:
         for name in _VARIATE_FIELDS:
             if variates.get(name) is not None:
                 setattr(v, name, conv(name, variates[name]))
-        check(self.lib.bsfg_sweep_injected(self._ctx, C.byref(v)))
+        fn = self.lib.bsfg_sweep_px_injected if getattr(self, "px_mode", False) else self.lib.bsfg_sweep_injected
+        check(fn(self._ctx, C.byref(v)))
 
     def sweep_fixed_lambda(self, Lambda, variates=None):
         """One iteration of the fixed-Lambda sampler (fast_BSFG_sampler_fixedlambda.R:159-236) with `Lambda` (p x k, all
@@ -315,10 +325,11 @@ class BSFGSweep:
         out = dict(Lambda_prec_rate=np.zeros((self.pl, k), order="F"), resid_Y_prec_rate=np.zeros(self.pl),
                    E_a_prec_rate=np.zeros(self.pl), delta_rate=np.zeros(k + 2), h2_log_ps=np.zeros((k, self.H), order="F"),
                    W_prec_rate=np.zeros(self.pl),
-                   Y_imputed=np.zeros((self.n, self.pl) if self.has_missing else (0, 0), order="F"))
+                   Y_imputed=np.zeros((self.n, self.pl) if self.has_missing else (0, 0), order="F"),
+                   px_rate=np.zeros(k))
         a = _lib.bsfg_aux(*[ptr(out[nm]) if out[nm].size else None
                             for nm in ("Lambda_prec_rate", "resid_Y_prec_rate", "E_a_prec_rate", "delta_rate", "h2_log_ps",
-                                       "W_prec_rate", "Y_imputed")])
+                                       "W_prec_rate", "Y_imputed", "px_rate")])
         check(self.lib.bsfg_get_aux(self._ctx, C.byref(a)))
         return out
 

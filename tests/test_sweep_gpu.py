@@ -366,6 +366,86 @@ def test_sweep_rejects_inconsistent_calls():
     assert ei.value.code == _lib.BSFG_ESHAPE
 
 
+def _px_state(cs, pri, rng):
+    cs = dict(cs)
+    k = cs["F"].shape[1]
+    cs["px_factor"] = rng.gamma(pri["px_shape"], 1.0, k) / pri["px_rate"] + 0.05      # fast_BSFG_sampler_init_px.R:221
+    cs["F_px"] = cs["F"] * np.sqrt(cs["px_factor"])[None, :]                        # :222
+    return cs
+
+
+def test_sweep_parameter_expanded():
+    """fast_BSFG_sampler_px.R:196-311: Lambda_px / F_px / px_factor; Plam divided by px_factor; F and Lambda derived."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 55, 42, 5
+    st = _build(n, p, k, "stable", seed=31)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    rng = np.random.default_rng(8)
+    ora = _px_state(cs, pri, rng)
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8)
+    try:
+        for it in (1, 2, 3):
+            v = I.draw_variates(rng, n, p, k, n, 1 + n, pri, px=True)
+            sw.set_state(ora)
+            ora_next, aux = O.gibbs_iteration_px(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            _compare_states(dev, ora_next, 1)
+            assert relerr(dev["px_factor"], ora_next["px_factor"]) < TOL
+            assert rowwise_relerr(dev["F_px"], ora_next["F_px"]) < TOL
+            a = sw.aux()
+            assert relerr(a["px_rate"], aux["px_rate"]) < TOL
+            assert relerr(a["Lambda_prec_rate"], aux["Lambda_prec_rate"]) < TOL
+            ora = ora_next
+        sw.set_state(ora)
+        sw.sweep(3)                                   # device Philox path of the px loop
+        out = sw.get_state()
+        assert np.all(np.isfinite(out["F"])) and np.all(out["px_factor"] > 0)
+        assert relerr(out["F"] * np.sqrt(out["px_factor"])[None, :], out["F_px"]) < 1e-13
+    finally:
+        sw.close()
+
+
+def test_update_k_px_add_and_drop():
+    """update_k of BSFG_functions_px.R:301-369: px_factor / F_px follow the added or dropped columns and Plam is recomputed
+    WITHOUT the px division in both arms (:328, :348)."""
+    from oracle import bsfg_oracle as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = 40, 30, 5
+    st = _build(n, p, k, "stable", seed=13)
+    d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
+    rng = np.random.default_rng(4)
+    cs = dict(cs)
+    # the 4th delta is huge: the last two loading columns are shrunk to ~1e-6 -> redundant -> the drop arm fires first
+    # (k: 5 -> 3), after which every column is important and the add arm fires (3 -> 4 -> 5 -> 6)
+    cs["delta"] = np.array([1.5, 1.2, 1.1, 1e12, 1.2]); cs["tauh"] = np.cumprod(cs["delta"])
+    cs["Plam"] = cs["Lambda_prec"] * cs["tauh"][None, :]
+    cs["nrun"] = 300
+    ora = _px_state(cs, pri, rng)
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8)
+    try:
+        sw.set_state(ora)
+        seen = set()
+        for it in range(301, 305):
+            kk = ora["F"].shape[1]
+            v = I.draw_variates(rng, n, p, kk, n, 1 + n, pri, add_arm=True, px=True)
+            v["u_k"] = 0.0                                          # always inside the adaptation probability
+            ora, _ = O.gibbs_iteration_px(d, rv, pri, rp, ora, it, v)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            k2 = ora["F"].shape[1]
+            seen.add("add" if k2 > kk else ("drop" if k2 < kk else "same"))
+            assert dev["F"].shape[1] == k2
+            assert rowwise_relerr(dev["F_px"], ora["F_px"]) < 1e-8 and relerr(dev["px_factor"], ora["px_factor"]) < 1e-8
+            assert rowwise_relerr(dev["Lambda"], ora["Lambda"]) < 1e-8 and relerr(dev["Plam"], ora["Plam"]) < 1e-8
+            assert relerr(dev["delta"], ora["delta"]) < 1e-8
+            sw.set_state(ora)
+        assert {"add", "drop"} <= seen, seen
+    finally:
+        sw.close()
+
+
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
     from oracle import bsfg_oracle as O, init_oracle as I
