@@ -1095,8 +1095,19 @@ static void posterior_store(bsfg_ctx* c, int sp_num) {
                                                                                                  tr.p + (long)s * tr.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     };
-    store(c->Lam.p, c->Lam.ld, pl, c->tr_Lambda);
-    store(c->F.p, c->F.ld, n, c->tr_F);
+    if (c->px_mode) {
+        // the px loop saves Lambda = Lambda_px sqrt(px) and F = F_px / sqrt(px)   (fast_BSFG_sampler_px.R:267, 294, 317)
+        px_vectors_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        DMat Lam = view(c->Lam, pl, k), Ls = view(c->Ptmp, pl, k), F = view(c->F, n, k), Fs = view(c->YL, n, k);
+        d.scale(Lam, nullptr, c->px_sq.p, Ls);
+        d.scale(F, nullptr, c->px_isq.p, Fs);
+        store(Ls.p, Ls.ld, pl, c->tr_Lambda);
+        store(Fs.p, Fs.ld, n, c->tr_F);
+    } else {
+        store(c->Lam.p, c->Lam.ld, pl, c->tr_Lambda);
+        store(c->F.p, c->F.ld, n, c->tr_F);
+    }
     store(c->Fa.p, c->Fa.ld, r, c->tr_Fa);
     store(c->delta.p, 1, 1, c->tr_delta);
     store(c->F_h2.p, 1, 1, c->tr_h2);
@@ -1184,7 +1195,7 @@ extern "C" int bsfg_sweep_collect(bsfg_ctx* c, int n_iter, int burn, int thin) {
         long i = c->iter, nxt = std::max<long>(i + 1, burn + 1);
         while ((nxt - burn) % thin != 0) nxt++;
         const int step = (int)std::min<long>(nxt - i, n_iter - done);
-        const int rc = bsfg_sweep(c, step);
+        const int rc = c->px_mode ? bsfg_sweep_px(c, step) : bsfg_sweep(c, step);
         if (rc != BSFG_OK) return rc;
         done += step;
         if (c->iter == nxt) posterior_store(c, (int)((nxt - burn) / thin));
@@ -1270,6 +1281,7 @@ extern "C" int bsfg_sweep_fixed_lambda(bsfg_ctx* c, const double* Lambda, int k,
     require_ready(c);
     REQUIRE_PTR(Lambda);
     if (k != c->k) fail(BSFG_ESHAPE, "bsfg_sweep_fixed_lambda: Lambda has %d columns, the state has k = %d", k, c->k);
+    if (c->px_mode) fail(BSFG_ESTATE, "bsfg_sweep_fixed_lambda: the state is parameter-expanded; set a plain state first");
     Device& d = c->dev;
     const int n = c->n, pl = c->pl, r = c->r, br = c->br;
     const long i = c->iter + 1;

@@ -403,6 +403,12 @@ def test_sweep_parameter_expanded():
         out = sw.get_state()
         assert np.all(np.isfinite(out["F"])) and np.all(out["px_factor"] > 0)
         assert relerr(out["F"] * np.sqrt(out["px_factor"])[None, :], out["F_px"]) < 1e-13
+        # device posterior in px mode stores the identified Lambda and F (:317), not Lambda_px / F_px
+        sw.posterior_begin(2)
+        sw.collect(2, 0, 1)
+        post, fin = sw.posterior(), sw.get_state()
+        assert relerr(post["Lambda"][:, 1].reshape(p, 8, order="F")[:, :k], fin["Lambda"]) < 1e-13
+        assert relerr(post["F"][:, 1].reshape(n, 8, order="F")[:, :k], fin["F"]) < 1e-13
     finally:
         sw.close()
 
