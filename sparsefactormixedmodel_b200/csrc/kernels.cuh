@@ -351,9 +351,11 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
         for (int e = 0; e < 2; e++) {
             const int i = r0 + e;
             if (i < 0 || i >= br) continue;
+            // mean = (v rp)/d, noise = z/sqrt(d) with one reciprocal square root r = d^-1/2 instead of a division, a
+            // square root and another division (cpp:76-78; the draw is compute bound on the FP64 pipe)
             const double d = s1[i] * epj + s2[i] * rpj;
-            const double mean = (DtYt[(long)j * ldd + i] * rpj) / d;
-            const double th = mean + z[e] / sqrt(d);
+            const double r = rsqrt(d);
+            const double th = ((DtYt[(long)j * ldd + i] * rpj) * r + z[e]) * r;
             theta[(long)j * ldt + i] = th;
             if (Bout) {
 #pragma unroll
