@@ -222,14 +222,17 @@ class ClockSampler:
 # CPU baseline: the oracle on a bounded trait sample (the ONLY place bench.py touches oracle/)
 # --------------------------------------------------------------------------------------------
 def cpu_baseline(data, rv, priors, rp, cs, n, p, k, sample_traits, iters=1, seed=1):
-    """Times oracle.gibbs_iteration (reference formulation, incl. U'Y, per-trait k x n GEMMs + chol, dense
-    Z_1 E_a and the full t(E_a) Ainv E_a product) on the first `sample_traits` traits at full n and k, and
-    scales to p traits: per-trait work dominates and is linear in p, so iter/s(p) ~= iter/s(sample) * sample/p.
-    (The p^2 r term of fast_BSFG_sampler.R:245 is under-counted by the sample -- in the reference's favour.)"""
-    from oracle import bsfg_oracle as O, init_oracle as I   # test infrastructure, used here as the timed baseline
+    """Times the C++ CPU oracle (oracle/c/bsfg_ref.cpp: the reference formulation -- U'Y, per-trait k x n GEMMs + chol +
+    3 solves, per-trait U gemv, dense Z_1 E_a, the full t(E_a) Ainv E_a product -- compiled against SciPy's OpenBLAS with
+    all host threads inside BLAS, i.e. the parallelism R + a threaded BLAS has) on the first `sample_traits` traits at
+    full n and k, and scales to p traits: per-trait work dominates and is linear in p, so
+    iter/s(p) ~= iter/s(sample) * sample/p.  (The p^2 r term of fast_BSFG_sampler.R:245 is under-counted by the sample --
+    in the reference's favour.)  Also reports "baseline-opt" (BASELINE.md section 2): the same code with the per-trait
+    loops under OpenMP and single-threaded BLAS per trait."""
+    from oracle import c_oracle as CO, init_oracle as I   # test infrastructure, used here as the timed baseline
     ps = min(sample_traits, p)
     sl = slice(0, ps)
-    d = dict(Y=np.ascontiguousarray(data["Y"][:, sl]), X=data["X"], Z_1=data["Z_1"])
+    d = dict(Y=np.asfortranarray(data["Y"][:, sl]), X=data["X"], Z_1=data["Z_1"])
     st = {kk: vv for kk, vv in cs.items() if vv is not None}
     for nm in ("Lambda", "Lambda_prec", "Plam"):
         st[nm] = np.asarray(st[nm])[sl, :]
@@ -237,23 +240,29 @@ def cpu_baseline(data, rv, priors, rp, cs, n, p, k, sample_traits, iters=1, seed
         st[nm] = np.asarray(st[nm])[sl]
     st["B"] = np.asarray(st["B"])[:, sl]
     rng = np.random.default_rng(seed)
-    t_best = None
-    for it in range(iters):
-        v = I.draw_variates(rng, n, ps, k, n, rv["b"] + n, priors)
-        t0 = time.perf_counter()
-        st, _ = O.gibbs_iteration(d, rv, priors, rp, st, it + 1, v, with_update_k=False)
-        dt = time.perf_counter() - t0
-        t_best = dt if t_best is None else min(t_best, dt)
-    try:
-        import threadpoolctl
-        cores = max([x.get("num_threads", 1) for x in threadpoolctl.threadpool_info()] + [1])
-    except Exception:
-        cores = os.cpu_count() or 1
-    value = 1.0 / (t_best * (p / ps))
+    cores = os.cpu_count() or 1
+    CO.blas_threads(cores)
+
+    def best(trait_threads):
+        t_best, cur = None, st
+        for it in range(iters):
+            v = I.draw_variates(rng, n, ps, k, n, rv["b"] + n, priors)
+            t0 = time.perf_counter()
+            cur, _ = CO.gibbs_iteration_c(d, rv, priors, rp, cur, v, trait_threads=trait_threads)
+            dt = time.perf_counter() - t0
+            t_best = dt if t_best is None else min(t_best, dt)
+        return t_best
+
+    t_ref = best(1)
+    t_opt = best(cores)
+    value = 1.0 / (t_ref * (p / ps))
     return {"value": value, "unit": "iter/s", "cores": int(cores), "kind": "port",
-            "sample": f"oracle.gibbs_iteration (NumPy/OpenBLAS restatement of the Rcpp path, reference formulation) on "
-                      f"{ps} of {p} traits at full n={n}, k={k}: {t_best:.2f} s/iter on the sample, scaled x{p / ps:.1f} "
-                      f"(per-trait work is linear in p); best of {iters}"}
+            "sample": f"oracle/c/bsfg_ref.cpp (C++ restatement of the Rcpp path in the reference formulation, SciPy OpenBLAS, "
+                      f"{CO.blas_threads()} BLAS threads) on {ps} of {p} traits at full n={n}, k={k}: {t_ref:.2f} s/iter on the "
+                      f"sample, scaled x{p / ps:.1f} (per-trait work is linear in p); best of {iters}",
+            "baseline_opt": {"value": 1.0 / (t_opt * (p / ps)), "unit": "iter/s",
+                             "what": f"same code, per-trait loops under OpenMP ({cores} threads) with single-threaded BLAS: "
+                                     f"{t_opt:.2f} s/iter on the sample"}}
 
 
 # --------------------------------------------------------------------------------------------

@@ -101,6 +101,23 @@ def test_golden_lists_satisfy_their_contract(name):
     assert relerr(got, np.linalg.inv(a_ * Z.T @ Z + b_ * rv["Ainv"])) < 1e-8
 
 
+@pytest.mark.parametrize("name", ("sim1", "example"))
+@pytest.mark.parametrize("trait_threads", (1, 3))
+def test_cpp_oracle_matches_numpy_oracle(name, trait_threads):
+    """oracle/c/bsfg_ref.cpp (the compiled CPU baseline of bench.py: reference formulation against SciPy's OpenBLAS) is a
+    third restatement; it must agree with the NumPy one on the reference's own fixtures, in the reference's serial
+    order and with the per-trait loops under OpenMP."""
+    from oracle import bsfg_oracle as O, c_oracle as CO
+    g, d, rv, pri, rp = golden_problem(name)
+    st, v = g["state0"], g["variates1"]
+    want, aux = O.gibbs_iteration(d, rv, pri, rp, st, 1, v, with_update_k=False)
+    got, aux_c = CO.gibbs_iteration_c(d, rv, pri, rp, st, v, trait_threads=trait_threads)
+    for f in STATE_FIELDS:
+        assert relerr(np.asarray(got[f]).ravel(), np.asarray(want[f]).ravel()) < 1e-10, f
+    assert relerr(aux_c["resid_Y_prec_rate"], aux["resid_Y_prec_rate"]) < 1e-10
+    assert relerr(aux_c["E_a_prec_rate"], aux["E_a_prec_rate"]) < 1e-10
+
+
 # ------------------------------------------------------------------------------------------------
 # (1) `_c` restatement == R-twin restatement
 # ------------------------------------------------------------------------------------------------
