@@ -112,6 +112,14 @@ int bsfg_sample_delta_c(const double* delta, const double* tauh, int k, const do
                         unsigned long long seed, double* delta_out, int* n_draws_out,
                         double* shapes_out, double* rates_out);
 
+/* GSVD_2_c(A,B)                                                                    cpp:27-40
+ * A, B n x n (B invertible).  The reference's literal route svd(A inv(B)): returns U, V (n x n, orthogonal), X (n x n) and
+ * the DIAGONALS of C and S (n each; the R closure rebuilds diagmat) with A = U C X', B = V S X', C^2 + S^2 = I.  Init-only in
+ * the reference (fast_BSFG_sampler_init.R:289,303,320); bsfg_init_lists is the faster, better-conditioned way to the same
+ * lists.  Any output may be NULL.  Uses cuSOLVER (getrf/getrs/gesvd) through dlopen.                                    */
+int bsfg_GSVD_2_c(const double* A, const double* B, int n, double* U_out, double* V_out, double* X_out, double* C_out,
+                  double* S_out);
+
 /* Process-wide default for the weighted-Gram evaluation used by bsfg_sample_Lambda_c and by contexts created with
  * gram_mode == 0 (see bsfg_config): mode 1 exact, 2 exponential sum (library default); terms/step 0 = keep.      */
 int bsfg_set_gram_default(int mode, int terms, double step);
@@ -228,6 +236,18 @@ typedef struct bsfg_variates {
      * ~ Gamma(px_shape, 1) for the add-a-factor arm (BSFG_functions_px.R:333) */
     const double* g_px; const double* k_g_px;
 } bsfg_variates;
+
+/* update_k(current_state, priors, run_parameters, data_matrices)  (R only, BSFG_functions.R:311-372; with px_factor and
+ * F_px (n x k_max) non-NULL the variant of BSFG_functions_px.R:301-369); device version named update_k_c.
+ * Factor-indexed arrays are IN/OUT with capacity k_max columns and leading dimension = rows: Lambda, Lambda_prec, Plam
+ * p x k_max; F n x k_max; F_a r x k_max; F_h2, delta, tauh, px_factor k_max entries; the first k (on return *k_out) columns
+ * are meaningful, and nothing is written when k does not change.  i = current_state$nrun (R:323).  Z_1 n x r, or NULL for
+ * the identity (r == n).  variates (or NULL members -> Philox keyed by (seed, i)): u_k (R:325) and the add-a-factor arm
+ * k_g_lp p, k_g_delta, k_z_lambda p, k_u_h2, k_z_Fa r, k_z_F n (R:334-341; k_g_px with px_factor).                      */
+int bsfg_update_k_c(int n, int p, int r, int k, int k_max, long long i, const bsfg_priors* priors, const double* Z_1,
+                    double* Lambda, double* Lambda_prec, double* Plam, double* delta, double* tauh, double* F_h2, double* F,
+                    double* F_a, double* px_factor, double* F_px, const bsfg_variates* variates, unsigned long long seed,
+                    int* k_out);
 
 /* Gamma (shape, rate) parameters of the last iteration's precision draws, for parity checks. */
 typedef struct bsfg_aux {

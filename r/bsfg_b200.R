@@ -27,6 +27,32 @@ sample_F_a_c <- function(F, Z_1, F_h2, invert_aZZt_Ainv, variates = NULL, seed =
 # device version of the R-only sample_delta (BSFG_functions.R:272); same argument order
 sample_delta_c <- function(delta, tauh, Lambda_prec, delta_1_shape, delta_1_rate, delta_2_shape, delta_2_rate, Lambda2, variates = NULL, seed = .bsfg_seed())
   .Call('R_bsfg_sample_delta_c', as.double(delta), as.double(tauh), Lambda_prec, delta_1_shape, delta_1_rate, delta_2_shape, delta_2_rate, Lambda2, variates, seed)
+# GSVD_2_c(A, B) (BSFG_functions_c.cpp:27-40): list(U, V, X, C, S)
+GSVD_2_c <- function(A, B) .Call('R_bsfg_GSVD_2_c', A, B)
+# device version of the R-only update_k (BSFG_functions.R:311-372; BSFG_functions_px.R:301-369 when current_state has px_factor);
+# same argument list, returns current_state
+update_k_c <- function(current_state, priors, run_parameters, data_matrices, seed = .bsfg_seed()) {
+  cs <- current_state; k <- ncol(cs$F); n <- nrow(cs$F); p <- nrow(cs$Lambda); r <- nrow(cs$F_a)
+  pad <- function(m) cbind(m, 0) + 0; padv <- function(v) c(as.double(v), 0)
+  b <- list(Lambda = pad(cs$Lambda), Lambda_prec = pad(cs$Lambda_prec), Plam = pad(cs$Plam), F = pad(cs$F), F_a = pad(cs$F_a),
+            delta = padv(cs$delta), tauh = padv(cs$tauh), F_h2 = padv(cs$F_h2))
+  px <- !is.null(cs$px_factor)
+  if (px) { b$px_factor <- padv(cs$px_factor); b$F_px <- pad(cs$F_px) }
+  pr <- priors; rp <- run_parameters
+  pri <- c(pr$resid_Y_prec_shape, pr$resid_Y_prec_rate, pr$E_a_prec_shape, pr$E_a_prec_rate, pr$Lambda_df,
+           pr$delta_1_shape, pr$delta_1_rate, pr$delta_2_shape, pr$delta_2_rate, pr$b_X_prec[1], rp$b0, rp$b1, rp$epsilon, rp$prop,
+           2, 0.1, if (px) pr$px_shape else 0.5, if (px) pr$px_rate else 0.5)
+  Z_1 <- data_matrices$Z_1
+  ident <- nrow(Z_1) == ncol(Z_1) && all(Z_1 == diag(nrow(Z_1)))
+  kn <- .Call('R_bsfg_update_k_c', as.integer(c(n, p, r, k, k + 1, cs$nrun)), pri, if (ident) NULL else Z_1, b$Lambda, b$Lambda_prec,
+              b$Plam, b$delta, b$tauh, b$F_h2, b$F, b$F_a, b$px_factor, b$F_px, seed)
+  if (kn != k) {
+    for (nm in c('Lambda', 'Lambda_prec', 'Plam', 'F', 'F_a', if (px) 'F_px')) cs[[nm]] <- b[[nm]][, 1:kn, drop = FALSE]
+    for (nm in c('delta', 'tauh', if (px) 'px_factor')) cs[[nm]] <- b[[nm]][1:kn]
+    cs$F_h2 <- matrix(b$F_h2[1:kn], kn, 1); cs$k <- kn
+  }
+  cs
+}
 
 # fast_BSFG_sampler with the loop body (fast_BSFG_sampler.R:176-270) on the GPU.  Prologue/epilogue of the
 # reference driver (state unpacking :56-152, Posterior growth :159-169, save/return :311-346) stay as they are;

@@ -102,6 +102,35 @@ SEXP R_bsfg_sample_delta_c(SEXP delta, SEXP tauh, SEXP LP, SEXP d1s, SEXP d1r, S
     return out;
 }
 
+/* GSVD_2_c(A,B)                                                                      cpp:27-40 */
+SEXP R_bsfg_GSVD_2_c(SEXP A, SEXP B) {
+    int n = Rf_ncols(B);
+    const char* names[] = {"U", "V", "X", "C", "S", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SEXP U = PROTECT(Rf_allocMatrix(REALSXP, n, n)), V = PROTECT(Rf_allocMatrix(REALSXP, n, n)), X = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+    SEXP Cm = PROTECT(Rf_allocMatrix(REALSXP, n, n)), Sm = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+    double* c = (double*)R_alloc(n, sizeof(double)); double* sd = (double*)R_alloc(n, sizeof(double));
+    chk(bsfg_GSVD_2_c(REAL(A), REAL(B), n, REAL(U), REAL(V), REAL(X), c, sd));
+    memset(REAL(Cm), 0, sizeof(double) * (size_t)n * n); memset(REAL(Sm), 0, sizeof(double) * (size_t)n * n);
+    for (int i = 0; i < n; i++) { REAL(Cm)[(size_t)i * n + i] = c[i]; REAL(Sm)[(size_t)i * n + i] = sd[i]; }   /* diagmat, cpp:35-36 */
+    SET_VECTOR_ELT(out, 0, U); SET_VECTOR_ELT(out, 1, V); SET_VECTOR_ELT(out, 2, X); SET_VECTOR_ELT(out, 3, Cm); SET_VECTOR_ELT(out, 4, Sm);
+    UNPROTECT(6);
+    return out;
+}
+/* update_k: the R closure pads the factor-indexed members to k_max = k + 1 columns (fresh copies), this call edits them in
+ * place and returns the new k; pri as in R_bsfg_create.                                      BSFG_functions.R:311-372 */
+SEXP R_bsfg_update_k_c(SEXP dims, SEXP pri, SEXP Z1, SEXP Lambda, SEXP LP, SEXP Plam, SEXP delta, SEXP tauh, SEXP F_h2, SEXP F,
+                       SEXP F_a, SEXP px_factor, SEXP F_px, SEXP seed) {
+    int* d = INTEGER(dims);            /* c(n,p,r,k,k_max,nrun) */
+    double* q = REAL(pri);
+    bsfg_priors pr = {q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], NULL, q[10], q[11], q[12], q[13],
+                      q[14], q[15], q[16], q[17]};
+    int k_out = 0;
+    chk(bsfg_update_k_c(d[0], d[1], d[2], d[3], d[4], (long long)d[5], &pr, opt(Z1), REAL(Lambda), REAL(LP), REAL(Plam), REAL(delta),
+                        REAL(tauh), REAL(F_h2), REAL(F), REAL(F_a), opt(px_factor), opt(F_px), NULL, seed_of(seed), &k_out));
+    return Rf_ScalarInteger(k_out);
+}
+
 /* ---- device-resident sweep: fast_BSFG_sampler.R:176-270 in one call --------------------------------------- */
 static void ctx_finalizer(SEXP ptr) {
     bsfg_ctx* c = (bsfg_ctx*)R_ExternalPtrAddr(ptr);

@@ -6,7 +6,7 @@ This package is the Python host-side mirror of the reference's `_c` functions an
 without the built library or without a CUDA device raises.
 """
 from ._lib import BSFGError, LIB_PATH, load  # noqa: F401
-from .samplers import (dgemm_tn, sample_delta_c, sample_F_a_c, sample_factors_scores_c,  # noqa: F401
+from .samplers import (GSVD_2_c, dgemm_tn, update_k_c, sample_delta_c, sample_F_a_c, sample_factors_scores_c,  # noqa: F401
                        sample_h2s_discrete_c, sample_Lambda_c, sample_lambda_c, sample_means_c,
                        sample_prec_discrete_conditional_c, sample_px_factors_scores_c)
 from .driver import BSFGSweep, fast_BSFG_sampler, init_lists, set_gram_default  # noqa: F401

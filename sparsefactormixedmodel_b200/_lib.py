@@ -91,6 +91,7 @@ EXPORTS = [
     "bsfg_sample_Lambda_c", "bsfg_sample_lambda_c", "bsfg_sample_means_c",
     "bsfg_sample_factors_scores_c", "bsfg_sample_px_factors_scores_c", "bsfg_sample_h2s_discrete_c",
     "bsfg_sample_prec_discrete_conditional_c", "bsfg_sample_F_a_c", "bsfg_sample_delta_c",
+    "bsfg_update_k_c", "bsfg_GSVD_2_c",
     "bsfg_dgemm_tn_host", "bsfg_set_gram_default", "bsfg_get_gram_stats",
     "bsfg_create", "bsfg_destroy", "bsfg_set_priors", "bsfg_upload_constants", "bsfg_set_state",
     "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda", "bsfg_sweep_px", "bsfg_sweep_px_injected",
@@ -138,3 +139,19 @@ def ptr(a):
     if a is None:
         return None
     return a.ctypes.data_as(c_double_p)
+
+
+def make_priors(priors, run_parameters):
+    """bsfg_priors from the reference's `priors` / `run_parameters` lists (model_setup.R:36-63).  Returns
+    (struct, keepalive): the struct points into keepalive's memory."""
+    h2p = np.ascontiguousarray(np.asarray(priors["h2_priors_factors"], dtype=np.float64).ravel())
+    bx = priors.get("b_X_prec", 1e-10)
+    bx = float(np.asarray(bx).ravel()[0]) if np.size(bx) else 1e-10
+    pr = bsfg_priors(priors["resid_Y_prec_shape"], priors["resid_Y_prec_rate"], priors["E_a_prec_shape"],
+                     priors["E_a_prec_rate"], priors["Lambda_df"], priors["delta_1_shape"],
+                     priors["delta_1_rate"], priors["delta_2_shape"], priors["delta_2_rate"], bx,
+                     ptr(h2p), run_parameters["b0"], run_parameters["b1"],
+                     run_parameters["epsilon"], run_parameters["prop"],
+                     priors.get("W_prec_shape", 2.0), priors.get("W_prec_rate", 0.1),
+                     priors.get("px_shape", 0.5), priors.get("px_rate", 0.5))
+    return pr, h2p

@@ -28,6 +28,12 @@ struct DenseApi {
     cusolverStatus_t (*Potrf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
     cusolverStatus_t (*PotriBuf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
     cusolverStatus_t (*Potri)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
+    cusolverStatus_t (*GetrfBuf)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
+    cusolverStatus_t (*Getrf)(cusolverDnHandle_t, int, int, double*, int, double*, int*, int*) = nullptr;
+    cusolverStatus_t (*Getrs)(cusolverDnHandle_t, cublasOperation_t, int, int, const double*, int, const int*, double*, int, int*) = nullptr;
+    cusolverStatus_t (*GesvdBuf)(cusolverDnHandle_t, int, int, int*) = nullptr;
+    cusolverStatus_t (*Gesvd)(cusolverDnHandle_t, signed char, signed char, int, int, double*, int, double*, double*, int, double*, int,
+                              double*, int, double*, int*) = nullptr;
     cublasStatus_t (*BCreate)(cublasHandle_t*) = nullptr;
     cublasStatus_t (*BSetStream)(cublasHandle_t, cudaStream_t) = nullptr;
     cublasStatus_t (*Trsm)(cublasHandle_t, cublasSideMode_t, cublasFillMode_t, cublasOperation_t, cublasDiagType_t, int, int,
@@ -53,6 +59,9 @@ struct DenseApi {
             BSFG_DSYM(hs, SyevdBuf, "cusolverDnDsyevd_bufferSize"); BSFG_DSYM(hs, Syevd, "cusolverDnDsyevd");
             BSFG_DSYM(hs, PotrfBuf, "cusolverDnDpotrf_bufferSize"); BSFG_DSYM(hs, Potrf, "cusolverDnDpotrf");
             BSFG_DSYM(hs, PotriBuf, "cusolverDnDpotri_bufferSize"); BSFG_DSYM(hs, Potri, "cusolverDnDpotri");
+            BSFG_DSYM(hs, GetrfBuf, "cusolverDnDgetrf_bufferSize"); BSFG_DSYM(hs, Getrf, "cusolverDnDgetrf");
+            BSFG_DSYM(hs, Getrs, "cusolverDnDgetrs");
+            BSFG_DSYM(hs, GesvdBuf, "cusolverDnDgesvd_bufferSize"); BSFG_DSYM(hs, Gesvd, "cusolverDnDgesvd");
             BSFG_DSYM(hb, BCreate, "cublasCreate_v2"); BSFG_DSYM(hb, BSetStream, "cublasSetStream_v2");
             BSFG_DSYM(hb, Trsm, "cublasDtrsm_v2"); BSFG_DSYM(hb, Gemm, "cublasDgemm_v2");
 #undef BSFG_DSYM
@@ -195,7 +204,64 @@ struct InitWork {
     }
 };
 
+// X[, j] *= sqrt(1 + d_j^2);  C_j = d_j / sqrt(1 + d_j^2);  S_j = 1 / sqrt(1 + d_j^2)        cpp:33-37
+__global__ void gsvd_finish_kernel(double* __restrict__ X, long ld, long n, const double* __restrict__ dsv, double* __restrict__ C,
+                                   double* __restrict__ S) {
+    const long total = n * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % n, j = idx / n;
+        const double nf = sqrt(1.0 + dsv[j] * dsv[j]);
+        X[j * ld + i] *= nf;
+        if (i == 0) { C[j] = dsv[j] / nf; S[j] = 1.0 / nf; }
+    }
+}
+
 }  // namespace bsfg
+
+// GSVD_2_c(A, B) (cpp:27-40), the literal route: svd(A inv(B)) = U diag(d) V', norm = sqrt(1 + d^2), C = d / norm, S = 1 / norm,
+// X = (B'V) diag(norm), so that A = U C X' and B = V S X'.  A inv(B) comes from an LU solve (B'M' = A'), the SVD from cuSOLVER gesvd.
+extern "C" int bsfg_GSVD_2_c(const double* A, const double* B, int n, double* U_out, double* V_out, double* X_out, double* C_out,
+                             double* S_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(A); REQUIRE_PTR(B);
+    if (n <= 0) fail(BSFG_ESHAPE, "GSVD_2_c: n must be positive");
+    Device& d = default_device();
+    g_dense.load(d.st);
+    InitWork w(d);
+    DMat dA(n, n), dB(n, n), LU(n, n), Mt(n, n), M(n, n), U(n, n), VT(n, n), V(n, n), X(n, n);
+    DVec sv(n), Cd(n), Sd(n), rwork(n);
+    dA.upload(A, d.st); dB.upload(B, d.st);
+    BSFG_CUDA(cudaMemcpy2DAsync(LU.p, LU.ld * 8, dB.p, dB.ld * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, d.st));
+    d.transpose(dA, Mt);                                                       // right-hand side A'
+    int* ipiv = nullptr;
+    BSFG_CUDA(cudaMalloc(&ipiv, sizeof(int) * (size_t)n));
+    struct PivGuard { int* p; ~PivGuard() { cudaFree(p); } } guard{ipiv};
+    int lwork = 0;
+    if (g_dense.GetrfBuf(g_dense.solver, n, n, LU.p, (int)LU.ld, &lwork) != CUSOLVER_STATUS_SUCCESS) fail(BSFG_ECUDA, "cusolverDnDgetrf_bufferSize failed");
+    w.need(lwork);
+    if (g_dense.Getrf(g_dense.solver, n, n, LU.p, (int)LU.ld, w.work.p, ipiv, w.info) != CUSOLVER_STATUS_SUCCESS) fail(BSFG_ECUDA, "cusolverDnDgetrf failed");
+    w.check_info("GSVD_2_c: inv(B) (B singular?)");
+    if (g_dense.Getrs(g_dense.solver, CUBLAS_OP_T, n, n, LU.p, (int)LU.ld, ipiv, Mt.p, (int)Mt.ld, w.info) != CUSOLVER_STATUS_SUCCESS)
+        fail(BSFG_ECUDA, "cusolverDnDgetrs failed");
+    w.check_info("GSVD_2_c: getrs");
+    d.transpose(Mt, M);                                                        // M = A inv(B)
+    if (g_dense.GesvdBuf(g_dense.solver, n, n, &lwork) != CUSOLVER_STATUS_SUCCESS) fail(BSFG_ECUDA, "cusolverDnDgesvd_bufferSize failed");
+    w.need(lwork);
+    if (g_dense.Gesvd(g_dense.solver, 'A', 'A', n, n, M.p, (int)M.ld, sv.p, U.p, (int)U.ld, VT.p, (int)VT.ld, w.work.p, lwork, rwork.p, w.info)
+        != CUSOLVER_STATUS_SUCCESS) fail(BSFG_ECUDA, "cusolverDnDgesvd failed");
+    w.check_info("GSVD_2_c: svd");
+    d.transpose(VT, V);
+    d.gemm(1.0, dB, V, 0.0, X);                                                // B'V
+    gsvd_finish_kernel<<<w.grid((long)n * n), 256, 0, d.st>>>(X.p, X.ld, n, sv.p, Cd.p, Sd.p);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    if (U_out) U.download(U_out, d.st);
+    if (V_out) V.download(V_out, d.st);
+    if (X_out) X.download(X_out, d.st);
+    if (C_out) Cd.download(C_out, d.st);
+    if (S_out) Sd.download(S_out, d.st);
+    d.sync();
+    BSFG_API_END
+}
 
 extern "C" int bsfg_init_lists(int n, int r, int b, int r2, const double* Z_1, const double* A, const double* X,
                                const double* Z_2, double b_X_prec, bsfg_init_out* out) {

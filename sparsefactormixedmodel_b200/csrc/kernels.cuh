@@ -973,7 +973,7 @@ __global__ void addk_traits_kernel(int p, int h, double df, double tauh_new, Var
         const double l = var_normal(z_lam, j, 0) * sqrt(1.0 / plam) * lam_mult;   // R:338
         LP[(long)h * ldp + j] = lp;
         Lam[(long)h * ldl + j] = l;
-        Lt[(long)j * ldlt + h] = l;
+        if (Lt) Lt[(long)j * ldlt + h] = l;
         Plamt[(long)j * ldpt + h] = plam;
     }
 }

@@ -620,6 +620,263 @@ extern "C" int bsfg_sample_F_a_c(const double* F, int n, int k, const double* Z_
     BSFG_API_END
 }
 
+// ---- update_k (BSFG_functions.R:311-372; px variant BSFG_functions_px.R:301-369): host decides, device applies ----
+// One implementation for the sweep's context (sweep.inl: update_k_step) and the stateless bsfg_update_k_c.
+struct KAddVariates { VarSrc g_lp, z_lam, z_fa, z_f; double g_delta, u_h2, g_px; bool have_scalars; };
+struct KRefs {
+    Device* d; const bsfg_priors* pri; uint64_t seed;
+    int n, pl, r, kmax; long p_total, p_off; int* k;
+    bool z1_identity, px_mode;
+    const double* Z1; long ldz1;
+    DMat *Lam, *LP, *Lt /* k x pl transposed copy, may be null */, *Plamt, *F, *Fa;
+    double *F_h2, *delta, *tauh, *px;
+    const double* cnt;        // device, k doubles: #{j: |Lambda[j,h]| < epsilon} over ALL traits (already reduced over ranks)
+    int* d_map;               // device scratch, kmax ints
+};
+
+// returns true when k changed
+static bool update_k_apply(KRefs& s, long i, double uu, const KAddVariates* inj) {
+    Device& d = *s.d;
+    const bsfg_priors& pri = *s.pri;
+    const double prob = 1.0 / exp(pri.b0 + pri.b1 * (double)i);             // R:324
+    if (!(uu < prob && i > 200)) return false;                              // R:331
+    const int k = *s.k, pl = s.pl, n = s.n, r = s.r;
+    std::vector<double> cnt(k);
+    BSFG_CUDA(cudaMemcpyAsync(cnt.data(), s.cnt, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+    d.sync();
+    std::vector<int> vec(k);
+    int num = 0;
+    bool all_below = true;
+    for (int h = 0; h < k; h++) {
+        const double lind = cnt[h] / (double)s.p_total;                     // colMeans(abs(Lambda) < epsilon), R:326
+        vec[h] = lind >= pri.prop;
+        num += vec[h];
+        if (!(lind < 0.995)) all_below = false;
+    }
+    if (i > 20 && num == 0 && all_below && k < 2 * s.p_total) {             // add a column, R:332-341
+        if (k + 1 > s.kmax) fail(BSFG_ESHAPE, "update_k wants factor %d but k_max = %d", k + 1, s.kmax);
+        const int h = k;
+        RngStream rs{s.seed, SITE_K_ADD, (uint32_t)i};
+        double g_delta, u_h2, g_px = 1.0;
+        if (inj && inj->have_scalars) { g_delta = inj->g_delta; u_h2 = inj->u_h2; g_px = inj->g_px; }
+        else {
+            g_delta = philox_gamma(rs, 0, pri.delta_2_shape);
+            u_h2 = philox_uniform(rs, 1);
+            if (s.px_mode) g_px = philox_gamma(rs, (uint64_t)1 << 40, pri.px_shape);
+        }
+        const double px_new = s.px_mode ? g_px / pri.px_rate : 1.0;         // BSFG_functions_px.R:333
+        std::vector<double> delta(k + 1);
+        BSFG_CUDA(cudaMemcpyAsync(delta.data(), s.delta, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+        d.sync();
+        delta[k] = g_delta / pri.delta_2_rate;                              // R:335
+        std::vector<double> tauh(k + 1);
+        double cp = 1.0;
+        for (int q = 0; q <= k; q++) { cp *= delta[q]; tauh[q] = cp; }
+        BSFG_CUDA(cudaMemcpyAsync(s.delta, delta.data(), sizeof(double) * (k + 1), cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(s.tauh, tauh.data(), sizeof(double) * (k + 1), cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(s.F_h2 + k, &u_h2, sizeof(double), cudaMemcpyHostToDevice, d.st));
+        d.sync();   // host vectors go out of scope
+        VarSrc g_lp, z_lam, z_fa, z_f;
+        if (inj) { g_lp = inj->g_lp; z_lam = inj->z_lam; z_fa = inj->z_fa; z_f = inj->z_f; }
+        else {
+            // element ranges of the SITE_K_ADD stream: [2, 2+p) g_lp, [2+p, 2+2p) z_lambda, then z_Fa (r), z_F (n)
+            g_lp = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + s.p_off, 1);
+            z_lam = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + (long)s.p_total + s.p_off, 1);
+            z_fa = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * s.p_total, 1);
+            z_f = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * s.p_total + r, 1);
+        }
+        addk_traits_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(
+            pl, h, pri.Lambda_df, tauh[k], g_lp, z_lam, s.LP->p, s.LP->ld, s.Lam->p, s.Lam->ld, s.Lt ? s.Lt->p : nullptr,
+            s.Lt ? s.Lt->ld : 0, s.Plamt->p, s.Plamt->ld, s.px_mode ? 1.0 / sqrt(px_new) : 1.0);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        addk_fa_kernel<<<std::min(ceil_div(r, 256), d.sms * 4), 256, 0, d.st>>>(r, h, u_h2, z_fa, s.Fa->p, s.Fa->ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        addk_f_kernel<<<std::min(ceil_div(n, 256), d.sms * 4), 256, 0, d.st>>>(
+            n, r, h, u_h2, s.z1_identity ? nullptr : s.Z1, s.ldz1, s.Fa->p, s.Fa->ld, z_f, s.F->p, s.F->ld,
+            s.px_mode ? sqrt(px_new) : 1.0);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (s.px_mode) {
+            // px_factor[k] and, as BSFG_functions_px.R:328 does, Plam = Lambda_prec * tauh for ALL columns (no px division)
+            BSFG_CUDA(cudaMemcpyAsync(s.px + k, &px_new, sizeof(double), cudaMemcpyHostToDevice, d.st));
+            d.sync();
+            dim3 grid(ceil_div(pl, 32), ceil_div(k + 1, 32)), block(32, 8);
+            plam_kernel<<<grid, block, 0, d.st>>>(s.LP->p, s.LP->ld, pl, k + 1, s.tauh, s.Plamt->p, s.Plamt->ld);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+        *s.k = k + 1;
+        return true;
+    }
+    if (num > 0) {                                                           // drop redundant columns, R:342-359
+        std::vector<int> nonred;
+        for (int h = 0; h < k; h++) if (!vec[h]) nonred.push_back(h);
+        const int knew = (int)nonred.size();
+        if (knew < 2) fail(BSFG_ESHAPE, "update_k would leave %d factors; sample_delta needs >= 2", knew);
+        std::vector<double> delta(k);
+        BSFG_CUDA(cudaMemcpyAsync(delta.data(), s.delta, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
+        d.sync();
+        for (int red = 0; red < k; red++) {                                  // R:347-352
+            if (!vec[red]) continue;
+            if (red == k - 1) continue;
+            delta[red + 1] = delta[red + 1] * delta[red];
+        }
+        std::vector<double> dnew(knew), tnew(knew);
+        double cp = 1.0;
+        for (int q = 0; q < knew; q++) { dnew[q] = delta[nonred[q]]; cp *= dnew[q]; tnew[q] = cp; }
+        BSFG_CUDA(cudaMemcpyAsync(s.delta, dnew.data(), sizeof(double) * knew, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(s.tauh, tnew.data(), sizeof(double) * knew, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(s.d_map, nonred.data(), sizeof(int) * knew, cudaMemcpyHostToDevice, d.st));
+        d.sync();
+        auto cc = [&](DMat& A, int rows) {
+            compact_cols_kernel<<<std::min(ceil_div(std::max(rows, 1), 256), d.sms * 4), 256, 0, d.st>>>(A.p, A.ld, rows, knew, s.d_map);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        };
+        cc(*s.Lam, pl); cc(*s.LP, pl); cc(*s.F, n); cc(*s.Fa, r);
+        compact_cols_kernel<<<1, 32, 0, d.st>>>(s.F_h2, 1, 1, knew, s.d_map);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (s.px_mode) {
+            compact_cols_kernel<<<1, 32, 0, d.st>>>(s.px, 1, 1, knew, s.d_map);          // px_factor[nonred], :351
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+        if (s.Lt) {
+            compact_rows_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(s.Lt->p, s.Lt->ld, pl, knew, s.d_map);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+        *s.k = knew;
+        {
+            dim3 grid(ceil_div(pl, 32), ceil_div(knew, 32)), block(32, 8);
+            plam_kernel<<<grid, block, 0, d.st>>>(s.LP->p, s.LP->ld, pl, knew, s.tauh, s.Plamt->p, s.Plamt->ld);   // R:356
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+        return true;
+    }
+    return false;
+}
+
+// ---- update_k_c: the stateless drop-in of the R function (not Rcpp in the reference; SURVEY.md 8b lists it as a new export) ----
+extern "C" int bsfg_update_k_c(int n, int p, int r, int k, int k_max, long long i, const bsfg_priors* priors,
+                               const double* Z_1, double* Lambda, double* Lambda_prec, double* Plam, double* delta,
+                               double* tauh, double* F_h2, double* F, double* F_a, double* px_factor, double* F_px,
+                               const bsfg_variates* variates, unsigned long long seed, int* k_out) {
+    BSFG_API_BEGIN
+    REQUIRE_PTR(priors); REQUIRE_PTR(Lambda); REQUIRE_PTR(Lambda_prec); REQUIRE_PTR(Plam); REQUIRE_PTR(delta); REQUIRE_PTR(tauh);
+    REQUIRE_PTR(F_h2); REQUIRE_PTR(F); REQUIRE_PTR(F_a); REQUIRE_PTR(k_out);
+    if (n <= 0 || p <= 0 || r <= 0 || k < 1 || k_max < k) fail(BSFG_ESHAPE, "update_k: inconsistent sizes");
+    if (!Z_1 && r != n) fail(BSFG_ESHAPE, "update_k: Z_1 = NULL means the identity and requires r == n");
+    if ((px_factor == nullptr) != (F_px == nullptr)) fail(BSFG_EARG, "update_k: px_factor and F_px go together");
+    Device& d = default_device();
+    // in/out arrays have capacity k_max columns with leading dimension = rows; only the first k (then k_out) are meaningful
+    DMat Lam(p, k_max), LP(p, k_max), Plamt(k_max, p), Fm(n, k_max), Fa(r, k_max), Z1;
+    DVec h2(k_max), dl(k_max), th(k_max), px(k_max), cc(2 * (long)k_max);
+    int* d_map = nullptr;
+    BSFG_CUDA(cudaMalloc(&d_map, sizeof(int) * (size_t)k_max));
+    struct MapGuard { int* p; ~MapGuard() { cudaFree(p); } } guard{d_map};
+    auto up = [&](DMat& M, const double* host, long rows) {
+        BSFG_CUDA(cudaMemcpy2DAsync(M.p, M.ld * sizeof(double), host, rows * sizeof(double), rows * sizeof(double), k,
+                                    cudaMemcpyHostToDevice, d.st));
+    };
+    up(Lam, Lambda, p); up(LP, Lambda_prec, p); up(Fm, F, n); up(Fa, F_a, r);
+    BSFG_CUDA(cudaMemcpyAsync(h2.p, F_h2, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    BSFG_CUDA(cudaMemcpyAsync(dl.p, delta, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    BSFG_CUDA(cudaMemcpyAsync(th.p, tauh, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    DMat Fpx;
+    if (px_factor) {
+        BSFG_CUDA(cudaMemcpyAsync(px.p, px_factor, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+        Fpx.alloc(n, k_max);
+        up(Fpx, F_px, n);
+    }
+    if (Z_1) { Z1.alloc(n, r); Z1.upload(Z_1, d.st); }
+    {   // Plam stays as passed unless k changes (R returns current_state untouched then)
+        DMat Pl(p, k_max);
+        up(Pl, Plam, p);
+        DMat Plv; Plv.p = Pl.p; Plv.rows = p; Plv.cols = k; Plv.ld = Pl.ld;
+        DMat Ptv; Ptv.p = Plamt.p; Ptv.rows = k; Ptv.cols = p; Ptv.ld = Plamt.ld;
+        d.transpose(Plv, Ptv);
+        d.sync();
+    }
+    factor_reduce_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, Lam.p, Lam.ld, p, k, priors->epsilon, cc.p, cc.p + k_max);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+
+    const uint32_t ii = (uint32_t)i;
+    double uu;
+    if (variates && variates->u_k) uu = *variates->u_k;
+    else { RngStream rs{seed, SITE_U_K, ii}; uu = philox_uniform(rs, 0); }
+    KAddVariates ka;
+    DVec vk;
+    const bool have_add = variates && variates->k_g_lp && variates->k_g_delta && variates->k_z_lambda && variates->k_u_h2 &&
+                          variates->k_z_Fa && variates->k_z_F && (!px_factor || variates->k_g_px);
+    if (have_add) {
+        vk.alloc(2L * p + r + n);
+        BSFG_CUDA(cudaMemcpyAsync(vk.p, variates->k_g_lp, sizeof(double) * p, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(vk.p + p, variates->k_z_lambda, sizeof(double) * p, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(vk.p + 2L * p, variates->k_z_Fa, sizeof(double) * r, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(vk.p + 2L * p + r, variates->k_z_F, sizeof(double) * n, cudaMemcpyHostToDevice, d.st));
+        d.sync();
+        auto mk = [&](double* q) { VarSrc v = make_var(nullptr, 0, 0, 0, 0, 1); v.ptr = q; v.ld = 0; return v; };
+        ka.g_lp = mk(vk.p); ka.z_lam = mk(vk.p + p); ka.z_fa = mk(vk.p + 2L * p); ka.z_f = mk(vk.p + 2L * p + r);
+        ka.g_delta = *variates->k_g_delta; ka.u_h2 = *variates->k_u_h2; ka.g_px = px_factor ? *variates->k_g_px : 1.0;
+        ka.have_scalars = true;
+    }
+    int knew = k;
+    KRefs s;
+    s.d = &d; s.pri = priors; s.seed = seed;
+    s.n = n; s.pl = p; s.r = r; s.kmax = k_max; s.p_total = p; s.p_off = 0; s.k = &knew;
+    // The R functions hold the UNEXPANDED Lambda and F (the sweep's context stores Lambda_px / F_px instead, hence its
+    // px_mode multipliers); px_factor / F_px are handled below, as BSFG_functions_px.R:333-334, 351-352 do.
+    s.z1_identity = Z_1 == nullptr; s.px_mode = false;
+    s.Z1 = Z1.p; s.ldz1 = Z1.ld;
+    s.Lam = &Lam; s.LP = &LP; s.Lt = nullptr; s.Plamt = &Plamt; s.F = &Fm; s.Fa = &Fa;
+    s.F_h2 = h2.p; s.delta = dl.p; s.tauh = th.p; s.px = px.p;
+    s.cnt = cc.p + k_max; s.d_map = d_map;
+    const bool changed = update_k_apply(s, (long)i, uu, have_add ? &ka : nullptr);
+    if (changed && knew > k) {
+        // R recomputes Plam = sweep(Lambda_prec, 2, tauh, '*') over ALL columns in the add arm (R:337)
+        dim3 grid(ceil_div(p, 32), ceil_div(knew, 32)), block(32, 8);
+        plam_kernel<<<grid, block, 0, d.st>>>(LP.p, LP.ld, p, knew, th.p, Plamt.p, Plamt.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+    }
+    if (changed && px_factor) {
+        if (knew > k) {
+            double g_px;
+            if (have_add) g_px = *variates->k_g_px;
+            else { RngStream rs{seed, SITE_K_ADD, ii}; g_px = philox_gamma(rs, (uint64_t)1 << 40, priors->px_shape); }
+            const double pxv[2] = {g_px / priors->px_rate, sqrt(g_px / priors->px_rate)};
+            BSFG_CUDA(cudaMemcpyAsync(px.p + k, &pxv[0], sizeof(double), cudaMemcpyHostToDevice, d.st));
+            BSFG_CUDA(cudaMemcpyAsync(cc.p, &pxv[1], sizeof(double), cudaMemcpyHostToDevice, d.st));
+            d.sync();
+            DMat fin; fin.p = Fm.p + (long)k * Fm.ld; fin.rows = n; fin.cols = 1; fin.ld = Fm.ld;
+            DMat fout; fout.p = Fpx.p + (long)k * Fpx.ld; fout.rows = n; fout.cols = 1; fout.ld = Fpx.ld;
+            d.scale(fin, nullptr, cc.p, fout);                                  // F_px[,k] = F[,k] sqrt(px_factor[k])
+        } else {
+            compact_cols_kernel<<<std::min(ceil_div(n, 256), d.sms * 4), 256, 0, d.st>>>(Fpx.p, Fpx.ld, n, knew, d_map);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            compact_cols_kernel<<<1, 32, 0, d.st>>>(px.p, 1, 1, knew, d_map);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        }
+    }
+    if (changed) {
+        auto down = [&](const DMat& M, double* host, long rows) {
+            BSFG_CUDA(cudaMemcpy2DAsync(host, rows * sizeof(double), M.p, M.ld * sizeof(double), rows * sizeof(double), knew,
+                                        cudaMemcpyDeviceToHost, d.st));
+        };
+        DMat Pl(p, k_max);
+        DMat Plv; Plv.p = Pl.p; Plv.rows = p; Plv.cols = knew; Plv.ld = Pl.ld;
+        DMat Ptv; Ptv.p = Plamt.p; Ptv.rows = knew; Ptv.cols = p; Ptv.ld = Plamt.ld;
+        d.transpose(Ptv, Plv);
+        down(Lam, Lambda, p); down(LP, Lambda_prec, p); down(Pl, Plam, p); down(Fm, F, n); down(Fa, F_a, r);
+        BSFG_CUDA(cudaMemcpyAsync(F_h2, h2.p, sizeof(double) * knew, cudaMemcpyDeviceToHost, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(delta, dl.p, sizeof(double) * knew, cudaMemcpyDeviceToHost, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(tauh, th.p, sizeof(double) * knew, cudaMemcpyDeviceToHost, d.st));
+        if (px_factor) {
+            BSFG_CUDA(cudaMemcpyAsync(px_factor, px.p, sizeof(double) * knew, cudaMemcpyDeviceToHost, d.st));
+            down(Fpx, F_px, n);
+        }
+        d.sync();
+    }
+    d.sync();
+    *k_out = knew;
+    BSFG_API_END
+}
+
 // ---- sample_delta_c (BSFG_functions.R:272-308) ------------------------------------------------
 extern "C" int bsfg_sample_delta_c(const double* delta, const double* tauh, int k, const double* Lambda_prec, int p,
                                    double delta_1_shape, double delta_1_rate, double delta_2_shape,

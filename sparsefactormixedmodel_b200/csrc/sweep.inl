@@ -485,122 +485,18 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     phase_mark(c, 11);
 }
 
-// ---- update_k (BSFG_functions.R:311-372); host decides, device applies -----------------------
-struct KAddVariates { VarSrc g_lp, z_lam, z_fa, z_f; double g_delta, u_h2, g_px; bool have_scalars; };
-
+// ---- update_k (BSFG_functions.R:311-372) on a context: the shared implementation is update_k_apply (stateless.inl) ----
 static void update_k_step(bsfg_ctx* c, long i, double uu, const KAddVariates* inj) {
-    Device& d = c->dev;
-    const double prob = 1.0 / exp(c->pri.b0 + c->pri.b1 * (double)i);       // R:324
-    if (!(uu < prob && i > 200)) return;                                    // R:331
-    const int k = c->k, pl = c->pl, n = c->n, r = c->r;
-    std::vector<double> cnt(k);
-    BSFG_CUDA(cudaMemcpyAsync(cnt.data(), c->colsum_cnt.p + c->kmax, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
-    d.sync();
-    std::vector<int> vec(k);
-    int num = 0;
-    bool all_below = true;
-    for (int h = 0; h < k; h++) {
-        const double lind = cnt[h] / (double)c->p_total;                    // colMeans(abs(Lambda) < epsilon), R:326
-        vec[h] = lind >= c->pri.prop;
-        num += vec[h];
-        if (!(lind < 0.995)) all_below = false;
-    }
-    if (i > 20 && num == 0 && all_below && k < 2 * c->p_total) {            // add a column, R:332-341
-        if (k + 1 > c->kmax) fail(BSFG_ESHAPE, "update_k wants factor %d but k_max = %d", k + 1, c->kmax);
-        const int h = k;
-        RngStream rs{c->cfg.seed, SITE_K_ADD, (uint32_t)i};
-        double g_delta, u_h2, g_px = 1.0;
-        if (inj && inj->have_scalars) { g_delta = inj->g_delta; u_h2 = inj->u_h2; g_px = inj->g_px; }
-        else {
-            g_delta = philox_gamma(rs, 0, c->pri.delta_2_shape);
-            u_h2 = philox_uniform(rs, 1);
-            if (c->px_mode) g_px = philox_gamma(rs, (uint64_t)1 << 40, c->pri.px_shape);
-        }
-        const double px_new = c->px_mode ? g_px / c->pri.px_rate : 1.0;         // BSFG_functions_px.R:333
-        std::vector<double> delta(k + 1);
-        BSFG_CUDA(cudaMemcpyAsync(delta.data(), c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
-        d.sync();
-        delta[k] = g_delta / c->pri.delta_2_rate;                            // R:335
-        std::vector<double> tauh(k + 1);
-        double cp = 1.0;
-        for (int q = 0; q <= k; q++) { cp *= delta[q]; tauh[q] = cp; }
-        BSFG_CUDA(cudaMemcpyAsync(c->delta.p, delta.data(), sizeof(double) * (k + 1), cudaMemcpyHostToDevice, d.st));
-        BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, tauh.data(), sizeof(double) * (k + 1), cudaMemcpyHostToDevice, d.st));
-        BSFG_CUDA(cudaMemcpyAsync(c->F_h2.p + k, &u_h2, sizeof(double), cudaMemcpyHostToDevice, d.st));
-        d.sync();   // host vectors go out of scope
-        VarSrc g_lp, z_lam, z_fa, z_f;
-        if (inj) { g_lp = inj->g_lp; z_lam = inj->z_lam; z_fa = inj->z_fa; z_f = inj->z_f; }
-        else {
-            // element ranges of the SITE_K_ADD stream: [2, 2+p) g_lp, [2+p, 2+2p) z_lambda, then z_Fa (r), z_F (n)
-            g_lp = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + c->p_off, 1);
-            z_lam = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + (long)c->p_total + c->p_off, 1);
-            z_fa = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * c->p_total, 1);
-            z_f = make_var(nullptr, c->cfg.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * c->p_total + r, 1);
-        }
-        addk_traits_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(
-            pl, h, c->pri.Lambda_df, tauh[k], g_lp, z_lam, c->LP.p, c->LP.ld, c->Lam.p, c->Lam.ld, c->Lt.p, c->Lt.ld,
-            c->Plamt.p, c->Plamt.ld, c->px_mode ? 1.0 / sqrt(px_new) : 1.0);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        addk_fa_kernel<<<std::min(ceil_div(r, 256), d.sms * 4), 256, 0, d.st>>>(r, h, u_h2, z_fa, c->Fa.p, c->Fa.ld);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        addk_f_kernel<<<std::min(ceil_div(n, 256), d.sms * 4), 256, 0, d.st>>>(
-            n, r, h, u_h2, c->z1_identity ? nullptr : c->Z1.p, c->Z1.ld, c->Fa.p, c->Fa.ld, z_f, c->F.p, c->F.ld,
-            c->px_mode ? sqrt(px_new) : 1.0);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        if (c->px_mode) {
-            // px_factor[k] and, as BSFG_functions_px.R:328 does, Plam = Lambda_prec * tauh for ALL columns (no px division)
-            BSFG_CUDA(cudaMemcpyAsync(c->px.p + k, &px_new, sizeof(double), cudaMemcpyHostToDevice, d.st));
-            d.sync();
-            dim3 grid(ceil_div(pl, 32), ceil_div(k + 1, 32)), block(32, 8);
-            plam_kernel<<<grid, block, 0, d.st>>>(c->LP.p, c->LP.ld, pl, k + 1, c->tauh.p, c->Plamt.p, c->Plamt.ld);
-            BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        }
-        c->k = k + 1;
-        c->derived_valid = false;
-    } else if (num > 0) {                                                    // drop redundant columns, R:342-359
-        std::vector<int> nonred;
-        for (int h = 0; h < k; h++) if (!vec[h]) nonred.push_back(h);
-        const int knew = (int)nonred.size();
-        if (knew < 2) fail(BSFG_ESHAPE, "update_k would leave %d factors; sample_delta needs >= 2", knew);
-        std::vector<double> delta(k);
-        BSFG_CUDA(cudaMemcpyAsync(delta.data(), c->delta.p, sizeof(double) * k, cudaMemcpyDeviceToHost, d.st));
-        d.sync();
-        for (int red = 0; red < k; red++) {                                  // R:347-352
-            if (!vec[red]) continue;
-            if (red == k - 1) continue;
-            delta[red + 1] = delta[red + 1] * delta[red];
-        }
-        std::vector<double> dnew(knew), tnew(knew);
-        double cp = 1.0;
-        for (int q = 0; q < knew; q++) { dnew[q] = delta[nonred[q]]; cp *= dnew[q]; tnew[q] = cp; }
-        BSFG_CUDA(cudaMemcpyAsync(c->delta.p, dnew.data(), sizeof(double) * knew, cudaMemcpyHostToDevice, d.st));
-        BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, tnew.data(), sizeof(double) * knew, cudaMemcpyHostToDevice, d.st));
-        BSFG_CUDA(cudaMemcpyAsync(c->d_map, nonred.data(), sizeof(int) * knew, cudaMemcpyHostToDevice, d.st));
-        d.sync();
-        auto cc = [&](DMat& A, int rows) {
-            compact_cols_kernel<<<std::min(ceil_div(std::max(rows, 1), 256), d.sms * 4), 256, 0, d.st>>>(A.p, A.ld, rows, knew, c->d_map);
-            BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        };
-        cc(c->Lam, pl); cc(c->LP, pl); cc(c->F, n); cc(c->Fa, r);
-        {
-            DMat h2v = view_at(c->F_h2.p, 1, k, 1);
-            compact_cols_kernel<<<1, 32, 0, d.st>>>(h2v.p, 1, 1, knew, c->d_map);
-            BSFG_CHECK_LAUNCH(); g_launch_counter++;
-            if (c->px_mode) {
-                compact_cols_kernel<<<1, 32, 0, d.st>>>(c->px.p, 1, 1, knew, c->d_map);     // px_factor[nonred], :351
-                BSFG_CHECK_LAUNCH(); g_launch_counter++;
-            }
-        }
-        compact_rows_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(c->Lt.p, c->Lt.ld, pl, knew, c->d_map);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        c->k = knew;
-        {
-            dim3 grid(ceil_div(pl, 32), ceil_div(knew, 32)), block(32, 8);
-            plam_kernel<<<grid, block, 0, d.st>>>(c->LP.p, c->LP.ld, pl, knew, c->tauh.p, c->Plamt.p, c->Plamt.ld);   // R:356
-            BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        }
-        c->derived_valid = false;
-    }
+    KRefs s;
+    s.d = &c->dev; s.pri = &c->pri; s.seed = c->cfg.seed;
+    s.n = c->n; s.pl = c->pl; s.r = c->r; s.kmax = c->kmax; s.p_total = c->p_total; s.p_off = c->p_off; s.k = &c->k;
+    s.z1_identity = c->z1_identity; s.px_mode = c->px_mode;
+    s.Z1 = c->z1_identity ? nullptr : c->Z1.p; s.ldz1 = c->Z1.ld;
+    s.Lam = &c->Lam; s.LP = &c->LP; s.Lt = &c->Lt; s.Plamt = &c->Plamt; s.F = &c->F; s.Fa = &c->Fa;
+    s.F_h2 = c->F_h2.p; s.delta = c->delta.p; s.tauh = c->tauh.p; s.px = c->px.p;
+    s.cnt = c->colsum_cnt.p + c->kmax;        // reduced over ranks in step 11 of gibbs_iteration
+    s.d_map = c->d_map;
+    if (update_k_apply(s, i, uu, inj)) c->derived_valid = false;
 }
 
 static void require_ready(bsfg_ctx* c) {

@@ -115,18 +115,9 @@ class BSFGSweep:
         self._ctx = C.c_void_p()
         check(self.lib.bsfg_create(C.byref(cfg), C.byref(self._ctx)))
         # priors / run parameters
-        self._h2p = np.ascontiguousarray(np.asarray(priors["h2_priors_factors"], dtype=np.float64).ravel())
+        pr, self._h2p = _lib.make_priors(priors, run_parameters)
         if self._h2p.shape[0] != self.H:
             raise ValueError("h2_priors_factors must have h2_divisions entries")
-        bx = priors.get("b_X_prec", 1e-10)
-        bx = float(np.asarray(bx).ravel()[0]) if np.size(bx) else 1e-10
-        pr = _lib.bsfg_priors(priors["resid_Y_prec_shape"], priors["resid_Y_prec_rate"], priors["E_a_prec_shape"],
-                              priors["E_a_prec_rate"], priors["Lambda_df"], priors["delta_1_shape"],
-                              priors["delta_1_rate"], priors["delta_2_shape"], priors["delta_2_rate"], bx,
-                              ptr(self._h2p), run_parameters["b0"], run_parameters["b1"],
-                              run_parameters["epsilon"], run_parameters["prop"],
-                              priors.get("W_prec_shape", 2.0), priors.get("W_prec_rate", 0.1),
-                              priors.get("px_shape", 0.5), priors.get("px_rate", 0.5))
         check(self.lib.bsfg_set_priors(self._ctx, C.byref(pr)))
         # constants (this rank's trait columns of Y)
         l1 = run_variables["invert_aI_bZAZ"]; l2 = run_variables["invert_aPXA_bDesignDesignT"]

@@ -173,6 +173,77 @@ def sample_delta_c(delta, tauh, Lambda_prec, delta_1_shape, delta_1_rate, delta_
     return out
 
 
+def update_k_c(current_state, priors, run_parameters, data_matrices, *, variates=None, seed=0, k_max=None):
+    """Device version of the R-only `update_k(current_state, priors, run_parameters, data_matrices)`
+    (BSFG_functions.R:311-372); with `px_factor` and `F_px` in current_state, the variant of BSFG_functions_px.R:301-369.
+    Returns a copy of current_state with the factor-indexed members grown / shrunk and `k` set; `nrun` is the iteration
+    count i of R:323.  variates: dict with u_k and, for the add-a-factor arm, k_g_lp, k_g_delta, k_z_lambda, k_u_h2, k_z_Fa,
+    k_z_F (and k_g_px), or None for the device Philox streams of (seed, nrun)."""
+    lib = _lib.load()
+    cs = dict(current_state)
+    Lam = as_f(cs["Lambda"]); p, k = Lam.shape
+    F = as_f(cs["F"]); n = F.shape[0]
+    Fa = as_f(cs["F_a"]); r = Fa.shape[0]
+    kmax = int(k_max if k_max is not None else k + 1)
+    if kmax < k:
+        raise ValueError("k_max < k")
+
+    def grow(a, rows):
+        out = np.zeros((rows, kmax), order="F")
+        out[:, :k] = as_f(a, (rows, k))
+        return out
+
+    def growv(a):
+        out = np.zeros(kmax)
+        out[:k] = _vec(a, k)
+        return out
+
+    bufs = dict(Lambda=grow(Lam, p), Lambda_prec=grow(cs["Lambda_prec"], p), Plam=grow(cs["Plam"], p), F=grow(F, n), F_a=grow(Fa, r))
+    vecs = dict(delta=growv(cs["delta"]), tauh=growv(cs["tauh"]), F_h2=growv(cs["F_h2"]))
+    px = cs.get("px_factor") is not None
+    if px:
+        vecs["px_factor"] = growv(cs["px_factor"])
+        bufs["F_px"] = grow(cs["F_px"], n)
+    Z_1 = data_matrices["Z_1"]
+    Z = None if (Z_1 is None or (Z_1.shape[0] == Z_1.shape[1] and np.array_equal(Z_1, np.eye(Z_1.shape[0])))) else as_f(Z_1, (n, r))
+    pr, hold_p = _lib.make_priors(priors, run_parameters)
+    v = _lib.bsfg_variates()
+    hold = []
+    if variates is not None:
+        for name in ("u_k", "k_g_lp", "k_g_delta", "k_z_lambda", "k_u_h2", "k_z_Fa", "k_z_F", "k_g_px"):
+            if variates.get(name) is not None:
+                a = np.ascontiguousarray(np.asarray(variates[name], dtype=np.float64).ravel())
+                hold.append(a)
+                setattr(v, name, ptr(a))
+    k_out = C.c_int(0)
+    check(lib.bsfg_update_k_c(n, p, r, k, kmax, C.c_longlong(int(cs["nrun"])), C.byref(pr), ptr(Z), ptr(bufs["Lambda"]),
+                              ptr(bufs["Lambda_prec"]), ptr(bufs["Plam"]), ptr(vecs["delta"]), ptr(vecs["tauh"]),
+                              ptr(vecs["F_h2"]), ptr(bufs["F"]), ptr(bufs["F_a"]), ptr(vecs.get("px_factor")),
+                              ptr(bufs.get("F_px")), C.byref(v) if variates is not None else None, C.c_ulonglong(seed),
+                              C.byref(k_out)))
+    kn = k_out.value
+    for name, a in bufs.items():
+        cs[name] = np.asfortranarray(a[:, :kn])
+    for name, a in vecs.items():
+        cs[name] = a[:kn].copy()
+    cs["k"] = kn
+    return cs
+
+
+def GSVD_2_c(A, B):
+    """`GSVD_2_c(A, B)` (BSFG_functions_c.cpp:27-40): list U, V, X, C, S with A = U C X', B = V S X' (C, S diagonal
+    matrices like the reference returns them)."""
+    lib = _lib.load()
+    A = as_f(A); B = as_f(B)
+    n = B.shape[1]
+    if A.shape != (n, n) or B.shape != (n, n):
+        raise ValueError("GSVD_2_c: A and B must be square of the same size (as every call site of the reference has them)")
+    U = np.zeros((n, n), order="F"); V = np.zeros((n, n), order="F"); X = np.zeros((n, n), order="F")
+    c = np.zeros(n); s = np.zeros(n)
+    check(lib.bsfg_GSVD_2_c(ptr(A), ptr(B), n, ptr(U), ptr(V), ptr(X), ptr(c), ptr(s)))
+    return {"U": U, "V": V, "X": X, "C": np.diag(c), "S": np.diag(s)}
+
+
 def dgemm_tn(At, B, alpha=1.0, beta=0.0, C_in=None):
     """C = alpha * At' @ B + beta * C_in through the library's DMMA/TMA GEMM (test/bench hook)."""
     lib = _lib.load()

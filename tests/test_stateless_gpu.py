@@ -281,3 +281,123 @@ def test_device_rng_moments(pkg, small_problem):
     dmat = np.outer(L["s1"], cs["E_a_prec"]) + np.outer(L["s2"], cs["resid_Y_prec"])
     zhat = np.linalg.solve(L["U"], a - mean) * np.sqrt(dmat)
     assert abs(zhat.mean()) < 0.1 and abs(zhat.std() - 1.0) < 0.05
+
+
+# ---- update_k_c: the R-only update_k behind the same argument list (BSFG_functions.R:311-372) --------------------------------
+def _update_k_case(arm, px=False, rect_Z=False):
+    from oracle import init_oracle as I
+    n, p, k = 40, 30, 5
+    rng = np.random.default_rng(77 + len(arm))
+    r = 12 if rect_Z else n
+    Z = np.zeros((n, r)); Z[np.arange(n), rng.integers(0, r, n)] = 1.0
+    if not rect_Z:
+        Z = np.eye(n)
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    cs = dict(Lambda=rng.standard_normal((p, k)), Lambda_prec=rng.gamma(1.5, 1.0, (p, k)), F=rng.standard_normal((n, k)),
+              F_a=rng.standard_normal((r, k)), F_h2=rng.integers(0, 40, k) / 50.0, nrun=301)
+    if arm == "drop":                         # columns 1 and 3 (0-based) and the LAST one are redundant: R skips red == k
+        delta = np.array([1.5, 1.2, 1.1, 1.3, 1.2])
+        cs["Lambda"][:, [1, 3, 4]] *= 1e-6
+    else:
+        delta = np.array([1.5, 1.2, 1.1, 1.3, 1.2])
+    cs["delta"] = delta; cs["tauh"] = np.cumprod(delta)
+    cs["Plam"] = cs["Lambda_prec"] * cs["tauh"][None, :]
+    if px:
+        cs["px_factor"] = rng.gamma(2.0, 1.0, k) + 0.05
+        cs["F_px"] = cs["F"] * np.sqrt(cs["px_factor"])[None, :]
+    v = dict(u_k=np.array(0.9 if arm == "none" else 1e-6), k_g_lp=rng.gamma(pri["Lambda_df"] / 2, 1.0, p),
+             k_g_delta=np.array(rng.gamma(pri["delta_2_shape"], 1.0)), k_z_lambda=rng.standard_normal(p),
+             k_u_h2=np.array(rng.uniform()), k_z_Fa=rng.standard_normal(r), k_z_F=rng.standard_normal(n),
+             k_g_px=np.array(rng.gamma(pri["px_shape"], 1.0)))
+    return cs, pri, rp, dict(Z_1=Z), v
+
+
+@pytest.mark.parametrize("arm", ["add", "drop", "none"])
+@pytest.mark.parametrize("px", [False, True])
+@pytest.mark.parametrize("rect_Z", [False, True])
+def test_update_k_c(pkg, arm, px, rect_Z):
+    from oracle import bsfg_oracle as O
+    cs, pri, rp, dm, v = _update_k_case(arm, px, rect_Z)
+    k = cs["F"].shape[1]
+    args = (cs["F"], cs["Lambda"], cs["F_a"], cs["F_h2"], cs["Lambda_prec"], cs["Plam"], cs["delta"], cs["tauh"])
+    tail = (dm["Z_1"], pri["Lambda_df"], pri["delta_2_shape"], pri["delta_2_rate"])
+    sched = (rp["b0"], rp["b1"], cs["nrun"], rp["epsilon"], rp["prop"], v)
+    if px:
+        want = O.update_k_px(*args, cs["px_factor"], cs["F_px"], *tail, pri["px_shape"], pri["px_rate"], *sched)
+    else:
+        want = O.update_k(*args, *tail, *sched)
+    k2 = want["F"].shape[1]
+    assert {"add": k2 == k + 1, "drop": k2 == 2, "none": k2 == k}[arm], "oracle took another arm; test inputs need retuning"
+    got = pkg.update_k_c(cs, pri, rp, dm, variates=v, k_max=k + 2)
+    assert got["k"] == k2
+    for f in ("Lambda", "Lambda_prec", "Plam", "F", "F_a") + (("F_px",) if px else ()):
+        assert got[f].shape == want[f].shape, f
+        assert relerr(got[f], want[f]) < 1e-12, f
+    for f in ("delta", "tauh", "F_h2") + (("px_factor",) if px else ()):
+        assert relerr(got[f], np.asarray(want[f]).ravel()) < 1e-12, f
+    if arm == "none":                           # nothing is written: bit-identical pass-through
+        assert np.array_equal(got["Plam"], cs["Plam"]) and np.array_equal(got["F"], cs["F"])
+
+
+def test_update_k_c_philox_and_errors(pkg):
+    """NULL variates: the draws come from the (seed, nrun) Philox streams -- reproducible, seed dependent, and the iteration
+    gate i > 200 (R:331) holds whatever uu is.  A full k_max is an error, as in the sweep."""
+    cs, pri, rp, dm, v = _update_k_case("add")
+    k = cs["F"].shape[1]
+    early = pkg.update_k_c(dict(cs, nrun=150), pri, rp, dm, variates=dict(u_k=np.array(0.0)))
+    assert early["k"] == k
+    outs = [pkg.update_k_c(cs, pri, rp, dm, variates=dict(u_k=np.array(0.0)), seed=s) for s in (4, 4, 5)]
+    assert all(o["k"] == k + 1 for o in outs)
+    assert np.array_equal(outs[0]["Lambda"], outs[1]["Lambda"]) and np.array_equal(outs[0]["F"], outs[1]["F"])
+    assert not np.array_equal(outs[0]["Lambda"][:, k], outs[2]["Lambda"][:, k])
+    assert np.array_equal(outs[0]["Lambda"][:, :k], cs["Lambda"])
+    new = outs[0]
+    assert np.isfinite(new["Lambda"]).all() and 0.0 <= new["F_h2"][k] < 1.0 and new["delta"][k] > 0
+    assert relerr(new["Plam"], new["Lambda_prec"] * np.cumprod(new["delta"])[None, :]) < 1e-14
+    with pytest.raises(pkg.BSFGError):
+        pkg.update_k_c(cs, pri, rp, dm, variates=v, k_max=k)
+
+
+# ---- GSVD_2_c (cpp:27-40) ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 64, 301])
+def test_GSVD_2_c_contract(pkg, n):
+    """U, V are only unique up to signs (and rotations inside repeated singular values), so the check is the contract the
+    reference's callers rely on (fast_BSFG_sampler_init.R:289-325) plus the singular values against the oracle's."""
+    from oracle import init_oracle as I
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    B = rng.standard_normal((n, n)) + 3.0 * np.eye(n)
+    got = pkg.GSVD_2_c(A, B)
+    want = I.GSVD_2_c(A, B)
+    U, V, X, Cm, Sm = (got[f] for f in ("U", "V", "X", "C", "S"))
+    eye = np.eye(n)
+    assert np.abs(U.T @ U - eye).max() < 1e-11 and np.abs(V.T @ V - eye).max() < 1e-11
+    assert np.abs(Cm @ Cm + Sm @ Sm - eye).max() < 1e-13
+    sc = max(1.0, np.abs(A).max(), np.abs(B).max())
+    assert np.abs(U @ Cm @ X.T - A).max() < 1e-10 * sc
+    assert np.abs(V @ Sm @ X.T - B).max() < 1e-10 * sc
+    assert relerr(np.diag(Cm), np.diag(want["C"])) < 1e-10 and relerr(np.diag(Sm), np.diag(want["S"])) < 1e-10
+    c = np.diag(Cm)
+    assert np.all(np.diff(c) <= 1e-14)          # svd order: descending d, hence descending C
+
+
+def test_GSVD_2_c_gives_the_init_lists(pkg):
+    """The way the reference uses it (init:289-295): U = t(solve(X)), s1 = diag(C)^2, s2 = diag(S)^2 diagonalise both forms."""
+    from oracle import init_oracle as I
+    rng = np.random.default_rng(5)
+    n, r = 30, 12
+    Z = np.zeros((n, r)); Z[np.arange(n), np.arange(n) % r] = 1.0
+    G = rng.standard_normal((r, r)); Ainv = G @ G.T / r + np.eye(r)
+    ZZ = Z.T @ Z
+    res = pkg.GSVD_2_c(I.cholcov(ZZ), I.cholcov(Ainv))
+    U = np.linalg.inv(res["X"]).T
+    s1, s2 = np.diag(res["C"]) ** 2, np.diag(res["S"]) ** 2
+    assert np.abs(U.T @ ZZ @ U - np.diag(s1)).max() < 1e-9
+    assert np.abs(U.T @ Ainv @ U - np.diag(s2)).max() < 1e-9
+    a, b = 0.7, 2.3
+    assert relerr(U @ np.diag(1.0 / (a * s1 + b * s2)) @ U.T, np.linalg.inv(a * ZZ + b * Ainv)) < 1e-9
+
+
+def test_GSVD_2_c_singular_B_is_an_error(pkg):
+    with pytest.raises(pkg.BSFGError):
+        pkg.GSVD_2_c(np.eye(4), np.zeros((4, 4)))
