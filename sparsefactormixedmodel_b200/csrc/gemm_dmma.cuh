@@ -14,6 +14,9 @@
 // under the hardware swizzle (chunk' = chunk ^ (row & 7)), so fragment loads are conflict-free
 // LDS.64 with no padding and no repacking.
 //
+// The kernel is persistent: at most one CTA per SM walks the (tile, split) work items with a fixed stride, and the TMA
+// ring runs across items, so an item's epilogue stores overlap the first loads of the next one.
+//
 // Warp roles: 8 warps, each owning a 64 x 32 sub-tile of the 128 x 128 CTA tile (8 x 4 DMMA
 // accumulators = 64 FP64 values = 128 registers per thread).  Thread 0 also issues the TMA loads,
 // STAGES-1 k-tiles ahead (a 9th producer warp would round the CTA up to 384 threads for register
@@ -124,22 +127,28 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // tile coordinates: grouped rasterisation so co-resident CTAs share operand panels in L2
-    int tile = blockIdx.x;
-    const int split = blockIdx.y;
-    const int group_sz = g.group_n * g.tiles_m;
-    const int grp = tile / group_sz;
-    const int first_n = grp * g.group_n;
-    const int gn = min(g.group_n, g.tiles_n - first_n);
-    const int in_grp = tile - grp * group_sz;
-    const int tile_n = first_n + in_grp % gn;
-    const int tile_m = in_grp / gn;
-    const int m0 = tile_m * BM, n0 = tile_n * BN;
-
+    // Work items = (output tile, K split); a CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ... (persistent when the
+    // grid is smaller than the item count: one CTA per SM).  Tiles are numbered with a grouped rasterisation so the CTAs
+    // that run side by side share operand panels in L2.
+    const int tiles = g.tiles_m * g.tiles_n;
+    const int work_total = tiles * g.splits;
     const int total_ktiles = (g.K + GEMM_BK - 1) / GEMM_BK;
-    const int kt_begin = split * g.ktiles_per_split;
-    const int kt_end = min(total_ktiles, kt_begin + g.ktiles_per_split);
-    const int nkt = max(0, kt_end - kt_begin);
+    struct Item { int m0, n0, kt_begin, nkt, split; };
+    auto decode = [&](int w) {
+        Item it;
+        const int tile = w % tiles;
+        it.split = w / tiles;
+        const int group_sz = g.group_n * g.tiles_m;
+        const int grp = tile / group_sz;
+        const int first_n = grp * g.group_n;
+        const int gn = min(g.group_n, g.tiles_n - first_n);
+        const int in_grp = tile - grp * group_sz;
+        it.n0 = (first_n + in_grp % gn) * BN;
+        it.m0 = (in_grp / gn) * BM;
+        it.kt_begin = it.split * g.ktiles_per_split;
+        it.nkt = max(0, min(total_ktiles, it.kt_begin + g.ktiles_per_split) - it.kt_begin);
+        return it;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -156,12 +165,6 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int wm0 = (warp % WM) * (FM * 8);
     const int wn0 = (warp / WM) * (FN * 8);
 
-    double acc[FM][FN][2];
-#pragma unroll
-    for (int i = 0; i < FM; i++)
-#pragma unroll
-        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
     // byte offset inside a 128-byte row for k-step j: chunk = j + 4*(q>>1), swizzled by (row&7)==gq
     uint32_t koff[4];
 #pragma unroll
@@ -170,98 +173,131 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t a_row = (uint32_t)((wm0 + gq) * 128);
     const uint32_t b_row = (uint32_t)(S::A_BYTES + (wn0 + gq) * 128);
 
-    // TMA issue is folded into consumer warp 0 (lane 0): it runs STAGES-1 k-tiles ahead of the math.
-    auto issue = [&](int nx) {
-        const int s2 = nx % STAGES;
-        mbar_wait(&empty_bar[s2], ((nx / STAGES) & 1) ^ 1);   // passes immediately on first use of a slot
+    // TMA issue is folded into consumer warp 0 (lane 0): it runs STAGES-1 k-tiles ahead of the math, ACROSS work items --
+    // the first k-tiles of the next item are requested before this item's epilogue, so its stores overlap their flight.
+    // ring_put / ring_get count k-tiles over the CTA's whole life; slot = count % STAGES, phase = (count / STAGES) & 1.
+    uint32_t ring_put = 0, ring_get = 0;
+    auto issue = [&](const Item& w, int kt) {
+        const int s2 = ring_put % STAGES;
+        mbar_wait(&empty_bar[s2], ((ring_put / STAGES) & 1) ^ 1);   // passes immediately on first use of a slot
         mbar_expect_tx(&full_bar[s2], S::STAGE_BYTES);
         uint8_t* sa = smem + s2 * S::STAGE_BYTES;
-        const int kc = (kt_begin + nx) * GEMM_BK;
-        tma_load_2d(sa, &tmA, &full_bar[s2], kc, m0);
-        tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s2], kc, n0);
+        const int kc = (w.kt_begin + kt) * GEMM_BK;
+        tma_load_2d(sa, &tmA, &full_bar[s2], kc, w.m0);
+        tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s2], kc, w.n0);
+        ring_put++;
     };
+    int w = blockIdx.x;
+    if (w >= work_total) return;
+    Item cur = decode(w);
+    int issued = 0;                // k-tiles of `cur` already requested (thread 0 only)
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int nx = 0; nx < STAGES - 1 && nx < nkt; nx++) issue(nx);
+        for (; issued < STAGES - 1 && issued < cur.nkt; issued++) issue(cur, issued);
     }
     __syncwarp();
 
-    for (int it = 0; it < nkt; it++) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        if (threadIdx.x == 0 && it + STAGES - 1 < nkt) issue(it + STAGES - 1);
-        __syncwarp();
-        mbar_wait(&full_bar[s], ph);
-        const uint32_t sbase = smem_base + s * S::STAGE_BYTES;
+    for (;;) {
+        double acc[FM][FN][2];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double a[FM], b[FN];
+        for (int i = 0; i < FM; i++)
 #pragma unroll
-            for (int i = 0; i < FM; i++) a[i] = lds_f64(sbase + a_row + i * 8 * 128 + koff[j]);
-#pragma unroll
-            for (int i = 0; i < FN; i++) b[i] = lds_f64(sbase + b_row + i * 8 * 128 + koff[j]);
-            // fragments beyond the matrix edge multiply TMA zero fill: skipping them (predicated DMMAs) was measured
-            // slower than issuing them, because the other warps of the CTA do the full work anyway
-#pragma unroll
-            for (int i = 0; i < FM; i++)
-#pragma unroll
-                for (int jj = 0; jj < FN; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
+            for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // ===================== epilogue =====================
-    // thread owns C[m0+wm0+8i+gq][n0+wn0+8j+2q+{0,1}]
-    if (g.splits > 1) {
-        double* ws = g.ws + (size_t)split * (size_t)g.M * (size_t)g.N;
+        for (int it = 0; it < cur.nkt; it++) {
+            const int s = ring_get % STAGES;
+            const uint32_t ph = (ring_get / STAGES) & 1;
+            if (threadIdx.x == 0 && issued < cur.nkt) { issue(cur, issued); issued++; }
+            __syncwarp();
+            mbar_wait(&full_bar[s], ph);
+            const uint32_t sbase = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < FM; i++) {
-            const int m = m0 + wm0 + 8 * i + gq;
-            if (m >= g.M) continue;
+            for (int j = 0; j < 4; j++) {
+                double a[FM], b[FN];
 #pragma unroll
-            for (int j = 0; j < FN; j++) {
+                for (int i = 0; i < FM; i++) a[i] = lds_f64(sbase + a_row + i * 8 * 128 + koff[j]);
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int n = n0 + wn0 + 8 * j + 2 * q + c;
-                    if (n < g.N) ws[(size_t)n * g.M + m] = acc[i][j][c];
-                }
+                for (int i = 0; i < FN; i++) b[i] = lds_f64(sbase + b_row + i * 8 * 128 + koff[j]);
+                // fragments beyond the matrix edge multiply TMA zero fill: skipping them (predicated DMMAs) was measured
+                // slower than issuing them, because the other warps of the CTA do the full work anyway
+#pragma unroll
+                for (int i = 0; i < FM; i++)
+#pragma unroll
+                    for (int jj = 0; jj < FN; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            ring_get++;
+        }
+
+        // next item: request its first k-tiles now (the slots free up as the other warps leave the loop above)
+        const int wn = w + (int)gridDim.x;
+        const bool more = wn < work_total;
+        if (threadIdx.x == 0) {
+            issued = 0;
+            if (more) {
+                const Item nxt = decode(wn);
+                for (; issued < STAGES - 1 && issued < nxt.nkt; issued++) issue(nxt, issued);
             }
         }
-        return;
-    }
-    // beta != 0: the 16 Cin values of one 8-column fragment strip are loaded as one batch before any of them is
-    // used, so 16 independent 8-byte loads per thread are in flight (a load->FMA->store chain per element made the
-    // K = k products, which are all epilogue, 2.5x slower).
-#pragma unroll
-    for (int j = 0; j < FN; j++) {
-        double cin[FM][2];
-        if (g.Cin) {
+        __syncwarp();
+
+        // ===================== epilogue =====================
+        // thread owns C[m0+wm0+8i+gq][n0+wn0+8j+2q+{0,1}]
+        const int m0 = cur.m0, n0 = cur.n0;
+        if (g.splits > 1) {
+            double* ws = g.ws + (size_t)cur.split * (size_t)g.M * (size_t)g.N;
 #pragma unroll
             for (int i = 0; i < FM; i++) {
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int m = m0 + wm0 + 8 * i + gq;
-                    const int n = n0 + wn0 + 8 * j + 2 * q + c;
-                    cin[i][c] = (m < g.M && n < g.N)
-                                    ? g.Cin[g.trans_out ? (size_t)m * g.ldcin + n : (size_t)n * g.ldcin + m] : 0.0;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < FM; i++) {
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
                 const int m = m0 + wm0 + 8 * i + gq;
-                const int n = n0 + wn0 + 8 * j + 2 * q + c;
-                if (m < g.M && n < g.N) {
-                    double v = g.alpha * acc[i][j][c];
-                    if (g.Cin) v += g.beta * cin[i][c];
-                    g.C[g.trans_out ? (size_t)m * g.ldc + n : (size_t)n * g.ldc + m] = v;
+                if (m >= g.M) continue;
+#pragma unroll
+                for (int j = 0; j < FN; j++) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int n = n0 + wn0 + 8 * j + 2 * q + c;
+                        if (n < g.N) ws[(size_t)n * g.M + m] = acc[i][j][c];
+                    }
+                }
+            }
+        } else {
+            // beta != 0: the 16 Cin values of one 8-column fragment strip are loaded as one batch before any of them is
+            // used, so 16 independent 8-byte loads per thread are in flight (a load->FMA->store chain per element made the
+            // K = k products, which are all epilogue, 2.5x slower).
+#pragma unroll
+            for (int j = 0; j < FN; j++) {
+                double cin[FM][2];
+                if (g.Cin) {
+#pragma unroll
+                    for (int i = 0; i < FM; i++) {
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            const int m = m0 + wm0 + 8 * i + gq;
+                            const int n = n0 + wn0 + 8 * j + 2 * q + c;
+                            cin[i][c] = (m < g.M && n < g.N)
+                                            ? g.Cin[g.trans_out ? (size_t)m * g.ldcin + n : (size_t)n * g.ldcin + m] : 0.0;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < FM; i++) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int m = m0 + wm0 + 8 * i + gq;
+                        const int n = n0 + wn0 + 8 * j + 2 * q + c;
+                        if (m < g.M && n < g.N) {
+                            double v = g.alpha * acc[i][j][c];
+                            if (g.Cin) v += g.beta * cin[i][c];
+                            g.C[g.trans_out ? (size_t)m * g.ldc + n : (size_t)n * g.ldc + m] = v;
+                        }
+                    }
                 }
             }
         }
+        if (!more) break;
+        w = wn;
+        cur = decode(w);       // re-derived after the epilogue rather than kept live across it (register budget)
     }
 }
 

@@ -99,7 +99,10 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     splits = ceil_div(ktiles, g.ktiles_per_split);    // no empty splits
     g.splits = splits;
     g.ws = ws;
-    dim3 grid(tiles, splits);
+    // persistent launch: one CTA per SM walks the (tile, split) items; BSFG_GEMM_PERSISTENT=0 launches one CTA per item
+    static const bool persistent = [] { const char* e = getenv("BSFG_GEMM_PERSISTENT"); return !e || atoi(e) != 0; }();
+    const long items = (long)tiles * splits;
+    dim3 grid((unsigned)(persistent ? std::min<long>(items, sm_count) : items));
     switch (BM) {
         case 32: launch_gemm<32>(st, tmA, tmB, g, grid); break;
         case 64: launch_gemm<64>(st, tmA, tmB, g, grid); break;
