@@ -20,7 +20,9 @@
 //           the 8x8 diagonal tile redundantly in registers (36 values; no shuffles, no extra barrier) and applies the
 //           8-step forward substitution to its own row of the panel below; the 8 owners also store the INVERSE of the
 //           factored diagonal block (used by the backward solve).
-// 2 barriers per block column.  The right-hand side m rides along as an extra matrix row k (with a huge diagonal), so
+// 2 barriers per block column.  (Factoring the tile in its 8 owner threads only and letting the panel rows multiply by
+// the shared inverse removes 40% of the kernel's instructions but needs a third barrier per column: measured SLOWER on
+// B200, Lambda-Cholesky phase 2.53 -> 2.73 ms at C4 -- the kernel is barrier/latency bound, not issue bound.)  The right-hand side m rides along as an extra matrix row k (with a huge diagonal), so
 // the forward solve v = L^-1 m costs nothing: v' is row k of the factor.  The backward solve L'x = v + z runs on ONE
 // warp without block barriers: x_J = inv(L_JJ)' w_J is an 8x8 mat-vec (no 8-step dependency chain), followed by an
 // 8-FMA update of the earlier rows.  (ncu on the first version: ~40% of the stall samples sat on the barriers of the
