@@ -27,14 +27,51 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_reference_export_names_are_mirrored():
-    """The eight Rcpp exports of BSFG_functions_c.cpp (lines 26,42,85,137,165,195,240,292) minus the
-    init-only GSVD_2_c, plus the north-star spellings."""
+    """The eight Rcpp exports of BSFG_functions_c.cpp (lines 26,42,85,137,165,195,240,292), the north-star spellings, and
+    the device versions of the two R-only steps."""
     import sparsefactormixedmodel_b200 as pkg
-    for name in ("sample_means_c", "sample_Lambda_c", "sample_lambda_c", "sample_factors_scores_c",
+    for name in ("GSVD_2_c", "sample_means_c", "sample_Lambda_c", "sample_lambda_c", "sample_factors_scores_c",
                  "sample_px_factors_scores_c", "sample_h2s_discrete_c",
-                 "sample_prec_discrete_conditional_c", "sample_F_a_c", "sample_delta_c",
+                 "sample_prec_discrete_conditional_c", "sample_F_a_c", "sample_delta_c", "update_k_c",
                  "fast_BSFG_sampler"):
         assert callable(getattr(pkg, name))
+
+
+def test_r_glue_binds_every_reference_export():
+    """r/bsfg_b200.R defines a closure under each Rcpp export name, and every .Call target exists in r/bsfg_glue.c (no R
+    in this container: a text-level check that the two files and the header stay in step)."""
+    rsrc = open(os.path.join(ROOT, "r", "bsfg_b200.R")).read()
+    csrc = open(os.path.join(ROOT, "r", "bsfg_glue.c")).read()
+    for name in ("GSVD_2_c", "sample_means_c", "sample_Lambda_c", "sample_lambda_c", "sample_factors_scores_c",
+                 "sample_px_factors_scores_c", "sample_h2s_discrete_c", "sample_prec_discrete_conditional_c",
+                 "sample_F_a_c", "sample_delta_c", "update_k_c", "bsfg_sweep_loop"):
+        assert re.search(r"^%s\s*<-\s*(function|sample_Lambda_c$)" % re.escape(name), rsrc, flags=re.M), name
+    targets = set(re.findall(r"\.Call\('(R_bsfg_[A-Za-z0-9_]+)'", rsrc))
+    assert targets
+    for t in targets:
+        assert re.search(r"^SEXP %s\(" % re.escape(t), csrc, flags=re.M), f"{t} is .Call'ed but not defined in bsfg_glue.c"
+    # argument counts: every .Call('R_x', a, b, ...) passes as many arguments as `SEXP R_x(SEXP ..., ...)` takes
+    def top_level_args(text, start):
+        depth, n, i = 0, 1, start
+        while True:
+            ch = text[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                if depth == 0:
+                    return n
+                depth -= 1
+            elif ch == "," and depth == 0:
+                n += 1
+            i += 1
+    for m in re.finditer(r"\.Call\('(R_bsfg_[A-Za-z0-9_]+)'", rsrc):
+        n_call = top_level_args(rsrc, m.end()) - 1                       # minus the symbol name itself
+        d = re.search(r"^SEXP %s\(([^)]*)\)" % re.escape(m.group(1)), csrc, flags=re.M)
+        n_def = len([a for a in d.group(1).split(",") if a.strip() and a.strip() != "void"])
+        assert n_call == n_def, f"{m.group(1)}: .Call passes {n_call} arguments, the C definition takes {n_def}"
+    declared = set(_declared_symbols())
+    for sym in set(re.findall(r"\b(bsfg_[A-Za-z0-9_]+)\s*\(", csrc)):
+        assert sym in declared, f"bsfg_glue.c calls {sym}, which include/bsfg_b200.h does not declare"
 
 
 def test_no_cpu_fallback_without_gpu():
