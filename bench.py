@@ -570,6 +570,7 @@ def run_reference(args):
             "metric": "Gibbs iter/sec at n=5000,p=20000,k=100 (1/2/4/8 B200) vs Rcpp host" if args.workload == "C4"
                       else f"Gibbs iter/sec at n={n},p={p},k={k}",
             "value": cb["value"], "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "steps_timed": steps,      # each a full iteration on the trait sample (best of them is reported), bounded so the arm ends in minutes
             "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: n={n} individuals, p={p} traits, k={k} factors, b=1, Z_1=I, r=n, H=50"},
