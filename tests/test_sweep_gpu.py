@@ -228,22 +228,34 @@ def test_sweep_fixed_lambda(b, with_z2):
         sw.close()
 
 
-def test_device_posterior_matches_host_bookkeeping():
+@pytest.mark.parametrize("adapt", [False, True])
+def test_device_posterior_matches_host_bookkeeping(adapt):
     """bsfg_sweep_collect keeps save_posterior_samples (BSFG_functions.R:375-408) on the device: same chain (same seed),
     samples pulled with get_state at every thinning boundary on the host vs collected on the device must be identical
-    for the traces and agree to rounding for the running means (B, E_a go through the mean of theta)."""
+    for the traces and agree to rounding for the running means (B, E_a go through the mean of theta).
+    adapt: the chain starts at nrun = 300 from a state with two crushed loading columns, so update_k drops and adds
+    factors between the samples -- the traces keep k_max columns per sample, zero beyond that sample's k (the
+    reference grows the rows of Posterior$Lambda / F / F_a instead, BSFG_functions.R:383-392)."""
     from oracle import init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 40, 30, 5
     st = _build(n, p, k, "stable", seed=17)
     d, rv, pri, rp, cs = (st["data_matrices"], st["run_variables"], st["priors"], st["run_parameters"], st["current_state"])
-    burn, thin, iters = 3, 2, 11                    # samples at i = 5, 7, 9, 11
-    a = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, seed=5)
-    bsw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, seed=5)
+    if adapt:
+        cs = dict(cs)
+        cs["delta"] = np.array([1.5, 1.2, 1.1, 1e12, 1.2]); cs["tauh"] = np.cumprod(cs["delta"])
+        cs["Plam"] = cs["Lambda_prec"] * cs["tauh"][None, :]
+        cs["nrun"] = 300
+        rp = dict(rp, b0=-5.0)                      # prob = 1/exp(b0 + b1 i) > 1: update_k acts every iteration (R:324, 331)
+    i0 = int(cs.get("nrun", 0))
+    KM = 16 if adapt else 8
+    burn, thin, iters = i0 + 3, 2, 11               # samples at i = i0 + 5, 7, 9, 11 (the schedule counts absolute iterations)
+    a = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=KM, seed=5)
+    bsw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=KM, seed=5)
     try:
         a.set_state(cs); bsw.set_state(cs)
         host = []
-        a.sweep(burn + thin)
+        a.sweep(burn - i0 + thin)
         for s in range(4):
             host.append(a.get_state())
             if s < 3:
@@ -251,11 +263,11 @@ def test_device_posterior_matches_host_bookkeeping():
         bsw.posterior_begin(8)
         bsw.collect(iters, burn, thin)
         post = bsw.posterior()
-        assert list(post["sp_num"]) == [1, 2, 3, 4] and post["k_max"] == 8
+        assert list(post["sp_num"]) == [1, 2, 3, 4] and post["k_max"] == KM
         for s, hs in enumerate(host):
             kk = hs["F"].shape[1]
             for name, rows in (("Lambda", p), ("F", n), ("F_a", n)):
-                got = post[name][:, s].reshape(rows, 8, order="F")
+                got = post[name][:, s].reshape(rows, KM, order="F")
                 assert np.array_equal(got[:, :kk], hs[name]) and not got[:, kk:].any()
             assert np.array_equal(post["delta"][:kk, s], hs["delta"]) and np.array_equal(post["F_h2"][:kk, s], hs["F_h2"])
             assert np.array_equal(post["resid_Y_prec"][:, s], hs["resid_Y_prec"])
@@ -266,6 +278,9 @@ def test_device_posterior_matches_host_bookkeeping():
         assert relerr(post["B"], Bm) < 1e-12 and relerr(post["E_a"], Em) < 1e-12
         # both chains ended in the same state
         assert np.array_equal(bsw.get_state()["F"], a.get_state()["F"])
+        if adapt:
+            ks = [hs["F"].shape[1] for hs in host]
+            assert len(set(ks)) > 1 or ks[0] != k, f"update_k never changed k ({ks}); test inputs need retuning"
     finally:
         a.close(); bsw.close()
 
