@@ -428,7 +428,7 @@ def fast_BSFG_sampler(BSFG_state, n_samples, *, seed=None, sweep=None):
                 cur = post[name]
                 prev = Posterior.get(name)
                 if prev is None or np.shape(prev) != cur.shape or first == 1:
-                    Posterior[name] = cur if first == 1 else cur
+                    Posterior[name] = cur
                 else:
                     # the device mean was started at sample `first` with the reference's recursion seeded by zero, i.e. it
                     # equals (sum of this call's samples) / last; add the earlier samples' share

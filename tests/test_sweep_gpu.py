@@ -601,3 +601,30 @@ def test_fast_BSFG_sampler_contract():
     assert np.array_equal(one["current_state"]["F"], out2["current_state"]["F"])
     assert relerr(out2["Posterior"]["E_a"], one["Posterior"]["E_a"]) < 1e-12
     assert relerr(out2["Posterior"]["B"], one["Posterior"]["B"]) < 1e-12
+
+
+def test_fast_BSFG_sampler_continuation_with_changing_k():
+    """The same continuation property while update_k is live (nrun > 200, prob forced above 1): 5 + 4 iterations in two
+    calls == 9 in one, with Posterior$Lambda / F / F_a growing rows to the largest k seen (BSFG_functions.R:383-392)."""
+    from sparsefactormixedmodel_b200 import fast_BSFG_sampler
+    n, p, k = 40, 30, 5
+    st = _build(n, p, k, "stable", seed=17)
+    st["run_parameters"].update(burn=300, thin=2, b0=-5.0)
+    cs = st["current_state"]
+    cs["delta"] = np.array([1.5, 1.2, 1.1, 1e12, 1.2]); cs["tauh"] = np.cumprod(cs["delta"])
+    cs["Plam"] = cs["Lambda_prec"] * cs["tauh"][None, :]
+    cs["nrun"] = 300
+    one = fast_BSFG_sampler(st, 9, seed=3)
+    a = fast_BSFG_sampler(st, 5, seed=3)
+    b = fast_BSFG_sampler(a, 4, seed=3)
+    k_end = one["current_state"]["F"].shape[1]
+    assert k_end != k and b["current_state"]["F"].shape[1] == k_end
+    assert np.array_equal(one["current_state"]["F"], b["current_state"]["F"])
+    assert np.array_equal(one["current_state"]["Lambda"], b["current_state"]["Lambda"])
+    for name in ("Lambda", "F", "F_a", "delta", "F_h2", "resid_Y_prec", "E_a_prec"):
+        assert one["Posterior"][name].shape == b["Posterior"][name].shape, name
+        assert np.array_equal(one["Posterior"][name], b["Posterior"][name]), name
+    assert one["Posterior"]["Lambda"].shape[1] == 4                      # i = 302, 304, 306, 308
+    rows = one["Posterior"]["Lambda"].shape[0]                          # p x the largest k among the SAMPLED iterations
+    assert rows % p == 0 and k < rows // p <= k_end
+    assert relerr(b["Posterior"]["E_a"], one["Posterior"]["E_a"]) < 1e-12
