@@ -11,6 +11,7 @@ Checks, on every rank:
      ranks, and the N-rank chain equals the 1-rank chain (run on rank 0) to 1e-10 -- the Philox element index
      of every trait-indexed draw is the global trait index, so sharding must not change the chain beyond the
      summation order of the allreduce.
+  3. the same injected-variate check for the Z_2 + missing-data sweep and for the parameter-expanded sweep.
 Prints "multi_gpu_check ok world=N" from rank 0 and exits 0; any mismatch raises.
 """
 import os
@@ -125,6 +126,40 @@ def main():
     sw.close()
     if rank == 0:
         print(f"multi_gpu_check ok (Z_2 + missing data) world={world}", flush=True)
+    # ---- third scenario: parameter-expanded sweep (fast_BSFG_sampler_px.R) under trait sharding --------------------------
+    # Opt-in (BSFG_MG_CHECK_PX=1): written at the end of round 1 and NOT yet run on hardware (GPU budget); the px sweep is
+    # parity-tested on one GPU only (tests/test_sweep_gpu.py::test_sweep_parameter_expanded).
+    if os.environ.get("BSFG_MG_CHECK_PX", "0") != "1":
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    n, p, k = 70, 45, 5
+    rs = np.random.default_rng(202)
+    setup = I.make_synthetic(n, p, 3, pedigree="halfsib", seed=29)
+    pri = I.default_priors(k_init=k)
+    st = I.sampler_init(setup, pri, rp, seed=11, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    ora = dict(cs)
+    ora["px_factor"] = rs.gamma(pri["px_shape"], 1.0, k) / pri["px_rate"] + 0.05
+    ora["F_px"] = ora["F"] * np.sqrt(ora["px_factor"])[None, :]
+    nccl_id = bcast(BSFGSweep.nccl_unique_id() if rank == 0 else None)
+    sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=8, seed=7, rank=rank, world=world, nccl_id=nccl_id)
+    lo, hi = sw.lo, sw.hi
+    for it in range(1, 4):
+        v = I.draw_variates(rs, n, p, k, n, 1 + n, pri, px=True)
+        sw.set_state(ora)
+        ora, _ = O.gibbs_iteration_px(d, rv, pri, rp, ora, it, v)
+        sw.sweep_injected(v)
+        dev = sw.get_state()
+        assert rowwise_relerr(dev["Lambda"], ora["Lambda"][lo:hi]) < tol
+        assert rowwise_relerr(dev["F_px"], ora["F_px"]) < tol and rowwise_relerr(dev["F"], ora["F"]) < tol
+        assert relerr(dev["px_factor"], ora["px_factor"]) < tol
+        assert relerr(dev["Plam"], ora["Plam"][lo:hi]) < tol * 10
+        assert relerr(dev["resid_Y_prec"], ora["resid_Y_prec"][lo:hi]) < tol
+        assert relerr(dev["delta"], ora["delta"]) < tol
+    sw.close()
+    if rank == 0:
+        print(f"multi_gpu_check ok (parameter-expanded sweep) world={world}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -33,3 +33,4 @@ def test_trait_sharded_sweep_matches_oracle_and_single_gpu():
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"multi_gpu_check ok world={world}" in out.stdout
+    assert f"multi_gpu_check ok (Z_2 + missing data) world={world}" in out.stdout
