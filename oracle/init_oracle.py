@@ -232,7 +232,7 @@ def make_synthetic(n, p, k_true, seed=20131, pedigree="random", b=1):
     Lambda = np.zeros((p, k_true))
     lo, hi = max(1, p // 30), max(2, p // 4)
     for h in range(k_true):
-        numeff = int(rng.integers(lo, hi + 1))
+        numeff = min(p, int(rng.integers(lo, hi + 1)))
         rows = rng.choice(p, size=numeff, replace=False)
         Lambda[rows, h] = rng.standard_normal(numeff)
     L_A = np.linalg.cholesky(A)

@@ -166,6 +166,45 @@ def test_twins_agree_on_reference_fixtures(name):
     assert np.array_equal(fin, np.isfinite(b)) and relerr(a[fin], b[fin]) < tol
 
 
+@pytest.mark.parametrize("n,p,k,b,pedigree,rect", [(20, 1, 2, 1, "halfsib", False), (30, 13, 7, 0, "random", False),
+                                                    (24, 9, 3, 2, "random", True), (40, 17, 5, 1, "halfsib", True)])
+def test_twins_agree_on_random_problems(n, p, k, b, pedigree, rect):
+    """The same twin agreement away from the fixtures: p = 1, k = 2, b = 0 and b = 2, a random pedigree (n distinct
+    eigenvalues) and a rectangular incidence matrix Z_1 (r < n), all functions chained like one sweep."""
+    from oracle import bsfg_oracle as O, bsfg_oracle_rtwin as R, init_oracle as I
+    rng = np.random.default_rng(1000 + n + p)
+    setup = I.make_synthetic(n, p, max(2, k // 2), pedigree=pedigree, seed=n + p, b=b)
+    if b == 0:
+        setup["X"] = np.zeros((n, 0))
+    if rect:                                            # two records per line: r = n / 2 random-effect levels
+        r = n // 2
+        Z = np.zeros((n, r)); Z[np.arange(n), np.arange(n) % r] = 1.0
+        setup["Z_1"] = Z; setup["A"] = setup["A"][:r, :r]; setup["r"] = r
+    pri = I.default_priors(k_init=k); rp = I.default_run_parameters()
+    st = I.sampler_init(setup, pri, rp, seed=3, lists="stable")
+    d, rv, pri, cs = st["data_matrices"], st["run_variables"], st["priors"], st["current_state"]
+    Y, X, Z = d["Y"], d["X"], d["Z_1"]
+    r = Z.shape[1]
+    v = I.draw_variates(rng, n, p, k, r, b + r, pri)
+    H = rp["h2_divisions"]
+    tol = 1e-9
+    B = np.asarray(cs["B"]).reshape(b, p)
+    Yt = Y - X @ B
+    Lam = O.sample_Lambda_c(Yt, cs["F"], cs["resid_Y_prec"], cs["E_a_prec"], cs["Plam"], rv["invert_aI_bZAZ"], v["z_Lambda"])
+    assert rowwise_relerr(Lam, R.sample_Lambda(Yt, cs["F"], cs["resid_Y_prec"], cs["E_a_prec"], cs["Plam"], rv["invert_aI_bZAZ"],
+                                               v["z_Lambda"])) < tol
+    Yt = Y - cs["F"] @ Lam.T
+    loc = O.sample_means_c(Yt, cs["resid_Y_prec"], cs["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    assert relerr(loc, R.sample_means(Yt, cs["resid_Y_prec"], cs["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])) < tol
+    h2 = O.sample_h2s_discrete_c(cs["F"], H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"])
+    assert np.array_equal(h2, R.sample_h2s_discrete(cs["F"], H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"]))
+    Fa = O.sample_F_a_c(cs["F"], Z, h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
+    assert relerr(Fa, R.sample_F_a(cs["F"], Z, h2, rv["invert_aZZt_Ainv"], v["z_Fa"])) < tol
+    Yt = Y - X @ loc[:b] - Z @ loc[b:]
+    F = O.sample_factors_scores_c(Yt, Z, Lam, cs["resid_Y_prec"], Fa, h2, v["z_F"])
+    assert rowwise_relerr(F, R.sample_factors_scores(Yt, Z, Lam, cs["resid_Y_prec"], Fa, h2, v["z_F"])) < 1e-8
+
+
 def test_twins_differ_exactly_where_the_reference_does():
     """cpp:274 integer n/2 vs BSFG_functions.R:99 real n/2 (odd n); cpp:326 `> 10000` vs R:229 `== Inf`."""
     from oracle import bsfg_oracle as O, bsfg_oracle_rtwin as R, init_oracle as I
