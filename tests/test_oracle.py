@@ -236,6 +236,78 @@ def test_twins_differ_exactly_where_the_reference_does():
 
 
 # ------------------------------------------------------------------------------------------------
+# (1b) `_c` restatement == transcription of the MATLAB originals (BSF-G/*.m), and the R-vs-MATLAB departures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_matlab_originals_agree_on_reference_fixtures(name):
+    from oracle import bsfg_oracle as O, bsfg_oracle_mtwin as M
+    g, d, rv, pri, rp, st, v = _twin_inputs(name)
+    Y, X, Z = g["aux1"].get("Y_imputed", d["Y"]), d["X"], d["Z_1"]
+    if "Z_2" in d:
+        Y = Y - d["Z_2"] @ st["W"]
+    H = rp["h2_divisions"]
+    tol = 1e-9
+    Yt = Y - X @ st["B"]
+    Lam = O.sample_Lambda_c(Yt, st["F"], st["resid_Y_prec"], st["E_a_prec"], st["Plam"], rv["invert_aI_bZAZ"], v["z_Lambda"])
+    assert rowwise_relerr(Lam, M.sample_lambda(Yt, st["F"], st["resid_Y_prec"], st["E_a_prec"], st["Plam"], rv["invert_aI_bZAZ"],
+                                               v["z_Lambda"])) < tol
+    Yt = Y - st["F"] @ Lam.T
+    loc = O.sample_means_c(Yt, st["resid_Y_prec"], st["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    locm = M.sample_means(Yt, st["resid_Y_prec"], st["E_a_prec"], rv["invert_aPXA_bDesignDesignT"], v["z_means"])
+    assert locm.shape == loc.T.shape and relerr(locm.T, loc) < tol          # MATLAB returns the transpose (sample_means.m:29)
+    h2 = O.sample_h2s_discrete_c(st["F"], H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"])
+    assert np.array_equal(h2, M.sample_h2s_discrete(st["F"], H, pri["h2_priors_factors"], rv["invert_aI_bZAZ"], v["u_h2"]))
+    Fa = O.sample_F_a_c(st["F"], Z, h2, rv["invert_aZZt_Ainv"], v["z_Fa"])
+    assert relerr(Fa, M.sample_F_a(st["F"], Z, h2, rv["invert_aZZt_Ainv"], v["z_Fa"])) < tol
+    Yt = Y - X @ st["B"] - Z @ st["E_a"]
+    F = O.sample_factors_scores_c(Yt, Z, Lam, st["resid_Y_prec"], Fa, h2, v["z_F"])
+    assert rowwise_relerr(F, M.sample_factors_scores(Yt, Z, Lam, st["resid_Y_prec"], Fa, h2, v["z_F"])) < 1e-8
+
+
+def test_R_port_departs_from_matlab_exactly_where_documented():
+    """sample_delta: R's `2:(k-1)` never resamples delta_k, MATLAB's `2:k` does.
+    update_k drop arm: R folds delta over every redundant column but the last, MATLAB only over those below the NEW
+    k - 1 (row a8).  The add arm and everything else coincide.  The device path follows R."""
+    from oracle import bsfg_oracle as O, bsfg_oracle_mtwin as M
+    rng = np.random.default_rng(12)
+    p, k, n = 11, 6, 9
+    LP = rng.gamma(1.5, 1.0, (p, k)); L2 = rng.standard_normal((p, k)) ** 2
+    delta = rng.gamma(3.0, 1.0, k) + 0.5; tauh = np.cumprod(delta)
+    g = rng.gamma(4.0, 1.0, k)
+    dr = O.sample_delta(delta, tauh, LP, 2.1, 0.05, 4.5, 1.0, L2, g[:k - 1])
+    dr = np.asarray(dr[0] if isinstance(dr, tuple) else dr).ravel()
+    dm, tm, shapes, rates = M.sample_delta(delta, tauh, LP, 2.1, 0.05, 4.5, 1.0, L2, g)
+    assert relerr(dm[:k - 1], dr[:k - 1]) < 1e-13                # same draws for delta_1 .. delta_{k-1}
+    assert dr[k - 1] == delta[k - 1] and dm[k - 1] != delta[k - 1]
+    assert relerr(tm, np.cumprod(dm)) < 1e-15 and len(shapes) == k
+
+    F = rng.standard_normal((n, k)); Fa = rng.standard_normal((n, k)); h2 = rng.integers(1, 40, k) / 50.0
+    Lam = rng.standard_normal((p, k))
+    v = dict(u_k=0.0, k_g_lp=rng.gamma(1.5, 1.0, p), k_g_delta=rng.gamma(4.5, 1.0), k_z_lambda=rng.standard_normal(p),
+             k_u_h2=rng.uniform(), k_z_Fa=rng.standard_normal(n), k_z_F=rng.standard_normal(n))
+    args = lambda L: (F, L, Fa, h2, LP, LP * tauh[None, :], delta, tauh, np.eye(n), 3.0, 4.5, 1.0, 1.0, 5e-4, 300, 1e-2, 1.0, v)
+    # add arm: identical
+    a, b = O.update_k(*args(Lam)), M.update_k(*args(Lam))
+    assert a["F"].shape[1] == k + 1
+    for f in a:
+        assert relerr(np.asarray(b[f]), np.asarray(a[f])) < 1e-13, f
+    # drop arm, one redundant column (2, 1-based): identical
+    L1 = Lam.copy(); L1[:, 1] *= 1e-6
+    a, b = O.update_k(*args(L1)), M.update_k(*args(L1))
+    assert a["F"].shape[1] == k - 1
+    for f in a:
+        assert relerr(np.asarray(b[f]), np.asarray(a[f])) < 1e-13, f
+    # drop arm, redundant columns 2 and 4: R folds both, MATLAB only column 2 (4 > new k - 1 = 3)
+    L2c = Lam.copy(); L2c[:, [1, 3]] *= 1e-6
+    a, b = O.update_k(*args(L2c)), M.update_k(*args(L2c))
+    assert a["F"].shape[1] == b["F"].shape[1] == k - 2
+    assert relerr(a["delta"], np.array([delta[0], delta[2] * delta[1], delta[4] * delta[3], delta[5]])) < 1e-15
+    assert relerr(b["delta"], np.array([delta[0], delta[2] * delta[1], delta[4], delta[5]])) < 1e-15
+    for f in ("F", "Lambda", "F_a", "F_h2", "Lambda_prec"):
+        assert np.array_equal(np.asarray(a[f]), np.asarray(b[f])), f
+
+
+# ------------------------------------------------------------------------------------------------
 # (2) closed-form identities (dense algebra straight from the model statement)
 # ------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
