@@ -7,12 +7,14 @@ It exists so the CUDA path can be checked; nothing under `sparsefactormixedmodel
 imports it.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may
 use it.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or saved chain outputs, and
-neither R/Rcpp/Armadillo nor MATLAB exist in the build container, so this restatement cannot be
-checked against outputs of the reference itself.  What pins it instead (tests/test_oracle.py):
+PARITY PINNED (round 2): `oracle/_ref/libbsfg_reference.so` is the reference's own `BSFG_functions_c.cpp`,
+compiled UNMODIFIED from `/root/reference` against a stand-in `RcppArmadillo.h` (`oracle/ref_shim/`, SciPy's
+OpenBLAS/LAPACK underneath; `oracle/ref_oracle.py` binds it).  tests/test_oracle.py asserts that every `_c` function
+below equals that library to <= 1e-12 (1e-10 row-wise for the two Cholesky-solve draws) on the reference's three
+fixtures at full size and on random edge-shaped problems, and tests/golden/*.npz hold the LIBRARY's outputs.
+The R-only steps (`sample_delta`, `update_k`, the loop body) cannot be run (no R here); they stay pinned by
   * a second, independent transcription of the R twins (`oracle/bsfg_oracle_rtwin.py`, following
-    `R_BSFG/BSFG_functions.R:23-269`) must agree with this one to 1e-10 under shared variates
-    (the reference author's own convention, README.md:37-38);
+    `R_BSFG/BSFG_functions.R:23-269`) and a third of the MATLAB originals (`oracle/bsfg_oracle_mtwin.py`);
   * closed-form identities (posterior mean/covariance of each Gaussian draw recomputed by dense
     inversion) on small cases.
 
@@ -324,10 +326,19 @@ def update_k(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, Z_W, Lambda_d
             "Plam": Plam, "delta": delta, "tauh": tauh}
 
 
+def _c_functions(fns):
+    """The `_c` samplers a loop body calls: this module's restatements, or (fns = `oracle.ref_oracle`) the compiled
+    reference itself -- same signatures, so the R-side loop restated below can drive either."""
+    import sys
+    m = sys.modules[__name__] if fns is None else fns
+    return (m.sample_Lambda_c, m.sample_means_c, m.sample_h2s_discrete_c, m.sample_F_a_c, m.sample_factors_scores_c,
+            m.sample_px_factors_scores_c)
+
+
 # --------------------------------------------------------------------------------------
 # One Gibbs iteration in the reference's formulation (fast_BSFG_sampler.R:176-270)
 # --------------------------------------------------------------------------------------
-def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
+def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True, fns=None):
     """One pass of the loop body of `fast_BSFG_sampler` with injected variates.
 
     data: dict Y, X, Z_1 and optionally Z_2 (n x r2; then rv has invert_aPXA_bDesignDesignT_rand2 / A_2_inv, the
@@ -337,7 +348,10 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
     st  : current_state dict (modified copy is returned)
     v   : variates dict: z_Lambda (k,p), z_means (br,p), u_h2 (k), z_Fa (r,k), z_F (n,k),
           g_Lambda_prec (p,k), g_resid (p), g_Ea (p), g_delta (>=k-1), u_k, [add-arm extras]
-    Also returns `aux` with the Gamma (shape, rate) parameters of every precision draw."""
+    Also returns `aux` with the Gamma (shape, rate) parameters of every precision draw.
+    fns : None (this module's `_c` restatements) or `oracle.ref_oracle` (the compiled reference)."""
+    (sample_Lambda_c, sample_means_c, sample_h2s_discrete_c, sample_F_a_c, sample_factors_scores_c,
+     sample_px_factors_scores_c) = _c_functions(fns)
     Y, X, Z_1 = data["Y"], data["X"], data["Z_1"]
     n, p = Y.shape
     r = Z_1.shape[1]
@@ -436,9 +450,11 @@ def gibbs_iteration(data, rv, priors, rp, st, i, v, with_update_k=True):
 # --------------------------------------------------------------------------------------
 # One iteration of the fixed-Lambda sampler (fast_BSFG_sampler_fixedlambda.R:159-236)
 # --------------------------------------------------------------------------------------
-def gibbs_iteration_fixedlambda(data, rv, priors, rp, st, Lambda, v):
+def gibbs_iteration_fixedlambda(data, rv, priors, rp, st, Lambda, v, fns=None):
     """Lambda (p, k) is a stored posterior draw (`matrix(BSFG_state$Lambda[,j], nr=p)`, :163-164); the loop resamples
     B/E_a (after ALSO removing X B, :180), W, F_h2, F_a, F and the three precisions; Lambda, Lambda_prec, delta, k stay."""
+    (sample_Lambda_c, sample_means_c, sample_h2s_discrete_c, sample_F_a_c, sample_factors_scores_c,
+     sample_px_factors_scores_c) = _c_functions(fns)
     Y, X, Z_1 = data["Y"], data["X"], data["Z_1"]
     n, p = Y.shape
     r = Z_1.shape[1]
@@ -507,9 +523,11 @@ def update_k_px(F, Lambda, F_a, F_h2, Lambda_prec, Plam, delta, tauh, px_factor,
     return res
 
 
-def gibbs_iteration_px(data, rv, priors, rp, st, i, v, with_update_k=True):
+def gibbs_iteration_px(data, rv, priors, rp, st, i, v, with_update_k=True, fns=None):
     """One pass of the loop body of fast_BSFG_sampler_px.R (:196-311).  State additionally holds px_factor (k) and F_px
     (n, k); variates additionally g_px (k) ~ Gamma(px_shape + n/2, 1) and, for the add arm, k_g_px ~ Gamma(px_shape, 1)."""
+    (sample_Lambda_c, sample_means_c, sample_h2s_discrete_c, sample_F_a_c, sample_factors_scores_c,
+     sample_px_factors_scores_c) = _c_functions(fns)
     Y, X, Z_1 = data["Y"], data["X"], data["Z_1"]
     n, p = Y.shape
     r = Z_1.shape[1]

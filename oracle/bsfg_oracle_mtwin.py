@@ -13,7 +13,8 @@ restatement) under shared variates, and checks that the two differ exactly where
     (BSFG_functions.R:347-352) -- the device path follows R;
   * `sample_F_a`: MATLAB tests `tau_e == Inf` (sample_F_a.m:26) like the R twin, C++ `tau_e > 10000`;
   * `sample_means` returns location_sample' (p x n; sample_means.m:29), the R/C++ versions n x p.
-PARITY UNPINNED in the same sense as the other oracle modules (no MATLAB / Octave here to run the originals).
+This transcription itself cannot be run against MATLAB (no MATLAB / Octave here); it is checked against the `_c`
+restatement, which tests/test_oracle.py pins to the compiled reference (oracle/_ref).
 """
 from __future__ import annotations
 

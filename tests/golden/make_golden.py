@@ -3,22 +3,20 @@ not exist on the GPU box; nothing in tests/, smoke() or bench.py reads /root/ref
 
     python tests/golden/make_golden.py
 
-The reference ships no golden vectors, so these fixtures pin the next best thing:
-the reference's OWN INPUT FIXTURES (`R_BSFG/Sim_1/setup.mat`, `R_BSFG/Example_simulation/setup.mat`,
-`.../Ayroles_et_al_Competitive_fitness/setup.mat`) pushed through the init restatement
-(fast_BSFG_sampler_init.R:63-345, `lists="reference"` = the GSVD route the R code takes) and two Gibbs
-iterations of the oracle (`oracle/bsfg_oracle.py`, restating BSFG_functions_c.cpp) under seeded, stored
-variates.  Each file holds every input of the `_c` boundary (data, the three diagonalisation lists, priors
-literals, state, variates) and the outputs, so
+The reference ships no golden vectors, so these fixtures are OUTPUTS OF THE REFERENCE ITSELF
+RUN HERE: the reference's own input fixtures, at their FULL size (`R_BSFG/Sim_1/setup.mat` n=250 p=100,
+`R_BSFG/Example_simulation/setup.mat` n=187 p=100, `.../Ayroles_et_al_Competitive_fitness/setup.mat` n=200 p=415
+r=40 b=2 with Z_2 and its real NaN pattern), pushed through the init restatement (fast_BSFG_sampler_init.R:63-345,
+`lists="reference"` = the GSVD route the R code takes) and two Gibbs iterations in which every `_c` sampler call is
+served by `oracle/_ref/libbsfg_reference.so` -- `R_BSFG/BSFG_functions_c.cpp` compiled unmodified
+(`oracle/ref_shim/Makefile`, `oracle/ref_oracle.py`) -- under seeded, stored variates injected in the reference's
+fill order.  The R-only glue between those calls (`fast_BSFG_sampler.R:176-270`, `sample_delta`, `update_k`; R is
+not installed) is the restatement in `oracle/bsfg_oracle.py`.  `ref.*` entries are the eight exports called one by
+one (GSVD_2_c and sample_prec_discrete_conditional_c are not on the active sweep).  Each file holds every input of
+the `_c` boundary (data, the three diagonalisation lists, priors literals, state, variates) and the outputs, so
 
-  * `-m "not gpu"` tests re-run the oracle from the stored inputs (pins it against drift: NumPy/LAPACK
-    version, later edits) and cross-check it against the R-twin transcription on the same inputs;
-  * `-m gpu` tests push the same stored inputs through the C ABI and compare with the stored outputs.
-
-Fixtures are sub-sampled to stay small (whole half-sib families / whole lines are kept so A stays a valid
-relationship matrix).  The Ayroles panel is used as it is: rectangular Z_1 (n=200 individuals, r=40 lines), b=2,
-the second random effect of the real data (Z_2 200 x 40, W, W_prec; fast_BSFG_sampler.R:211-216, 248-250) and its
-real missing phenotypes (NaN, re-imputed every iteration, fast_BSFG_sampler.R:180-184).
+  * `-m "not gpu"` tests re-run the NumPy oracle from the stored inputs and must reproduce the reference's outputs;
+  * `-m gpu` tests push the same stored inputs through the C ABI and compare with the reference's outputs.
 """
 import os
 import sys
@@ -29,14 +27,14 @@ import scipy.io as sio
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from oracle import bsfg_oracle as O, init_oracle as I  # noqa: E402
+from oracle import bsfg_oracle as O, init_oracle as I, ref_oracle as R  # noqa: E402
 
 REF = "/root/reference/R_BSFG"
 CASES = {
     # name: (path, individuals kept, traits kept, k)
-    "sim1": (f"{REF}/Sim_1/setup.mat", 60, 40, 6),
-    "example": (f"{REF}/Example_simulation/setup.mat", 64, 36, 5),
-    "ayroles": (f"{REF}/Runcie_Mukherjee_analyses/Ayroles_et_al_Competitive_fitness/setup.mat", 200, 48, 7),
+    "sim1": (f"{REF}/Sim_1/setup.mat", 250, 100, 20),          # k_init = 20: model_setup.R:58
+    "example": (f"{REF}/Example_simulation/setup.mat", 187, 100, 10),
+    "ayroles": (f"{REF}/Runcie_Mukherjee_analyses/Ayroles_et_al_Competitive_fitness/setup.mat", 200, 415, 12),
 }
 
 
@@ -73,6 +71,7 @@ def flatten(prefix, d, out):
 
 
 def main():
+    I.GSVD_2_c = R.GSVD_2_c          # the init's two GSVD_2_c calls (fast_BSFG_sampler_init.R:289, 320) -> compiled reference
     for name, (path, n_keep, p_keep, k) in CASES.items():
         setup = load_setup(name, path, n_keep, p_keep)
         pri = I.default_priors(k_init=k)
@@ -92,7 +91,7 @@ def main():
         cur = cs
         for it in (1, 2):
             v = I.draw_variates(rng, n, p, k, r, b + r, pri, r2=r2, missing=bool(np.isnan(d["Y"]).any()))
-            nxt, aux = O.gibbs_iteration(d, rv, pri, rp, cur, it, v)
+            nxt, aux = R.gibbs_iteration(d, rv, pri, rp, cur, it, v)      # `_c` calls -> compiled reference
             flatten(f"variates{it}.", v, out)
             flatten(f"state{it}.", {kk: vv for kk, vv in nxt.items() if kk not in skip}, out)
             flatten(f"aux{it}.", {kk: vv for kk, vv in aux.items() if kk.endswith("_rate") or kk == "Y_imputed"}, out)
@@ -100,11 +99,18 @@ def main():
         # the export that is off the active sweep (fast_BSFG_sampler.R:198-199): stored separately
         u = rng.uniform(size=p)
         Yc = out.get("aux1.Y_imputed", d["Y"])
-        prec = O.sample_prec_discrete_conditional_c(Yc, rp["h2_divisions"], pri["h2_priors_factors"],
+        prec = R.sample_prec_discrete_conditional_c(Yc, rp["h2_divisions"], pri["h2_priors_factors"],
                                                     rv["invert_aI_bZAZ"], cs["resid_Y_prec"], u)
         out["prec_cond.u"] = u
         out["prec_cond.Prec"] = prec
+        # GSVD_2_c (cpp:27-40) on the pair the init hands it for the [B;E_a] list (fast_BSFG_sampler_init.R:287-289)
+        Dm = np.column_stack([d["X"], d["Z_1"]])
+        gA, gB = I.cholcov(I.block_diag2(1e-10 * np.eye(b), rv["Ainv"])), I.cholcov(Dm.T @ Dm)
+        out["gsvd.A"], out["gsvd.B"] = gA, gB
+        for kk, vv in R.GSVD_2_c(gA, gB).items():
+            out[f"gsvd.{kk}"] = vv
         out["meta.k"] = np.int64(k)
+        out["meta.generated_by"] = np.array("oracle/_ref/libbsfg_reference.so (BSFG_functions_c.cpp compiled unmodified)")
         dst = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(dst, **out)
         print(name, f"n={n} p={p} r={r} b={b} k={k}", f"{os.path.getsize(dst) / 1024:.0f} KiB")

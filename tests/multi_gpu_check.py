@@ -28,7 +28,7 @@ def main():
     import torch
     import torch.distributed as dist
     from conftest import relerr, rowwise_relerr
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

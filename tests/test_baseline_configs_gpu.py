@@ -10,7 +10,7 @@ TOL = 1e-9
 
 
 def _parity(n, p, k, pedigree, seed, iters=1, gram="default"):
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     setup = I.make_synthetic(n, p, max(2, k // 2), pedigree=pedigree, seed=seed)
     pri = I.default_priors(k_init=k); rp = I.default_run_parameters()

@@ -1,6 +1,7 @@
-"""GPU parity against the committed golden fixtures (tests/golden/*.npz: the reference's own setup.mat inputs
--> reference-route init lists -> oracle outputs, see tests/golden/make_golden.py).  Nothing here runs the oracle:
-stored inputs go through the C ABI, results are compared with stored outputs.  Tolerance 1e-9 relative
+"""GPU parity against the committed golden fixtures (tests/golden/*.npz: the reference's own setup.mat inputs at
+full size -> reference-route init lists -> outputs of the COMPILED REFERENCE, oracle/_ref, see
+tests/golden/make_golden.py).  Nothing here runs a checker: stored inputs go through the C ABI, results are
+compared with the reference's stored outputs.  Tolerance 1e-9 relative
 (BASELINE.json north_star), exact h2 indices."""
 import numpy as np
 import pytest
@@ -10,6 +11,14 @@ from test_oracle import CASES, golden_problem
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
+
+
+def test_checker_is_the_compiled_reference():
+    """The other `-m gpu` files compare the device with `oracle.checker`; on the GPU box that must be the reference
+    library that travelled with the snapshot, not the NumPy restatement."""
+    from oracle import checker
+    assert checker.KIND == "reference"
+    assert checker.sample_Lambda_c.__module__ == "oracle.ref_oracle"
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -58,7 +58,7 @@ def test_init_lists_contract(pedigree, rect, r2):
 
 def test_sweep_on_device_made_lists_matches_oracle():
     import sparsefactormixedmodel_b200 as B
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     n, p, k, r2 = 50, 31, 5, 4
     setup = _setup(n, p, r2, "random", 43)
     pri = I.default_priors(k_init=k); rp = I.default_run_parameters()

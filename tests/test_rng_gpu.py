@@ -23,7 +23,7 @@ def test_philox_normals_are_standard_normal():
     """theta = mean + z / sqrt(d) (cpp:75-78): back out z from a Philox draw of sample_means_c; 6000 values, KS vs N(0,1),
     and no correlation between the cosine / sine branches of one Box-Muller block (elements 2q, 2q+1)."""
     import sparsefactormixedmodel_b200 as B
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     setup, st = _build(100, 60, 4, 3)
     d, rv, cs = st["data_matrices"], st["run_variables"], st["current_state"]
     L = rv["invert_aPXA_bDesignDesignT"]

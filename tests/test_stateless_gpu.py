@@ -56,7 +56,7 @@ def _prob(small_problem):
 
 
 def test_sample_Lambda_c(pkg, small_problem, gram):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     rng = np.random.default_rng(11)
     z = rng.standard_normal((k, p))
@@ -76,7 +76,7 @@ def test_sample_Lambda_c(pkg, small_problem, gram):
 def test_sample_Lambda_c_shapes(pkg, n, p, k, gram):
     """ragged sizes incl. odd n (padded leading dimensions); k across the 4-warp (k <= 128) and 8-warp (k <= 216, the
     shared-memory limit) instantiations of the blocked Cholesky, incl. k not a multiple of 8."""
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     rng = np.random.default_rng(n + p + k)
     A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n) * 0.1
     s, U = np.linalg.eigh(A); s = s[::-1].copy(); U = U[:, ::-1].copy()
@@ -95,7 +95,7 @@ def test_sample_Lambda_c_expsum_range_guard(pkg, spread, terms):
     """The exponential-sum Gram must never lose accuracy silently: with a precision ratio E_a_prec/resid_Y_prec
     spread over 2*log10(spread) decades, or too few nodes, the device guard falls back to the exact GEMM; either way
     the draw matches the oracle to 1e-9."""
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     rng = np.random.default_rng(3)
     n, p, k = 96, 40, 9
     A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n) * 0.05
@@ -129,7 +129,7 @@ def test_sample_Lambda_c_not_pd(pkg):
 
 
 def test_sample_means_c(pkg, small_problem):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     rng = np.random.default_rng(12)
     br = b + r
@@ -144,7 +144,7 @@ def test_sample_means_c(pkg, small_problem):
 
 
 def test_sample_factors_scores_c(pkg, small_problem):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     rng = np.random.default_rng(13)
     z = rng.standard_normal((n, k))
@@ -175,7 +175,7 @@ def _check_grid_draw(got_h2, got_lp, want_h2, want_lp, u, H):
 
 
 def test_sample_h2s_discrete_c(pkg, small_problem):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     rng = np.random.default_rng(14)
     H = 50
@@ -197,7 +197,7 @@ def test_sample_h2s_discrete_c(pkg, small_problem):
 @pytest.mark.parametrize("n", [60, 61])
 def test_sample_prec_discrete_conditional_c(pkg, n):
     """odd n exercises the C++ integer division n/2 (cpp:274)."""
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     rng = np.random.default_rng(15 + n)
     p, H = 37, 50
     A = rng.standard_normal((n, n)); A = A @ A.T / n + 0.2 * np.eye(n)
@@ -220,7 +220,7 @@ def test_sample_prec_discrete_conditional_c(pkg, n):
 
 
 def test_sample_F_a_c(pkg, small_problem):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     rng = np.random.default_rng(16)
     z = rng.standard_normal((r, k))
@@ -234,7 +234,7 @@ def test_sample_F_a_c(pkg, small_problem):
 
 def test_sample_F_a_c_rectangular_Z(pkg):
     """Ayroles-shaped incidence matrix: r < n lines, several individuals per line."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     rng = np.random.default_rng(17)
     n, r, k = 90, 30, 5
     Z1 = np.zeros((n, r)); Z1[np.arange(n), np.arange(n) % r] = 1.0
@@ -249,7 +249,7 @@ def test_sample_F_a_c_rectangular_Z(pkg):
 
 @pytest.mark.parametrize("k", [2, 3, 6, 20])
 def test_sample_delta_c(pkg, k):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     rng = np.random.default_rng(18 + k)
     p = 45
     delta = rng.gamma(3, 1, k) + 0.5
@@ -272,7 +272,7 @@ def test_device_rng_moments(pkg, small_problem):
     d, rv, cs, pri, n, p, k, r, b = _prob(small_problem)
     Yt = d["Y"] - cs["F"] @ cs["Lambda"].T
     L = rv["invert_aPXA_bDesignDesignT"]
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     mean = O.sample_means_c(Yt, cs["resid_Y_prec"], cs["E_a_prec"], L, np.zeros((b + r, p)))
     a = pkg.sample_means_c(Yt, cs["resid_Y_prec"], cs["E_a_prec"], L, seed=123)
     a2 = pkg.sample_means_c(Yt, cs["resid_Y_prec"], cs["E_a_prec"], L, seed=123)
@@ -316,7 +316,7 @@ def _update_k_case(arm, px=False, rect_Z=False):
 @pytest.mark.parametrize("px", [False, True])
 @pytest.mark.parametrize("rect_Z", [False, True])
 def test_update_k_c(pkg, arm, px, rect_Z):
-    from oracle import bsfg_oracle as O
+    from oracle import checker as O
     cs, pri, rp, dm, v = _update_k_case(arm, px, rect_Z)
     k = cs["F"].shape[1]
     args = (cs["F"], cs["Lambda"], cs["F_a"], cs["F_h2"], cs["Lambda_prec"], cs["Plam"], cs["delta"], cs["tauh"])

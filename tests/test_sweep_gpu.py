@@ -39,7 +39,7 @@ def _compare_states(dev, ora, b, tol=TOL, h2_exact=True):
 @pytest.mark.parametrize("lists,mode,expect", [("stable", "auto", "diag"), ("reference", "auto", "direct"),
                                                ("stable", "direct", "direct")])
 def test_sweep_injected_matches_oracle(lists, mode, expect, gram):
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 60, 45, 6
     st = _build(n, p, k, lists)
@@ -74,7 +74,7 @@ def test_sweep_injected_matches_oracle(lists, mode, expect, gram):
 def test_sweep_expsum_falls_back_to_exact_gram_when_range_is_too_wide():
     """(s + E_a_prec/resid_Y_prec) spanning 15 decades cannot be covered by 256 nodes: the device raises the fallback flag,
     the exact Gram GEMM runs for that iteration, the result still matches the oracle, and the event is counted."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 60, 45, 6
     st = _build(n, p, k, "stable")
@@ -109,7 +109,7 @@ def test_sweep_expsum_falls_back_to_exact_gram_when_range_is_too_wide():
 def test_sweep_second_random_effect(lists, gram):
     """Z_2 / W (fast_BSFG_sampler.R:211-216, 248-250): the second sample_means_c call with W_prec and the rand2 list,
     every residual that carries Z_2 W, and the W_prec Gamma draw."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k, r2 = 55, 41, 5, 9
     rng = np.random.default_rng(77)
@@ -147,7 +147,7 @@ def test_sweep_second_random_effect(lists, gram):
 def test_sweep_missing_phenotypes(with_z2):
     """NaN in Y (fast_BSFG_sampler.R:180-184): imputed from the current state + rnorm at the start of every iteration,
     then every rotated quantity is rebuilt.  20% missing, like the Ayroles panel."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k, r2 = 45, 38, 4, (6 if with_z2 else 0)
     rng = np.random.default_rng(99)
@@ -185,7 +185,7 @@ def test_sweep_missing_phenotypes(with_z2):
 def test_sweep_fixed_lambda(b, with_z2):
     """fast_BSFG_sampler_fixedlambda.R:159-236: Lambda supplied per iteration, everything else resampled; the (B,E_a)
     step removes X B as that driver does."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k, r2 = 50, 33, 4, (5 if with_z2 else 0)
     rng = np.random.default_rng(123)
@@ -287,7 +287,7 @@ def test_device_posterior_matches_host_bookkeeping(adapt):
 
 def test_sweep_adaptive_expsum_terms():
     """gram_terms = -1: the node count adapts between bsfg_sweep calls; parity with the oracle is unchanged."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 60, 45, 6
     st = _build(n, p, k, "stable")
@@ -317,7 +317,7 @@ def test_sweep_adaptive_expsum_terms():
 def test_sweep_edge_sizes(n, p, k, b):
     """Smallest shapes the reference's R code accepts: a single trait, k = 2 (where R's `2:(k-1)` loop of sample_delta
     counts DOWN, BSFG_functions.R:296), no fixed effects (b = 0), more factors than traits, n not a multiple of anything."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     setup = I.make_synthetic(n, max(p, 2), 2, pedigree="halfsib", seed=n + p, b=max(b, 1))
     setup["Y"] = setup["Y"][:, :p]
@@ -391,7 +391,7 @@ def _px_state(cs, pri, rng):
 
 def test_sweep_parameter_expanded():
     """fast_BSFG_sampler_px.R:196-311: Lambda_px / F_px / px_factor; Plam divided by px_factor; F and Lambda derived."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 55, 42, 5
     st = _build(n, p, k, "stable", seed=31)
@@ -431,7 +431,7 @@ def test_sweep_parameter_expanded():
 def test_update_k_px_add_and_drop():
     """update_k of BSFG_functions_px.R:301-369: px_factor / F_px follow the added or dropped columns and Plam is recomputed
     WITHOUT the px division in both arms (:328, :348)."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 40, 30, 5
     st = _build(n, p, k, "stable", seed=13)
@@ -469,7 +469,7 @@ def test_update_k_px_add_and_drop():
 
 def test_sweep_free_running_three_iterations():
     """no re-synchronisation: the chain itself must track the oracle (errors compound, so 1e-7)."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 50, 64, 5
     st = _build(n, p, k, "stable", seed=11)
@@ -491,7 +491,7 @@ def test_sweep_free_running_three_iterations():
 
 def test_sweep_random_pedigree_rectangular_design():
     """n distinct eigenvalues (random pedigree), b = 2 fixed effects, odd sizes."""
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 53, 37, 7
     st = _build(n, p, k, "stable", pedigree="random", seed=5, b=2)
@@ -509,7 +509,7 @@ def test_sweep_random_pedigree_rectangular_design():
 
 
 def test_update_k_add_and_drop():
-    from oracle import bsfg_oracle as O, init_oracle as I
+    from oracle import checker as O, init_oracle as I
     from sparsefactormixedmodel_b200 import BSFGSweep
     n, p, k = 40, 30, 5
     st = _build(n, p, k, "stable", seed=13)
