@@ -73,8 +73,14 @@ def random_pedigree_A(n, rng, frac_founders=0.2, frac_gen1=0.3):
     return A
 
 
-def make_problem(n, p, k, seed=20131, device=None):
-    """Returns (data_matrices, run_variables, priors, run_parameters, current_state) as host NumPy."""
+def make_problem(n, p, k, seed=20131, device=None, lists_route="device", start="prior"):
+    """Returns (data_matrices, run_variables, priors, run_parameters, current_state) as host NumPy.
+
+    lists_route  "device": the product's own init (bsfg_init_lists, SURVEY.md 8f-1) when a GPU is present;
+                 "host": the same eigen route through torch.linalg, never importing the product (the reference arm).
+    start        "prior": initial state drawn from the priors (fast_BSFG_sampler_init.R:127-216);
+                 "truth": k_true = k simulated factors and the chain started at the simulated Lambda / F / F_a with flat
+                 shrinkage, so that no column is redundant and update_k keeps k near its start value (the C5 live leg)."""
     import torch
     dev = torch.device(device if device is not None else ("cuda:0" if torch.cuda.is_available() else "cpu"))
     f64 = torch.float64
@@ -82,7 +88,7 @@ def make_problem(n, p, k, seed=20131, device=None):
     gen = torch.Generator(device=dev); gen.manual_seed(seed)
     A_np = random_pedigree_A(n, rng)
     A = torch.from_numpy(A_np).to(dev)
-    k_true = max(2, k // 2)
+    k_true = k if start == "truth" else max(2, k // 2)
     factor_h2s = np.linspace(1.0, 0.0, k_true + 1)[:k_true].copy()
     factor_h2s[0::2] = 0.0
     Lam_true = np.zeros((p, k_true))
@@ -95,10 +101,14 @@ def make_problem(n, p, k, seed=20131, device=None):
     h2 = torch.from_numpy(factor_h2s).to(dev)
     L_A = torch.linalg.cholesky(A)
     rn = lambda *s: torch.randn(*s, dtype=f64, device=dev, generator=gen)
-    U_act = L_A @ (rn(n, k_true) @ (Lt_ * h2.sqrt()[None, :]).T + np.sqrt(0.2) * rn(n, p))
-    E_act = rn(n, k_true) @ (Lt_ * (1 - h2).sqrt()[None, :]).T + np.sqrt(0.2) * rn(n, p)
-    Y = U_act + E_act
-    del U_act, E_act
+    Fa_true = L_A @ rn(n, k_true) * h2.sqrt()[None, :]
+    Fe_true = rn(n, k_true) * (1 - h2).sqrt()[None, :]
+    Y = Fa_true @ Lt_.T
+    Y += L_A @ (np.sqrt(0.2) * rn(n, p))
+    Y += Fe_true @ Lt_.T
+    Y += np.sqrt(0.2) * rn(n, p)
+    Fa_true_h, F_true_h = Fa_true.cpu().numpy(), (Fa_true + Fe_true).cpu().numpy()
+    del Fa_true, Fe_true
     X = torch.ones(n, 1, dtype=f64, device=dev)
     b = 1
     # --- the three diagonalisations (contract of fast_BSFG_sampler_init.R:263-325): the library's own device init
@@ -106,7 +116,7 @@ def make_problem(n, p, k, seed=20131, device=None):
     A_host = np.asfortranarray(A.cpu().numpy())
     X_host = np.asfortranarray(X.cpu().numpy())
     lists = None
-    if dev.type == "cuda":
+    if dev.type == "cuda" and lists_route == "device":
         del A, L_A
         torch.cuda.synchronize(); torch.cuda.empty_cache()
         import sparsefactormixedmodel_b200 as pkg
@@ -152,6 +162,14 @@ def make_problem(n, p, k, seed=20131, device=None):
     F_a = rng.standard_normal((n, k)) * np.sqrt(F_h2)[None, :]
     F = F_a + rng.standard_normal((n, k)) * np.sqrt(1 - F_h2)[None, :]
     B = rng.standard_normal((b, p))
+    if start == "truth":
+        delta = np.ones(k); delta[0] = 2.0
+        tauh = np.cumprod(delta)
+        Plam = Lambda_prec * tauh[None, :]
+        Lambda = Lam_true.copy()
+        F_h2 = np.clip(factor_h2s, 0.0, 0.98)
+        F, F_a = F_true_h, Fa_true_h
+        B = np.zeros((b, p))
     cpu = lambda t: np.asfortranarray(t.cpu().numpy())
     data = dict(Y=cpu(Y), X=X_host, Z_1=np.eye(n), Z_2=np.zeros((n, 0)))
     rv = dict(p=p, n=n, r=n, r2=0, b=b, Ainv=lists["Ainv"], invert_aI_bZAZ=lists["invert_aI_bZAZ"],
@@ -161,6 +179,32 @@ def make_problem(n, p, k, seed=20131, device=None):
     if dev.type == "cuda":
         torch.cuda.synchronize(); torch.cuda.empty_cache()
     return data, rv, priors, run_parameters, cs
+
+
+HBM_PEAK_GBS_FALLBACK = 6553.9
+
+
+def iteration_roofline(n, pl, k, b, phases, gstats, tensor_tf, ms_iter):
+    """Whole-iteration speed of light: per phase, floor = max(FLOP / FP64 tensor rate, bytes / HBM copy rate) with the FLOP and
+    byte counts of what the device formulation executes (tools/phase_floors.py), next to the CUDA-event
+    phase times of the last timed iteration.  The three longest phases are listed with their own fractions."""
+    from tools.phase_floors import floors
+    hbm = HBM_PEAK_GBS_FALLBACK
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    rows, tot_f, tot_m = [], 0.0, 0.0
+    for name, flop, byts, what in floors(n, pl, k, b, R=gstats["terms"] if gstats["mode"] == "expsum" else 0, exact=gstats["mode"] != "expsum"):
+        t_t, t_b = flop / (tensor_tf * 1e12) * 1e3, byts / (hbm * 1e9) * 1e3
+        m = phases.get(name, 0.0) + (phases.get("F_comm", 0.0) if name == "F_solve" else 0.0)
+        f = max(t_t, t_b)
+        tot_f += f; tot_m += m
+        rows.append({"phase": name, "ms": m, "floor_ms": f, "frac": (f / m) if m > 0 else None, "bound": "tensor" if t_t >= t_b else "hbm",
+                     "gflop": flop * 1e-9, "gbytes": byts * 1e-9})
+    top = sorted(rows, key=lambda r_: -r_["ms"])[:3]
+    return {"floor_ms": tot_f, "phases_ms": tot_m, "ms_per_iteration": ms_iter, "frac": tot_f / ms_iter if ms_iter > 0 else None,
+            "hbm_gbs": hbm, "tensor_tflops": tensor_tf, "top3_by_time": top, "all": rows}
 
 
 def algorithmic_flops(n, p, k, b=1):
@@ -219,19 +263,24 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU baseline: the oracle on a bounded trait sample (the ONLY place bench.py touches oracle/)
+# CPU legs: the reference itself on the host cores (the ONLY place bench.py touches oracle/)
 # --------------------------------------------------------------------------------------------
-def cpu_baseline(data, rv, priors, rp, cs, n, p, k, sample_traits, iters=1, seed=1):
-    """Times the C++ CPU oracle (oracle/c/bsfg_ref.cpp: the reference formulation -- U'Y, per-trait k x n GEMMs + chol +
-    3 solves, per-trait U gemv, dense Z_1 E_a, the full t(E_a) Ainv E_a product -- compiled against SciPy's OpenBLAS with
-    all host threads inside BLAS, i.e. the parallelism R + a threaded BLAS has) on the first `sample_traits` traits at
-    full n and k, and scales to p traits: per-trait work dominates and is linear in p, so
-    iter/s(p) ~= iter/s(sample) * sample/p.  (The p^2 r term of fast_BSFG_sampler.R:245 is under-counted by the sample --
-    in the reference's favour.)  Also reports "baseline-opt" (BASELINE.md section 2): the same code with the per-trait
-    loops under OpenMP and single-threaded BLAS per trait."""
-    from oracle import c_oracle as CO, init_oracle as I   # test infrastructure, used here as the timed baseline
-    ps = min(sample_traits, p)
-    sl = slice(0, ps)
+def _reference_checker():
+    """(module, kind, description): the compiled reference (oracle/_ref: BSFG_functions_c.cpp built unmodified against the
+    stand-in RcppArmadillo.h + SciPy OpenBLAS; the R loop body around it is oracle/bsfg_oracle.gibbs_iteration, R itself
+    cannot run here), else the C++ restatement oracle/c."""
+    from oracle import ref_oracle as R
+    if R.available():
+        R.load()
+        return R, "reference", ("oracle/_ref/libbsfg_reference.so = the reference's BSFG_functions_c.cpp compiled unmodified (stand-in "
+                                "RcppArmadillo.h over SciPy OpenBLAS/LAPACK); the R loop body fast_BSFG_sampler.R:176-270 around the _c calls "
+                                "is restated in NumPy (no R in the image) with the reference's own operations incl. dense Z_1 E_a and the "
+                                "p x p t(E_a) Ainv E_a product")
+    from oracle import c_oracle as CO
+    return CO, "port", "oracle/c/bsfg_ref.cpp (C++ restatement of the Rcpp path in the reference formulation, SciPy OpenBLAS)"
+
+
+def _slice_traits(data, cs, sl):
     d = dict(Y=np.asfortranarray(data["Y"][:, sl]), X=data["X"], Z_1=data["Z_1"])
     st = {kk: vv for kk, vv in cs.items() if vv is not None}
     for nm in ("Lambda", "Lambda_prec", "Plam"):
@@ -239,30 +288,51 @@ def cpu_baseline(data, rv, priors, rp, cs, n, p, k, sample_traits, iters=1, seed
     for nm in ("resid_Y_prec", "E_a_prec"):
         st[nm] = np.asarray(st[nm])[sl]
     st["B"] = np.asarray(st["B"])[:, sl]
-    rng = np.random.default_rng(seed)
+    return d, st
+
+
+def reference_iterations(data, rv, priors, rp, cs, n, p, k, traits=None, iters=1, seed=1, warm=True):
+    """Times `iters` Gibbs iterations of the reference on the host cores, on all p traits (traits=None) or on the first
+    `traits` of them.  Returns (seconds per iteration [list], kind, description, cores, blas threads)."""
+    from oracle import init_oracle as I
+    M, kind, what = _reference_checker()
     cores = os.cpu_count() or 1
-    CO.blas_threads(cores)
+    M.blas_threads(cores)
+    rng = np.random.default_rng(seed)
+    if warm:                      # BLAS thread pool + page-in on a tiny trait block (not timed)
+        dw, sw_ = _slice_traits(data, cs, slice(0, min(p, 64)))
+        vw = I.draw_variates(rng, n, dw["Y"].shape[1], k, n, rv["b"] + n, priors)
+        _one_reference_iteration(M, kind, dw, rv, priors, rp, sw_, vw)
+    ps = p if traits is None else min(traits, p)
+    d, st = (dict(Y=data["Y"], X=data["X"], Z_1=data["Z_1"]), {kk: vv for kk, vv in cs.items() if vv is not None}) if ps == p \
+        else _slice_traits(data, cs, slice(0, ps))
+    times = []
+    for _ in range(iters):
+        v = I.draw_variates(rng, n, ps, k, n, rv["b"] + n, priors)
+        t0 = time.perf_counter()
+        st = _one_reference_iteration(M, kind, d, rv, priors, rp, st, v)
+        times.append(time.perf_counter() - t0)
+    return times, kind, what, int(cores), int(M.blas_threads()), ps
 
-    def best(trait_threads):
-        t_best, cur = None, st
-        for it in range(iters):
-            v = I.draw_variates(rng, n, ps, k, n, rv["b"] + n, priors)
-            t0 = time.perf_counter()
-            cur, _ = CO.gibbs_iteration_c(d, rv, priors, rp, cur, v, trait_threads=trait_threads)
-            dt = time.perf_counter() - t0
-            t_best = dt if t_best is None else min(t_best, dt)
-        return t_best
 
-    t_ref = best(1)
-    t_opt = best(cores)
-    value = 1.0 / (t_ref * (p / ps))
-    return {"value": value, "unit": "iter/s", "cores": int(cores), "kind": "port",
-            "sample": f"oracle/c/bsfg_ref.cpp (C++ restatement of the Rcpp path in the reference formulation, SciPy OpenBLAS, "
-                      f"{CO.blas_threads()} BLAS threads) on {ps} of {p} traits at full n={n}, k={k}: {t_ref:.2f} s/iter on the "
-                      f"sample, scaled x{p / ps:.1f} (per-trait work is linear in p); best of {iters}",
-            "baseline_opt": {"value": 1.0 / (t_opt * (p / ps)), "unit": "iter/s",
-                             "what": f"same code, per-trait loops under OpenMP ({cores} threads) with single-threaded BLAS: "
-                                     f"{t_opt:.2f} s/iter on the sample"}}
+def _one_reference_iteration(M, kind, d, rv, priors, rp, st, v):
+    if kind == "reference":
+        nxt, _ = M.gibbs_iteration(d, rv, priors, rp, st, 1, v, with_update_k=False)   # i = 1 <= 200: update_k gated off either way
+    else:
+        nxt, _ = M.gibbs_iteration_c(d, rv, priors, rp, st, v, trait_threads=1)
+    return nxt
+
+
+def cpu_baseline(data, rv, priors, rp, cs, n, p, k, sample_traits):
+    """The bounded CPU leg printed beside the GPU number: ONE iteration of the reference on the first `sample_traits` traits
+    at full n and k, scaled by p / sample (per-trait work dominates and is linear in p; the p^2 r term of
+    fast_BSFG_sampler.R:245 is under-counted by the sample, in the reference's favour; the p-independent F_h2 / F_a / F
+    steps are over-counted by the scaling -- < 1 % of the iteration).  `--impl reference` measures the whole workload."""
+    times, kind, what, cores, threads, ps = reference_iterations(data, rv, priors, rp, cs, n, p, k, traits=sample_traits)
+    t = times[0]
+    return {"value": 1.0 / (t * (p / ps)), "unit": "iter/s", "cores": cores, "kind": kind, "extrapolated": ps != p,
+            "sample": f"{what}; {threads} BLAS threads; 1 iteration on {ps} of {p} traits at full n={n}, k={k}: {t:.2f} s, "
+                      f"scaled x{p / ps:.1f}"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -360,8 +430,13 @@ def run_ours(args):
     n, p, k = WORKLOADS[args.workload]
 
     t_setup = time.time()
+    # C5 (BASELINE.json configs[4]) runs with update_k live (start at iteration 200: the i > 200 gate of BSFG_functions.R:331
+    # is open from the first iteration).  Two legs: --c5-leg held  = k fixed at its start value (iterations <= 200);
+    #                                               --c5-leg live  = update_k live on a chain started at the simulated truth
+    #                                                                with k_true = k, so k stays near its start value
+    held = args.workload != "C5" or args.c5_leg == "held"
     if rank == 0:
-        prob = make_problem(n, p, k, device=f"cuda:{local}")
+        prob = make_problem(n, p, k, device=f"cuda:{local}", start="prior" if held else "truth")
     else:
         prob = None
     if world > 1:
@@ -370,10 +445,8 @@ def run_ours(args):
     nccl_id = None
     if world > 1:
         nccl_id = bcast_obj(BSFGSweep.nccl_unique_id() if rank == 0 else None)
-    # C5 (BASELINE.json configs[4]) runs with update_k live: start at iteration 200 (the i > 200 gate of
-    # BSFG_functions.R:331 is open from the first timed iteration) and leave room for added factors
-    start_iter = args.start_iter if args.start_iter >= 0 else (200 if args.workload == "C5" else 0)
-    k_max = k if start_iter + args.warmup + args.steps + 8 <= 200 else min(k + 16, 216)
+    start_iter = args.start_iter if args.start_iter >= 0 else (0 if held else 200)
+    k_max = k if start_iter + args.warmup + args.steps + 8 <= 200 else min(k + 16, pkg.k_limit() if hasattr(pkg, "k_limit") else 216)
     cs = dict(cs); cs["nrun"] = start_iter
     live_k = start_iter + args.warmup + args.steps > 200
     sw = BSFGSweep(data, rv, priors, rp, k_init=k, k_max=k_max, seed=20131, rank=rank, world=world, nccl_id=nccl_id,
@@ -401,12 +474,22 @@ def run_ours(args):
     clocks = ClockSampler(local); clocks.start()
     launches0 = lib.bsfg_launch_count()
     wall0 = time.perf_counter()
-    sw.sweep(args.steps)                      # K iterations, one call, CUDA events inside on the sweep stream
-    barrier()
+    k_per_iter = None
+    if not live_k:
+        sw.sweep(args.steps)                  # K iterations, one call, CUDA events inside on the sweep stream
+        barrier()
+        dev_ms, _, phases = sw.timing()
+    else:                                     # k moves: one call per iteration so k can be reported per timed iteration
+        dev_ms, k_per_iter, phases = 0.0, [], None
+        for _ in range(args.steps):
+            sw.sweep(1)
+            ms1, _, phases = sw.timing()
+            dev_ms += ms1
+            k_per_iter.append(int(sw.k()))
+        barrier()
     wall = time.perf_counter() - wall0
     launches = lib.bsfg_launch_count() - launches0
     clk = clocks.stop()
-    dev_ms, _, phases = sw.timing()
     dev_ms = max_over_ranks(dev_ms)
     value = args.steps / (dev_ms * 1e-3)
     gstats = sw.gram_stats()                 # Gram evaluation in use + its two GEMM timings (last timed iteration)
@@ -432,7 +515,7 @@ def run_ours(args):
     full = dict(cur)
     for nm in ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "B"):
         full[nm] = pinned(full[nm])
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = args.steps
     kk_ = k_now
     h2d = 8 * (3 * sw.pl * kk_ + 2 * n * kk_ + sw.b * sw.pl + 2 * sw.pl + 3 * kk_)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
     d2h = 8 * (3 * sw.pl * kk_ + n * kk_ + n * kk_ + kk_ + sw.b * sw.pl + 2 * sw.pl + 2 * kk_)
@@ -469,12 +552,18 @@ def run_ours(args):
         kern_ms = phases["lambda"]
         kern_name = "dgemm_tn_kernel<128,128,6> (exact weighted Gram Q = G'W, M=k(k+1)/2, N=p_local, K=n)"
     achieved = kern_flop / (kern_ms * 1e-3) * 1e-12 if kern_ms > 0 else None
+    # DRAM bytes of that launch: the ncu --set full figure when this very launch shape was captured (profiles/), else null;
+    # the model (operands read once + result written once) is reported beside it for every shape
     traffic = None
     if os.path.exists(NCU_SUMMARY_FILE):
         try:
-            traffic = json.load(open(NCU_SUMMARY_FILE)).get("dram_bytes_per_launch_" + gstats["mode"])
+            cap = json.load(open(NCU_SUMMARY_FILE))
+            if cap.get("shape_" + gstats["mode"]) == [int(npairs), int(sw.pl), int(gstats["terms"] if gstats["mode"] == "expsum" else n)]:
+                traffic = cap.get("dram_bytes_per_launch_" + gstats["mode"])
         except Exception:
             traffic = None
+    kdim = gstats["terms"] if gstats["mode"] == "expsum" else n
+    traffic_model = 8.0 * (npairs * sw.pl + kdim * npairs + kdim * sw.pl)
 
     # ---- the exact (reference-order) Gram evaluation, timed beside the default: the full-size DMMA GEMM -------
     exact_leg = None
@@ -519,13 +608,13 @@ def run_ours(args):
         "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: n={n} individuals, p={p} traits, k={k} factors, b=1, Z_1=I, r=n, H=50, "
-                               f"random 3-generation pedigree, traits sharded over {world} rank(s)",
+        "config": {"workload": WORKLOAD_TEXT.format(w=args.workload, n=n, p=p, k=k),
                    "parallelism": f"trait-shard x{world}", "l2": "inputs larger than L2 (rotated data 2.4 GB/rank-set, "
                    "Gram operands 1 GB) -- no explicit flush", "formulation": mode,
                    "diag_identity_residuals": [r1, r2],
-                   "update_k": (f"LIVE: iterations {start_iter + 1}.. (i > 200), k {k} -> {k_now} after warm-up + timed steps, k_max {k_max}"
+                   "update_k": (f"LIVE: iterations {start_iter + 1}.. (i > 200), chain started at the simulated truth (k_true = k), k_max {k_max}"
                                 if live_k else "gated off by i<=200 (uu still drawn)"),
+                   "k_per_timed_iteration": k_per_iter if live_k else k,
                    "gram": {kk: gstats[kk] for kk in ("mode", "terms", "step", "fallbacks", "c_min", "c_max")},
                    "rng": "device Philox4x32-10", "setup_s": round(t_setup, 1), "wall_s_timed_region": round(wall, 3)},
         "clocks": clk,
@@ -536,11 +625,12 @@ def run_ours(args):
                                       "get_state_d2h": 1e3 * e2e_parts[2] / e2e_steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "traffic_model": traffic_model,
                      "kernel": kern_name,
                      "flop_per_launch": kern_flop, "ms_per_launch": kern_ms, "peak_source": peak_src,
                      "dmma_issue_peak_tflops": 37.1},
         "phases_ms_last_iter": phases,
+        "iteration_roofline": iteration_roofline(n, sw.pl, k_now, 1, phases, gstats, peak_tf, dev_ms / args.steps),
         "sweep_algorithmic_tflops": algorithmic_flops(n, p, k) / world / (dev_ms / args.steps * 1e-3) * 1e-12,
         "sweep_algorithmic_tflops_note": "SURVEY.md 8d W_flop of the exact formulation (k(k+1)np weighted Gram) per GPU / time; in expsum "
                                          "mode fewer FLOPs are executed, so this can exceed the FP64 peak",
@@ -556,26 +646,39 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+WORKLOAD_TEXT = "{w}: n={n} individuals, p={p} traits, k={k} factors, b=1, Z_1=I, r=n, H=50, random 3-generation pedigree"
+
+
 def run_reference(args):
-    """--impl reference: the reference formulation on the host cores (the Rcpp path cannot be built here: no
-    R/Rcpp/Armadillo), same config/metric.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref, the unmodified
+    BSFG_functions_c.cpp) on the host cores, on the WHOLE workload -- every trait, the dense Z_1 E_a products and the
+    p x p temporary of fast_BSFG_sampler.R:245 included.  One whole iteration at C4 is about a minute of 16 cores, so the arm
+    times `--ref-steps` (default 1) iterations, however many --steps asks for, and says so in `steps_timed`; nothing is
+    extrapolated.  The problem is built without the product (torch.linalg on the CPU).  Rank 0 only."""
     rank, world, local = dist_env()
     if rank != 0:
         return
     n, p, k = WORKLOADS[args.workload]
-    data, rv, priors, rp, cs = make_problem(n, p, k)
-    steps = max(1, min(args.steps, 3))
-    cb = cpu_baseline(data, rv, priors, rp, cs, n, p, k, args.cpu_sample_traits, iters=steps)
+    t0 = time.perf_counter()
+    data, rv, priors, rp, cs = make_problem(n, p, k, device="cpu", lists_route="host")
+    t_setup = time.perf_counter() - t0
+    steps = max(1, args.ref_steps)
+    times, kind, what, cores, threads, _ = reference_iterations(data, rv, priors, rp, cs, n, p, k, traits=None, iters=steps)
+    t_it = float(np.mean(times))
+    value = 1.0 / t_it
     line = {"impl": "reference",
             "metric": "Gibbs iter/sec at n=5000,p=20000,k=100 (1/2/4/8 B200) vs Rcpp host" if args.workload == "C4"
                       else f"Gibbs iter/sec at n={n},p={p},k={k}",
-            "value": cb["value"], "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "steps_timed": steps,      # each a full iteration on the trait sample (best of them is reported), bounded so the arm ends in minutes
-            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "value": value, "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "steps_timed": steps, "timed_region_s": float(np.sum(times)), "s_per_iteration": [round(t, 3) for t in times],
+            "warmup_note": "one untimed iteration on a 64-trait block (BLAS thread pool, page-in); whole-workload warm-up iterations "
+                           "would cost a minute each",
+            "ms_per_step": 1e3 * t_it, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: n={n} individuals, p={p} traits, k={k} factors, b=1, Z_1=I, r=n, H=50"},
-            "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": {"workload": WORKLOAD_TEXT.format(w=args.workload, n=n, p=p, k=k), "setup_s": round(t_setup, 1)},
+            "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": kind, "extrapolated": False,
+                             "sample": f"{what}; {threads} BLAS threads; {steps} whole iteration(s) on all {p} traits"},
+            "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -586,11 +689,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-traits", type=int, default=4000)
+    ap.add_argument("--cpu-sample-traits", type=int, default=1000, help="trait sample of the bounded CPU leg beside the GPU number")
+    ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: whole-workload iterations actually timed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gram", default="default", choices=["default", "expsum", "exact"],
                     help="weighted-Gram evaluation of the Lambda draw (DESIGN.md section 3a)")
     ap.add_argument("--no-exact-leg", action="store_true", help="skip the extra exact-Gram timing beside the default")
+    ap.add_argument("--c5-leg", default="live", choices=["live", "held"],
+                    help="C5 only: update_k live on a chain started at the simulated truth (k stays near 200), or k held (i <= 200)")
     ap.add_argument("--start-iter", type=int, default=-1, help="current_state$nrun at entry (default 0; 200 for C5 so update_k is live)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -104,7 +104,7 @@ static int kt_for(int k) {
     return 8;
 }
 
-// batched Cholesky + solves (chol_blocked.cuh): 4 warps per system up to k = 128, 8 warps above
+// batched Cholesky + solves (chol_blocked.cuh): 4 warps per system up to 13 block rows (k + 1 <= 104), 8 warps above
 static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int nsys, const double* dadd,
                               long dadd_sys_stride, long dadd_elem_stride, const double* rhs, long ldr,
                               const VarSrc& z, double* out, long ldo, double* Lout) {
@@ -113,7 +113,7 @@ static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int 
     const size_t smem = cb_smem_bytes(k, rhs != nullptr);
     if (smem > 227 * 1024) fail(BSFG_ESHAPE, "k = %d: the tiled Cholesky needs %zu B of shared memory", k, smem);
     const uint16_t* map = d.chol_map(k);
-    if (k + (rhs ? 1 : 0) <= 128) {      // one thread per matrix row (incl. the right-hand-side row): 4 warps cover 128 rows
+    if (cb_warps(k, rhs != nullptr) == 4) {
         BSFG_CUDA(cudaFuncSetAttribute(chol_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         chol_blocked_kernel<4><<<nsys, 128, smem, d.st>>>(Qp, ldq, k, nsys, map, dadd, dadd_sys_stride, dadd_elem_stride,
                                                           rhs, ldr, z, out, ldo, Lout, d.d_flag);

@@ -210,6 +210,12 @@ class BSFGSweep:
         out["nrun"] = st.nrun
         return out
 
+    def k(self):
+        """Current number of factors (update_k changes it at run time)."""
+        probe = _lib.bsfg_state()
+        check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))     # all-NULL call: just k and nrun
+        return int(probe.k)
+
     def alloc_state(self, k, with_E_a=True, empty=None):
         """Host buffers for get_state; `empty(shape)` may return pinned F-ordered float64 arrays."""
         mk = empty or (lambda shape: np.zeros(shape, order="F"))

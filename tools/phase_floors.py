@@ -15,15 +15,18 @@ TENSOR = 35.45e12          # FLOP/s, cuBLAS DGEMM 8192^3 on this pool
 HBM = 6553.9e9             # B/s
 
 
-def floors(n, p, k, b, R=256):
+def floors(n, p, k, b, R=256, exact=False):
     br, npair = n + b, k * (k + 1) // 2
     D = 8.0
     rows = []
     add = lambda name, flop, byts, what: rows.append((name, flop, byts, what))
     add("lambda_prep", 0, D * (n * npair + 2 * n * p + n * R + R * p),
         "Gram features (write n x k(k+1)/2), weights (read U'Y, write w.U'y), exp-sum nodes A and E")
-    add("lambda", 2.0 * R * npair * n + 2.0 * npair * R * p, D * npair * p,
-        "node product (G'A) and trait product Q = (G'A)'E; writes Q")
+    if exact:
+        add("lambda", 2.0 * npair * n * p, D * npair * p, "exact weighted Gram Q = G'W (K = n); writes Q")
+    else:
+        add("lambda", 2.0 * R * npair * n + 2.0 * npair * R * p, D * npair * p,
+            "node product (G'A) and trait product Q = (G'A)'E; writes Q")
     add("lambda_chol", 2.0 * k * n * p + p * (k ** 3 / 3.0 + 3.0 * k * k), D * (npair * p + n * p),
         "m = (U'F)'(w.U'y), then p Cholesky factorisations + 3 solves of order k (latency bound: dependency chains of 8x8 tiles)")
     add("means", 2.0 * br * p * k, D * 6 * br * p,
