@@ -541,6 +541,7 @@ def run_ours(args):
     if live_k:
         args.no_exact_leg = True          # k moves under update_k: the fixed-k roofline legs do not apply
     npairs = k_now * (k_now + 1) // 2
+    pl_local = sw.pl
     if gstats["mode"] == "expsum":
         # dominant tensor kernel: the trait product Q = (G'A)' E, M = k(k+1)/2, N = p_local, K = R nodes
         kern_flop = 2 * npairs * gstats["terms"] * sw.pl
@@ -630,7 +631,7 @@ def run_ours(args):
                      "flop_per_launch": kern_flop, "ms_per_launch": kern_ms, "peak_source": peak_src,
                      "dmma_issue_peak_tflops": 37.1},
         "phases_ms_last_iter": phases,
-        "iteration_roofline": iteration_roofline(n, sw.pl, k_now, 1, phases, gstats, peak_tf, dev_ms / args.steps),
+        "iteration_roofline": iteration_roofline(n, pl_local, k_now, 1, phases, gstats, peak_tf, dev_ms / args.steps),
         "sweep_algorithmic_tflops": algorithmic_flops(n, p, k) / world / (dev_ms / args.steps * 1e-3) * 1e-12,
         "sweep_algorithmic_tflops_note": "SURVEY.md 8d W_flop of the exact formulation (k(k+1)np weighted Gram) per GPU / time; in expsum "
                                          "mode fewer FLOPs are executed, so this can exceed the FP64 peak",

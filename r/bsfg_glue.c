@@ -175,6 +175,7 @@ static void fill_state(bsfg_state* st, SEXP cs, int k, int nrun) {
 }
 SEXP R_bsfg_set_state(SEXP ptr, SEXP cs) {
     bsfg_state st;
+    memset(&st, 0, sizeof st);      /* px_factor / F_px stay NULL: bsfg_set_state reads them as "not a px chain" */
     fill_state(&st, cs, Rf_ncols(member(cs, "F")), Rf_asInteger(member(cs, "nrun")));
     chk(bsfg_set_state((bsfg_ctx*)R_ExternalPtrAddr(ptr), &st));
     return R_NilValue;

@@ -185,7 +185,13 @@ enum Site : uint32_t {
     SITE_Z_MEANS_W = 13,   // randn(r2,p)           :68 (second call, fast_BSFG_sampler.R:214)
     SITE_G_W = 14,         // rgamma(p)             fast_BSFG_sampler.R:249
     SITE_Z_Y = 15,         // rnorm(p*n)            fast_BSFG_sampler.R:182 (missing phenotypes)
-    SITE_G_PX = 16         // rgamma(k)             fast_BSFG_sampler_px.R:263
+    SITE_G_PX = 16,        // rgamma(k)             fast_BSFG_sampler_px.R:263
+    // the vector draws of the add-a-factor arm each have their own site: Gamma draws address Philox blocks by element and
+    // normal draws by element PAIR, so two families on one site would share blocks (SITE_K_ADD keeps the three scalars)
+    SITE_K_ADD_LP = 17,    // rgamma(p)             BSFG_functions.R:336
+    SITE_K_ADD_ZL = 18,    // rnorm(p)              :338
+    SITE_K_ADD_ZFA = 19,   // rnorm(r)              :340
+    SITE_K_ADD_ZF = 20     // rnorm(n)              :341
 };
 
 struct RngStream {

@@ -679,11 +679,11 @@ static bool update_k_apply(KRefs& s, long i, double uu, const KAddVariates* inj)
         VarSrc g_lp, z_lam, z_fa, z_f;
         if (inj) { g_lp = inj->g_lp; z_lam = inj->z_lam; z_fa = inj->z_fa; z_f = inj->z_f; }
         else {
-            // element ranges of the SITE_K_ADD stream: [2, 2+p) g_lp, [2+p, 2+2p) z_lambda, then z_Fa (r), z_F (n)
-            g_lp = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + s.p_off, 1);
-            z_lam = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + (long)s.p_total + s.p_off, 1);
-            z_fa = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * s.p_total, 1);
-            z_f = make_var(nullptr, s.seed, SITE_K_ADD, (uint32_t)i, 2 + 2L * s.p_total + r, 1);
+            // one Philox site per draw family (element = global trait / individual index), scalars on SITE_K_ADD
+            g_lp = make_var(nullptr, s.seed, SITE_K_ADD_LP, (uint32_t)i, s.p_off, 1);
+            z_lam = make_var(nullptr, s.seed, SITE_K_ADD_ZL, (uint32_t)i, s.p_off, 1);
+            z_fa = make_var(nullptr, s.seed, SITE_K_ADD_ZFA, (uint32_t)i, 0, 1);
+            z_f = make_var(nullptr, s.seed, SITE_K_ADD_ZF, (uint32_t)i, 0, 1);
         }
         addk_traits_kernel<<<std::min(ceil_div(pl, 256), d.sms * 4), 256, 0, d.st>>>(
             pl, h, pri.Lambda_df, tauh[k], g_lp, z_lam, s.LP->p, s.LP->ld, s.Lam->p, s.Lam->ld, s.Lt ? s.Lt->p : nullptr,

@@ -969,8 +969,8 @@ static int sweep_impl(bsfg_ctx* c, int n_iter, bool px) {
         c->phase_timing = (it == n_iter - 1);
         gibbs_iteration(c, v, false, px);
         RngStream rs{seed, SITE_U_K, ii};
+        c->iter = i;             // the Gibbs body of iteration i has run: an update_k failure must not leave the chain half-stepped
         update_k_step(c, i, philox_uniform(rs, 0), nullptr);               // uu = runif(1) every iteration, R:325
-        c->iter = i;
     }
     finish_timing(c, launches_before, n_iter);
     BSFG_API_END
@@ -1164,8 +1164,8 @@ static int sweep_injected_impl(bsfg_ctx* c, const bsfg_variates* hv, bool px) {
         ka.z_f = mk(c->v_kadd.p + 2L * pl + r);
         ka.g_delta = *hv->k_g_delta; ka.u_h2 = *hv->k_u_h2; ka.g_px = px ? *hv->k_g_px : 1.0; ka.have_scalars = true;
     }
-    update_k_step(c, i, uu, have_add ? &ka : nullptr);
     c->iter = i;
+    update_k_step(c, i, uu, have_add ? &ka : nullptr);
     finish_timing(c, launches_before, 1);
     BSFG_API_END
 }

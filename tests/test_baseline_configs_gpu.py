@@ -58,3 +58,47 @@ def test_C4_shape_properties_k100():
     oracle finishes in seconds, both Gram evaluations."""
     _parity(300, 400, 100, "random", 401, gram="expsum")
     _parity(300, 400, 100, "random", 401, gram="exact")
+
+
+def test_C4_full_size_one_iteration_n5000_p20000_k100():
+    """BASELINE.json configs[3] / the `metric` workload at FULL size: one injected-variate Gibbs iteration of the device path
+    (both weighted-Gram evaluations: the 256-node exponential sum that is the default, and the exact reference order) against
+    the compiled reference (`oracle/_ref`: sample_Lambda_c over 20000 traits with n = 5000-term sums, the dense Z_1 E_a
+    products and the p x p `t(E_a) Ainv E_a` of fast_BSFG_sampler.R:245) -- about a minute of host time.  The problem is
+    bench.py's own (random 3-generation pedigree, prior-drawn state: tauh spans many decades).  Row-wise 1e-9, exact h2
+    indices, no fallback of the exponential sum."""
+    import bench
+    from oracle import checker as O, init_oracle as I
+    from sparsefactormixedmodel_b200 import BSFGSweep
+    n, p, k = bench.WORKLOADS["C4"]
+    d, rv, pri, rp, cs = bench.make_problem(n, p, k, device="cuda:0")
+    v = I.draw_variates(np.random.default_rng(4004), n, p, k, n, rv["b"] + n, pri)
+    ora, aux = O.gibbs_iteration(d, rv, pri, rp, cs, 1, v)
+    for gram in ("expsum", "exact"):
+        sw = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=k, gram=gram)
+        try:
+            sw.set_state(cs)
+            sw.sweep_injected(v)
+            dev = sw.get_state()
+            assert rowwise_relerr(dev["Lambda"], ora["Lambda"]) < TOL, gram
+            assert rowwise_relerr(dev["F"], ora["F"]) < TOL, gram
+            assert rowwise_relerr(dev["F_a"].T, ora["F_a"].T) < TOL, gram
+            assert np.array_equal(dev["F_h2"], np.asarray(ora["F_h2"]).ravel()), gram
+            assert relerr(dev["B"], ora["B"].reshape(dev["B"].shape)) < TOL, gram
+            assert rowwise_relerr(dev["E_a"].T, ora["E_a"].T) < TOL, gram
+            for f in ("Lambda_prec", "resid_Y_prec", "E_a_prec", "delta", "tauh"):
+                assert relerr(dev[f], ora[f]) < TOL, (gram, f)
+            a = sw.aux()
+            assert relerr(a["resid_Y_prec_rate"], aux["resid_Y_prec_rate"]) < TOL, gram
+            assert relerr(a["E_a_prec_rate"], aux["E_a_prec_rate"]) < TOL, gram
+            gs = sw.gram_stats()
+            assert gs["mode"] == gram and gs["fallbacks"] == 0
+        finally:
+            sw.close()
+
+
+def test_C5_factor_count_k200():
+    """C5's factor count (k = 200: the 8-warp Cholesky with 26 block rows, 190 KB of tiles per system) at a size the
+    reference finishes in seconds (n = 2000, p = 3000), both Gram evaluations."""
+    _parity(2000, 3000, 200, "random", 501, gram="expsum")
+    _parity(2000, 3000, 200, "random", 501, gram="exact")
