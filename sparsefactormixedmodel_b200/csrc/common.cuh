@@ -168,6 +168,18 @@ __host__ __device__ inline double u01_from_bits(uint32_t hi, uint32_t lo) {
     return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// 1/sqrt(x) to ~1 ulp without the special-case handling of CUDA's rsqrt(double): the hardware seed (MUFU.RSQ64H,
+// relative error 2^-22) and ONE third-order step y <- y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 (error (5/16) e^3 ~ 2^-67):
+// four dependent FP64 operations after the seed.  x > 0 finite and normal is the caller's business.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);
+}
+
 // draw sites (the `site` word of the Philox counter); one per reference RNG call site
 enum Site : uint32_t {
     SITE_Z_LAMBDA = 1,     // randn(k,p)            BSFG_functions_c.cpp:110

@@ -318,58 +318,101 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 // sample_means element-wise step (cpp:75-78 without the U product):
 //   theta[i,j] = (DtYt[i,j] * rp_j) / d + z[i,j] / sqrt(d),  d = s1_i ep_j + s2_i rp_j
 // ------------------------------------------------------------------------------------
-// One CTA per trait.  When Bout != null the first b (<= MEANS_BMAX) rows of location_sample = U theta (cpp:78),
-// i.e. B (fast_BSFG_sampler.R:206), are reduced in the same pass: B[c,j] = sum_i U[c,i] theta[i,j], U given
-// transposed (Ut[i,c], column c contiguous).
+// One CTA per MEANS_TC = 4 consecutive traits, rows in chunks of MEANS_CH = 512 (two per thread).  Besides theta (br x p)
+// the kernel writes theta' (p x br; the K = p operand of theta Lmsg, R:230) when thetat != null: the chunk is staged in
+// shared memory and stored with the 4 traits of a row side by side -- one full 32-byte sector per row instead of a
+// separate transpose pass over the whole array.  When Bout != null the first b (<= MEANS_BMAX) rows of
+// location_sample = U theta (cpp:78), i.e. B (fast_BSFG_sampler.R:206), are reduced in the same pass:
+// B[c,j] = sum_i U[c,i] theta[i,j], U given transposed (Ut[i,c], column c contiguous).
+// Philox draws: a thread owns the element pair that shares one Philox block (even stream index first); the stream index
+// of element (i, j) is (j + col_offset) rows_total + i, so for odd rows_total the pairs of odd traits start at row -1:
+// those columns run one extra pair per chunk (thread 0) and keep only the rows of the chunk.
 constexpr int MEANS_BMAX = 4;
+constexpr int MEANS_TC = 4;
+constexpr int MEANS_CH = 512;
 __global__ void __launch_bounds__(256)
 means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
                    const double* __restrict__ s1, const double* __restrict__ s2,
                    const double* __restrict__ rp, const double* __restrict__ ep, VarSrc zsrc,
-                   double* __restrict__ theta, long ldt,
+                   double* __restrict__ theta, long ldt, double* __restrict__ thetat, long ldtt,
                    const double* __restrict__ Ut, long ldu, int b, double* __restrict__ Bout, long ldb) {
     __shared__ double red[32];
-    const int j = blockIdx.x;
-    if (j >= p) return;
-    const double rpj = rp[j], epj = ep[j];
-    double acc[MEANS_BMAX];
+    __shared__ double tile[MEANS_TC][MEANS_CH + 2];               // [trait][row in chunk]: conflict-free in both directions
+    const int j0 = blockIdx.x * MEANS_TC;
+    if (j0 >= p) return;
+    const int nc = min(MEANS_TC, p - j0);
+    double rpj[MEANS_TC], epj[MEANS_TC];
+    long base[MEANS_TC];
 #pragma unroll
-    for (int c = 0; c < MEANS_BMAX; c++) acc[c] = 0.0;
-    // each thread owns Philox-aligned element pairs (rows r0, r0+1 with an even stream index) -> one block per 2 draws
-    const long base = zsrc.ptr ? 0 : (long)(j + zsrc.col_offset) * zsrc.rows_total;
-    const int par = (int)(base & 1);
-    for (int t = threadIdx.x; 2 * t - par < br; t += blockDim.x) {
-        const int r0 = 2 * t - par;
-        double z[2];
-        if (zsrc.ptr) {
-            z[0] = (r0 >= 0) ? zsrc.ptr[(long)j * zsrc.ld + r0] : 0.0;
-            z[1] = (r0 + 1 < br) ? zsrc.ptr[(long)j * zsrc.ld + r0 + 1] : 0.0;
-        } else {
-            philox_normal_pair(zsrc.rs, (uint64_t)((base + r0) >> 1), &z[0], &z[1]);
-        }
+    for (int c = 0; c < MEANS_TC; c++) {
+        const int j = min(j0 + c, p - 1);
+        rpj[c] = rp[j]; epj[c] = ep[j];
+        base[c] = zsrc.ptr ? 0 : (long)(j + zsrc.col_offset) * zsrc.rows_total;
+    }
+    double acc[MEANS_TC][MEANS_BMAX];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int i = r0 + e;
-            if (i < 0 || i >= br) continue;
-            // mean = (v rp)/d, noise = z/sqrt(d) with one reciprocal square root r = d^-1/2 instead of a division, a
-            // square root and another division (cpp:76-78; the draw is compute bound on the FP64 pipe)
-            const double d = s1[i] * epj + s2[i] * rpj;
-            const double r = rsqrt(d);
-            const double th = ((DtYt[(long)j * ldd + i] * rpj) * r + z[e]) * r;
-            theta[(long)j * ldt + i] = th;
-            if (Bout) {
+    for (int c = 0; c < MEANS_TC; c++)
 #pragma unroll
-                for (int c = 0; c < MEANS_BMAX; c++)
-                    if (c < b) acc[c] += Ut[(long)c * ldu + i] * th;
+        for (int cc = 0; cc < MEANS_BMAX; cc++) acc[c][cc] = 0.0;
+    for (int c0 = 0; c0 < br; c0 += MEANS_CH) {
+        const int hi = min(c0 + MEANS_CH, br);
+#pragma unroll
+        for (int c = 0; c < MEANS_TC; c++) {
+            if (c >= nc) break;
+            const int j = j0 + c;
+            const int par = (int)(base[c] & 1);
+            for (int t = threadIdx.x; t < MEANS_CH / 2 + par; t += blockDim.x) {
+                const int r0 = c0 + 2 * t - par;                 // base + r0 is even: rows r0, r0 + 1 share one Philox block
+                if (r0 >= hi) break;
+                double z[2];
+                if (zsrc.ptr) {
+                    z[0] = (r0 >= c0) ? zsrc.ptr[(long)j * zsrc.ld + r0] : 0.0;
+                    z[1] = (r0 + 1 < hi) ? zsrc.ptr[(long)j * zsrc.ld + r0 + 1] : 0.0;
+                } else {
+                    philox_normal_pair(zsrc.rs, (uint64_t)((base[c] + r0) >> 1), &z[0], &z[1]);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int i = r0 + e;
+                    if (i < c0 || i >= hi) continue;
+                    // mean = (v rp)/d, noise = z/sqrt(d) with one reciprocal square root r = d^-1/2 instead of a division, a
+                    // square root and another division (cpp:76-78; the draw is compute bound on the FP64 pipe)
+                    const double d = s1[i] * epj[c] + s2[i] * rpj[c];
+                    const double r = fast_rsqrt(d);
+                    const double th = ((DtYt[(long)j * ldd + i] * rpj[c]) * r + z[e]) * r;
+                    theta[(long)j * ldt + i] = th;
+                    if (thetat) tile[c][i - c0] = th;
+                    if (Bout) {
+#pragma unroll
+                        for (int cc = 0; cc < MEANS_BMAX; cc++)
+                            if (cc < b) acc[c][cc] += Ut[(long)cc * ldu + i] * th;
+                    }
+                }
             }
+        }
+        if (thetat) {
+            __syncthreads();
+            for (int u = threadIdx.x; u < hi - c0; u += blockDim.x) {
+                double* dst = thetat + (long)(c0 + u) * ldtt + j0;     // ldtt even and j0 % 4 == 0: 16-byte aligned
+                if (nc == MEANS_TC) {
+                    reinterpret_cast<double2*>(dst)[0] = make_double2(tile[0][u], tile[1][u]);
+                    reinterpret_cast<double2*>(dst)[1] = make_double2(tile[2][u], tile[3][u]);
+                } else {
+                    for (int c = 0; c < nc; c++) dst[c] = tile[c][u];
+                }
+            }
+            __syncthreads();
         }
     }
     if (Bout) {
 #pragma unroll
-        for (int c = 0; c < MEANS_BMAX; c++) {
-            if (c < b) {
-                const double v = block_sum(acc[c], red);
-                if (threadIdx.x == 0) Bout[(long)j * ldb + c] = v;
+        for (int c = 0; c < MEANS_TC; c++) {
+#pragma unroll
+            for (int cc = 0; cc < MEANS_BMAX; cc++) {
+                if (cc < b && c < nc) {                              // uniform over the CTA
+                    const double v = block_sum(acc[c][cc], red);
+                    if (threadIdx.x == 0) Bout[(long)(j0 + c) * ldb + cc] = v;
+                }
             }
         }
     }

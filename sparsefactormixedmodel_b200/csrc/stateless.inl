@@ -411,8 +411,8 @@ extern "C" int bsfg_sample_means_c(const double* Y_tilde, int n, int p, const do
     d.gemm(1.0, dD, dY, 0.0, DtY);                       // Design_U' Y_tilde, cpp:65
     VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_MEANS, 0, 0, br);
     {
-        means_theta_kernel<<<p, 256, 0, d.st>>>(DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p, theta.ld,
-                                                nullptr, 0, 0, nullptr, 0);
+        means_theta_kernel<<<ceil_div(p, MEANS_TC), 256, 0, d.st>>>(DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p,
+                                                                    theta.ld, nullptr, 0, nullptr, 0, 0, nullptr, 0);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
     d.transpose(dU, dUt);

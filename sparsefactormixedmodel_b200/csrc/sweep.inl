@@ -74,7 +74,7 @@ struct bsfg_ctx {
     double resid_s1 = -1, resid_s2 = -1;
     long iter = 0;                // current_state$nrun
     // constants
-    bsfg::DMat UtY, UtYt, DtY, U1, U1t, UtX, U2, U2t, DU, DUt, U3, U3t, Z1, Z1t, M1, M2;
+    bsfg::DMat UtY, Yt, DtY, U1, UtX, U2, U2t, DU, DUt, U3, U3t, Z1, Z1t, M1, M2;
     bsfg::DVec yy, s, s1_2, s2_2, s1_3, s2_3, h2_prior;
     // state (factor-indexed storage has kmax columns / rows)
     bsfg::DMat Lt, Lam, Lmsg, LP, Plamt, Ptmp, F, Fa, Bfix, theta, thetat, Ea_in;
@@ -227,7 +227,7 @@ static void refresh_derived(bsfg_ctx* c) {
 static void rotate_data(bsfg_ctx* c, const DMat& Y) {
     Device& d = c->dev;
     d.gemm(1.0, c->U1, Y, 0.0, c->UtY);
-    d.transpose(c->UtY, c->UtYt);
+    d.transpose(Y, c->Yt);                     // Y' (p x n): the K = p operand of Y_tilde Lmsg (cpp:149)
     d.gemm(1.0, c->DU, Y, 0.0, c->DtY);
     if (c->r2 > 0) d.gemm(1.0, c->Z2, Y, 0.0, c->Z2tY);
     colsumsq_kernel<<<ceil_div((long)c->pl * 32, 256), 256, 0, d.st>>>(Y.p, Y.ld, c->n, c->pl, c->yy.p);
@@ -305,16 +305,16 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
                  c->tmp_brp.p, c->tmp_brp.ld, d.ws.p, Device::WS_DOUBLES);
     {
         const bool fuse_b = b > 0 && b <= MEANS_BMAX;      // B = location_sample[1:b,] (R:206) reduced in the same pass
-        means_theta_kernel<<<pl, 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
-                                                 c->ep.p, v.zM, c->theta.p, c->theta.ld, c->U2t.p, c->U2t.ld, b,
-                                                 fuse_b ? c->Bfix.p : nullptr, c->Bfix.ld);
+        // theta and theta' (the K = p operand of step 6) leave the same kernel: no transpose pass over the br x p array
+        means_theta_kernel<<<ceil_div(pl, MEANS_TC), 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
+                                                                     c->ep.p, v.zM, c->theta.p, c->theta.ld, c->thetat.p, c->thetat.ld,
+                                                                     c->U2t.p, c->U2t.ld, b, fuse_b ? c->Bfix.p : nullptr, c->Bfix.ld);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         if (b > 0 && !fuse_b) {
             DMat U2Bt = view(c->U2t, br, b);               // first b columns of U2' = rows 0..b-1 of U2
             d.gemm(1.0, U2Bt, c->theta, 0.0, c->Bfix);
         }
     }
-    d.transpose(c->theta, c->thetat);
     c->theta_valid = true;
     // 3. W | B, E_a, F, Lambda: second sample_means_c call, with W_prec and the rand2 list    R:211-216
     //    Design_U2'(Y - X B - Z_1 E_a - F Lambda') = Uw'[Z_2'Y - (Z_2'Design_U) theta - (Z_2'F) Lambda']
@@ -325,8 +325,8 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
                  d.ws.p, Device::WS_DOUBLES);                                             // Z_2'Y - Z_2'F Lambda'
         d.gemm(1.0, c->Uw, c->gW, 0.0, c->tmpw);
         d.gemm(-1.0, c->Uw, c->Z2DUth, 1.0, c->tmpw);
-        means_theta_kernel<<<pl, 256, 0, d.st>>>(c->tmpw.p, c->tmpw.ld, r2, pl, c->s1w.p, c->s2w.p, c->rp.p, c->wp.p, v.zW,
-                                                 c->thw.p, c->thw.ld, nullptr, 0, 0, nullptr, 0);
+        means_theta_kernel<<<ceil_div(pl, MEANS_TC), 256, 0, d.st>>>(c->tmpw.p, c->tmpw.ld, r2, pl, c->s1w.p, c->s2w.p, c->rp.p, c->wp.p,
+                                                                     v.zW, c->thw.p, c->thw.ld, nullptr, 0, nullptr, 0, 0, nullptr, 0);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
         d.gemm(1.0, c->Uwt, c->thw, 0.0, c->W);                                            // W = U theta_w (cpp:78)
         d.transpose(c->W, c->Wt);
@@ -363,7 +363,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     DMat P1 = view_at(c->red1.p + o1, n, k, c->red1.ld);
     DMat P2 = view_at(c->red1.p + o2, br, k, c->red1.ld);
     d.gemm(1.0, Lam, Lmsg, 0.0, LtL);
-    d.gemm(1.0, c->UtYt, Lmsg, 0.0, P1);
+    d.gemm(1.0, c->Yt, Lmsg, 0.0, P1);                      // Y Lmsg in original coordinates (U U' = I: no rotation needed here)
     d.gemm(1.0, c->thetat, Lmsg, 0.0, P2);
     const long o3 = o2 + round_up(br, 2);
     DMat P3 = view_at(c->red1.p + o3, r2, k, c->red1.ld);
@@ -376,8 +376,9 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
         // then the blocks are all-gathered (bit-identical F on every rank)
         DMat YL = view(c->YL, n, k);
         const RowShard sn = row_shard(c, n);
-        gemm_rows(c, sn, 1.0, c->U1t, P1, 0.0, YL);
-        gemm_rows(c, sn, -1.0, c->DUt, P2, 1.0, YL);
+        if (sn.cnt > 0)                                                                  // YL = Y Lmsg - Design_U (theta Lmsg)
+            dgemm_tn(d.st, d.sms, (int)sn.cnt, k, br, -1.0, c->DUt.p + sn.lo * c->DUt.ld, c->DUt.ld, P2.p, P2.ld, 1.0,
+                     P1.p + sn.lo, P1.ld, YL.p + sn.lo, YL.ld, d.ws.p, Device::WS_DOUBLES);
         if (r2 > 0) gemm_rows(c, sn, -1.0, c->Z2t, P3, 1.0, YL);                         // ... - Z_2 W Lmsg  (R:230)
         // px sweep: F_a_px = F_a * sqrt(px), tau_e = 1 / (px (1 - F_h2))          fast_BSFG_sampler_px.R:249-250
         DMat Fa_use = px ? view(c->T1, r, k) : view(c->Fa, r, k);
@@ -618,14 +619,14 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
     const int n = c->n, pl = c->pl, r = c->r, b = c->b, br = c->br;
     if (b > 0) REQUIRE_PTR(k->X);
     if (!c->z1_identity) REQUIRE_PTR(k->Z_1);
-    c->U1.alloc(n, n); c->U1t.alloc(n, n); c->U2.alloc(br, br); c->U2t.alloc(br, br); c->DU.alloc(n, br); c->DUt.alloc(br, n);
+    c->U1.alloc(n, n); c->U2.alloc(br, br); c->U2t.alloc(br, br); c->DU.alloc(n, br); c->DUt.alloc(br, n);
     c->U3.alloc(r, r); c->U3t.alloc(r, r);
     c->s.alloc(n); c->s1_2.alloc(br); c->s2_2.alloc(br); c->s1_3.alloc(r); c->s2_3.alloc(r);
     c->U1.upload(k->U1, d.st); c->U2.upload(k->U2, d.st); c->DU.upload(k->Design_U, d.st); c->U3.upload(k->U3, d.st);
     host_minmax(k->s, n, &c->gram.s_min, &c->gram.s_max);
     c->s.upload(k->s, d.st); c->s1_2.upload(k->s1_2, d.st); c->s2_2.upload(k->s2_2, d.st);
     c->s1_3.upload(k->s1_3, d.st); c->s2_3.upload(k->s2_3, d.st);
-    d.transpose(c->U1, c->U1t); d.transpose(c->U2, c->U2t); d.transpose(c->DU, c->DUt); d.transpose(c->U3, c->U3t);
+    d.transpose(c->U2, c->U2t); d.transpose(c->DU, c->DUt); d.transpose(c->U3, c->U3t);
     if (!c->z1_identity) {
         c->Z1.alloc(n, r); c->Z1t.alloc(r, n);
         c->Z1.upload(k->Z_1, d.st);
@@ -657,7 +658,7 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
         const size_t total = (size_t)n * (size_t)pl;
         for (size_t e = 0; e < total; e++)
             if (k->Y[e] != k->Y[e]) { c->has_missing = true; break; }       // is.na(Y), fast_BSFG_sampler_init.R:69
-        c->UtY.alloc(n, pl); c->UtYt.alloc(pl, n); c->DtY.alloc(br, pl);
+        c->UtY.alloc(n, pl); c->Yt.alloc(pl, n); c->DtY.alloc(br, pl);
         if (c->r2 > 0) c->Z2tY.alloc(c->r2, pl);
         if (c->has_missing) {
             // rotated data are rebuilt after every imputation; keep Y itself (NaN = missing) on the device

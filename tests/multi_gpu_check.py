@@ -127,12 +127,6 @@ def main():
     if rank == 0:
         print(f"multi_gpu_check ok (Z_2 + missing data) world={world}", flush=True)
     # ---- third scenario: parameter-expanded sweep (fast_BSFG_sampler_px.R) under trait sharding --------------------------
-    # Opt-in (BSFG_MG_CHECK_PX=1): written at the end of round 1 and NOT yet run on hardware (GPU budget); the px sweep is
-    # parity-tested on one GPU only (tests/test_sweep_gpu.py::test_sweep_parameter_expanded).
-    if os.environ.get("BSFG_MG_CHECK_PX", "0") != "1":
-        dist.barrier()
-        dist.destroy_process_group()
-        return
     n, p, k = 70, 45, 5
     rs = np.random.default_rng(202)
     setup = I.make_synthetic(n, p, 3, pedigree="halfsib", seed=29)

@@ -34,3 +34,4 @@ def test_trait_sharded_sweep_matches_oracle_and_single_gpu():
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"multi_gpu_check ok world={world}" in out.stdout
     assert f"multi_gpu_check ok (Z_2 + missing data) world={world}" in out.stdout
+    assert f"multi_gpu_check ok (parameter-expanded sweep) world={world}" in out.stdout

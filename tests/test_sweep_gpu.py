@@ -169,7 +169,9 @@ def test_sweep_missing_phenotypes(with_z2):
             ora, aux = O.gibbs_iteration(d, rv, pri, rp, ora, it, v)
             sw.sweep_injected(v)
             a = sw.aux()
-            assert relerr(a["Y_imputed"], aux["Y_imputed"]) < 1e-8
+            # iteration 1 starts from the same state: the north-star 1e-9; iterations 2, 3 run free (no re-synchronisation),
+            # the imputation then sees the device's own theta and the difference compounds by about 10x per iteration
+            assert relerr(a["Y_imputed"], aux["Y_imputed"]) < (1e-9 if it == 1 else 1e-8), it
             assert np.array_equal(a["Y_imputed"][~np.isnan(Y)], Y[~np.isnan(Y)])      # observed entries untouched
         dev = sw.get_state()
         _compare_states(dev, ora, 1, tol=1e-7)
@@ -458,9 +460,10 @@ def test_update_k_px_add_and_drop():
             k2 = ora["F"].shape[1]
             seen.add("add" if k2 > kk else ("drop" if k2 < kk else "same"))
             assert dev["F"].shape[1] == k2
-            assert rowwise_relerr(dev["F_px"], ora["F_px"]) < 1e-8 and relerr(dev["px_factor"], ora["px_factor"]) < 1e-8
-            assert rowwise_relerr(dev["Lambda"], ora["Lambda"]) < 1e-8 and relerr(dev["Plam"], ora["Plam"]) < 1e-8
-            assert relerr(dev["delta"], ora["delta"]) < 1e-8
+            errs = dict(F_px=rowwise_relerr(dev["F_px"], ora["F_px"]), px_factor=relerr(dev["px_factor"], ora["px_factor"]),
+                        Lambda=rowwise_relerr(dev["Lambda"], ora["Lambda"]), Plam=relerr(dev["Plam"], ora["Plam"]),
+                        delta=relerr(dev["delta"], ora["delta"]))
+            assert max(errs.values()) < TOL, (it, errs)             # state re-synchronised every iteration: the 1e-9 bar
             sw.set_state(ora)
         assert {"add", "drop"} <= seen, seen
     finally:
