@@ -162,10 +162,20 @@ struct Philox {
     }
 };
 
-// two 32-bit words -> U(0,1) double strictly inside (0,1) (53-bit mantissa, half-ulp offset)
+// two 32-bit words -> U(0,1) double strictly inside (0,1): the top 52 bits become the mantissa of a double in [1, 2)
+// (two shifts and an OR instead of a 64-bit integer -> double conversion), minus 1, plus half a grid step:
+// values (m + 1/2) 2^-52, m = 0 .. 2^52 - 1.
 __host__ __device__ inline double u01_from_bits(uint32_t hi, uint32_t lo) {
-    uint64_t x = ((uint64_t)hi << 32) | lo;
-    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const uint32_t mh = 0x3FF00000u | (hi >> 12);
+    const uint32_t ml = (hi << 20) | (lo >> 12);
+#ifdef __CUDA_ARCH__
+    const double d = __hiloint2double((int)mh, (int)ml);
+#else
+    const uint64_t bits = ((uint64_t)mh << 32) | ml;
+    double d;
+    memcpy(&d, &bits, sizeof d);
+#endif
+    return (d - 1.0) + 1.1102230246251565e-16;      // + 2^-53
 }
 
 // 1/sqrt(x) to ~1 ulp without the special-case handling of CUDA's rsqrt(double): the hardware seed (MUFU.RSQ64H,

@@ -125,18 +125,29 @@ __global__ void lambda_weights_kernel(const double* __restrict__ UtY, long ldy, 
     const double c = epj / rp[j];
     double bj[4] = {0.0, 0.0, 0.0, 0.0};
     for (int cc = 0; cc < b && cc < 4; cc++) bj[cc] = B[(long)j * ldb + cc];
+    // UtY, UtX, W, WY are DMat storage (even leading dimension, zero pad row): rows are processed as 16-byte pairs
     const double* __restrict__ ycol = UtY + (long)j * ldy;
     double* __restrict__ wycol = WY + (long)j * ldwy;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double w = epj / (s[i] + c);
-        double y = ycol[i];
+    double* __restrict__ wcol = write_w ? W + (long)j * ldw : nullptr;
+#pragma unroll 2
+    for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x) {
+        const bool has1 = i + 1 < n;
+        const double w0 = epj / (s[i] + c);
+        const double w1 = has1 ? epj / (s[i + 1] + c) : 0.0;
+        double2 y = *reinterpret_cast<const double2*>(ycol + i);
 #pragma unroll
         for (int cc = 0; cc < 4; cc++)
-            if (cc < b) y -= UtX[(long)cc * ldx + i] * bj[cc];
-        for (int cc = 4; cc < b; cc++) y -= UtX[(long)cc * ldx + i] * B[(long)j * ldb + cc];
-        if (write_w) W[(long)j * ldw + i] = w;
-        wycol[i] = w * y;
+            if (cc < b) {
+                const double2 x = *reinterpret_cast<const double2*>(UtX + (long)cc * ldx + i);
+                y.x -= x.x * bj[cc]; y.y -= x.y * bj[cc];
+            }
+        for (int cc = 4; cc < b; cc++) {
+            const double bb = B[(long)j * ldb + cc];
+            y.x -= UtX[(long)cc * ldx + i] * bb;
+            if (has1) y.y -= UtX[(long)cc * ldx + i + 1] * bb;
+        }
+        if (write_w) *reinterpret_cast<double2*>(wcol + i) = make_double2(w0, w1);
+        *reinterpret_cast<double2*>(wycol + i) = make_double2(w0 * y.x, w1 * y.y);
     }
 }
 
@@ -318,100 +329,156 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 // sample_means element-wise step (cpp:75-78 without the U product):
 //   theta[i,j] = (DtYt[i,j] * rp_j) / d + z[i,j] / sqrt(d),  d = s1_i ep_j + s2_i rp_j
 // ------------------------------------------------------------------------------------
-// One CTA per MEANS_TC = 4 consecutive traits, rows in chunks of MEANS_CH = 512 (two per thread).  Besides theta (br x p)
-// the kernel writes theta' (p x br; the K = p operand of theta Lmsg, R:230) when thetat != null: the chunk is staged in
-// shared memory and stored with the 4 traits of a row side by side -- one full 32-byte sector per row instead of a
-// separate transpose pass over the whole array.  When Bout != null the first b (<= MEANS_BMAX) rows of
-// location_sample = U theta (cpp:78), i.e. B (fast_BSFG_sampler.R:206), are reduced in the same pass:
-// B[c,j] = sum_i U[c,i] theta[i,j], U given transposed (Ut[i,c], column c contiguous).
-// Philox draws: a thread owns the element pair that shares one Philox block (even stream index first); the stream index
-// of element (i, j) is (j + col_offset) rows_total + i, so for odd rows_total the pairs of odd traits start at row -1:
-// those columns run one extra pair per chunk (thread 0) and keep only the rows of the chunk.
+// One CTA per MEANS_TC = 16 consecutive traits.  A warp covers a 16-row x 16-trait tile: lane (rp, cg) owns the row pair
+// (2 rp, 2 rp + 1) of the four traits 4 cg .. 4 cg + 3, so
+//   * the two rows of a pair share one Philox block (one Box-Muller transform per two draws),
+//   * DtYt is read and theta written as 16-byte pairs, 8 lanes side by side = one 128-byte line per trait,
+//   * theta' (p x br; the K = p operand of theta Lmsg, R:230), when thetat != null, is written from the same registers as
+//     32 bytes per lane, 4 lanes side by side = one 128-byte line per row -- no transpose pass over the br x p array.
+// When Bout != null the first b (<= MEANS_BMAX) rows of location_sample = U theta (cpp:78), i.e. B
+// (fast_BSFG_sampler.R:206), are reduced in the same pass: B[c,j] = sum_i U[c,i] theta[i,j], U given transposed
+// (Ut[i,c], column c contiguous); fixed summation order (shuffles, then warps in order).
+// DtYt and theta are DMat storage (even leading dimension, zero pad row): the pair access of the last odd row is in bounds.
+// Philox draws: element (i, j) has stream index (j + col_offset) rows_total + i; callers pass an even rows_total so that a
+// row pair is one aligned Philox pair (an odd rows_total falls back to one block per draw).
 constexpr int MEANS_BMAX = 4;
-constexpr int MEANS_TC = 4;
-constexpr int MEANS_CH = 512;
-__global__ void __launch_bounds__(256)
+constexpr int MEANS_TC = 16;
+constexpr int MEANS_THREADS = 128;
+// gridDim.y CTAs split the rows of a trait tile (rows_per_cta each, a multiple of 64); with Bout they leave partial sums in
+// Bpart[gridDim.y][p][MEANS_BMAX] and the last one to finish (counter[blockIdx.x], self-resetting) adds them in split order.
+__global__ void __launch_bounds__(MEANS_THREADS, 4)
 means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
                    const double* __restrict__ s1, const double* __restrict__ s2,
                    const double* __restrict__ rp, const double* __restrict__ ep, VarSrc zsrc,
                    double* __restrict__ theta, long ldt, double* __restrict__ thetat, long ldtt,
-                   const double* __restrict__ Ut, long ldu, int b, double* __restrict__ Bout, long ldb) {
-    __shared__ double red[32];
-    __shared__ double tile[MEANS_TC][MEANS_CH + 2];               // [trait][row in chunk]: conflict-free in both directions
-    const int j0 = blockIdx.x * MEANS_TC;
-    if (j0 >= p) return;
-    const int nc = min(MEANS_TC, p - j0);
-    double rpj[MEANS_TC], epj[MEANS_TC];
-    long base[MEANS_TC];
+                   const double* __restrict__ Ut, long ldu, int b, double* __restrict__ Bout, long ldb,
+                   int rows_per_cta, double* __restrict__ Bpart, int* __restrict__ counter) {
+    __shared__ double red[MEANS_THREADS / 32][MEANS_TC][MEANS_BMAX];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rpi = lane & 7, cg = lane >> 3;
+    const int j0 = blockIdx.x * MEANS_TC + cg * 4;          // first of this lane's four traits
+    const int nc = max(0, min(4, p - j0));
+    double rpj[4], epj[4];
+    const double* dcol[4];
+    double* tcol[4];
+    uint64_t base[4];
 #pragma unroll
-    for (int c = 0; c < MEANS_TC; c++) {
+    for (int c = 0; c < 4; c++) {
         const int j = min(j0 + c, p - 1);
         rpj[c] = rp[j]; epj[c] = ep[j];
-        base[c] = zsrc.ptr ? 0 : (long)(j + zsrc.col_offset) * zsrc.rows_total;
+        dcol[c] = DtYt + (long)j * ldd;
+        tcol[c] = theta + (long)j * ldt;
+        base[c] = (uint64_t)(j + zsrc.col_offset) * (uint64_t)zsrc.rows_total;
     }
-    double acc[MEANS_TC][MEANS_BMAX];
+    const bool paired = (zsrc.rows_total & 1) == 0;
+    double acc[4][MEANS_BMAX];
 #pragma unroll
-    for (int c = 0; c < MEANS_TC; c++)
+    for (int c = 0; c < 4; c++)
 #pragma unroll
         for (int cc = 0; cc < MEANS_BMAX; cc++) acc[c][cc] = 0.0;
-    for (int c0 = 0; c0 < br; c0 += MEANS_CH) {
-        const int hi = min(c0 + MEANS_CH, br);
+    const int row_lo = blockIdx.y * rows_per_cta, row_hi = min(br, row_lo + rows_per_cta);
+    for (int r0 = row_lo + (warp * 8 + rpi) * 2; r0 < row_hi; r0 += (MEANS_THREADS / 32) * 16) {
+        const bool has1 = r0 + 1 < br;
+        const double s1a = s1[r0], s2a = s2[r0];
+        const double s1b = has1 ? s1[r0 + 1] : 1.0, s2b = has1 ? s2[r0 + 1] : 1.0;
+        double ua[MEANS_BMAX], ub[MEANS_BMAX];
+        if (Bout) {
 #pragma unroll
-        for (int c = 0; c < MEANS_TC; c++) {
-            if (c >= nc) break;
-            const int j = j0 + c;
-            const int par = (int)(base[c] & 1);
-            for (int t = threadIdx.x; t < MEANS_CH / 2 + par; t += blockDim.x) {
-                const int r0 = c0 + 2 * t - par;                 // base + r0 is even: rows r0, r0 + 1 share one Philox block
-                if (r0 >= hi) break;
-                double z[2];
+            for (int cc = 0; cc < MEANS_BMAX; cc++) {
+                ua[cc] = cc < b ? Ut[(long)cc * ldu + r0] : 0.0;
+                ub[cc] = (cc < b && has1) ? Ut[(long)cc * ldu + r0 + 1] : 0.0;
+            }
+        }
+        double2 vin[4];                          // the four 16-byte loads are in flight before the first Box-Muller starts
+#pragma unroll
+        for (int c = 0; c < 4; c++) vin[c] = c < nc ? *reinterpret_cast<const double2*>(dcol[c] + r0) : make_double2(0.0, 0.0);
+        double th[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            th[c][0] = th[c][1] = 0.0;
+            if (c < nc) {
+                double z0, z1;
                 if (zsrc.ptr) {
-                    z[0] = (r0 >= c0) ? zsrc.ptr[(long)j * zsrc.ld + r0] : 0.0;
-                    z[1] = (r0 + 1 < hi) ? zsrc.ptr[(long)j * zsrc.ld + r0 + 1] : 0.0;
+                    const double* zc = zsrc.ptr + (long)(j0 + c) * zsrc.ld + r0;
+                    z0 = zc[0]; z1 = has1 ? zc[1] : 0.0;
+                } else if (paired) {
+                    philox_normal_pair(zsrc.rs, (base[c] + (uint64_t)r0) >> 1, &z0, &z1);
                 } else {
-                    philox_normal_pair(zsrc.rs, (uint64_t)((base[c] + r0) >> 1), &z[0], &z[1]);
+                    z0 = philox_normal(zsrc.rs, base[c] + (uint64_t)r0);
+                    z1 = philox_normal(zsrc.rs, base[c] + (uint64_t)r0 + 1);
                 }
+                const double2 v = vin[c];
+                // mean = (v rp)/d, noise = z/sqrt(d) with one reciprocal square root r = d^-1/2 instead of a division, a
+                // square root and another division (cpp:76-78)
+                const double ra = fast_rsqrt(s1a * epj[c] + s2a * rpj[c]);
+                const double rb = fast_rsqrt(s1b * epj[c] + s2b * rpj[c]);
+                th[c][0] = ((v.x * rpj[c]) * ra + z0) * ra;
+                th[c][1] = has1 ? ((v.y * rpj[c]) * rb + z1) * rb : 0.0;
+                *reinterpret_cast<double2*>(tcol[c] + r0) = make_double2(th[c][0], th[c][1]);
+                if (Bout) {
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int i = r0 + e;
-                    if (i < c0 || i >= hi) continue;
-                    // mean = (v rp)/d, noise = z/sqrt(d) with one reciprocal square root r = d^-1/2 instead of a division, a
-                    // square root and another division (cpp:76-78; the draw is compute bound on the FP64 pipe)
-                    const double d = s1[i] * epj[c] + s2[i] * rpj[c];
-                    const double r = fast_rsqrt(d);
-                    const double th = ((DtYt[(long)j * ldd + i] * rpj[c]) * r + z[e]) * r;
-                    theta[(long)j * ldt + i] = th;
-                    if (thetat) tile[c][i - c0] = th;
-                    if (Bout) {
-#pragma unroll
-                        for (int cc = 0; cc < MEANS_BMAX; cc++)
-                            if (cc < b) acc[c][cc] += Ut[(long)cc * ldu + i] * th;
-                    }
+                    for (int cc = 0; cc < MEANS_BMAX; cc++)
+                        if (cc < b) acc[c][cc] += ua[cc] * th[c][0] + ub[cc] * th[c][1];
                 }
             }
         }
-        if (thetat) {
-            __syncthreads();
-            for (int u = threadIdx.x; u < hi - c0; u += blockDim.x) {
-                double* dst = thetat + (long)(c0 + u) * ldtt + j0;     // ldtt even and j0 % 4 == 0: 16-byte aligned
-                if (nc == MEANS_TC) {
-                    reinterpret_cast<double2*>(dst)[0] = make_double2(tile[0][u], tile[1][u]);
-                    reinterpret_cast<double2*>(dst)[1] = make_double2(tile[2][u], tile[3][u]);
+        if (thetat && nc > 0) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (e == 1 && !has1) break;
+                double* dst = thetat + (long)(r0 + e) * ldtt + j0;       // ldtt even, j0 % 4 == 0: 16-byte aligned
+                if (nc == 4) {
+                    reinterpret_cast<double2*>(dst)[0] = make_double2(th[0][e], th[1][e]);
+                    reinterpret_cast<double2*>(dst)[1] = make_double2(th[2][e], th[3][e]);
                 } else {
-                    for (int c = 0; c < nc; c++) dst[c] = tile[c][u];
+                    for (int c = 0; c < nc; c++) dst[c] = th[c][e];
                 }
             }
-            __syncthreads();
         }
     }
     if (Bout) {
 #pragma unroll
-        for (int c = 0; c < MEANS_TC; c++) {
+        for (int c = 0; c < 4; c++)
 #pragma unroll
             for (int cc = 0; cc < MEANS_BMAX; cc++) {
-                if (cc < b && c < nc) {                              // uniform over the CTA
-                    const double v = block_sum(acc[c][cc], red);
-                    if (threadIdx.x == 0) Bout[(long)(j0 + c) * ldb + cc] = v;
+                double v = acc[c][cc];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (rpi == 0) red[warp][cg * 4 + c][cc] = v;
+            }
+        __syncthreads();
+        const bool split = gridDim.y > 1;
+        for (int idx = threadIdx.x; idx < MEANS_TC * MEANS_BMAX; idx += MEANS_THREADS) {
+            const int cl = idx / MEANS_BMAX, cc = idx % MEANS_BMAX;
+            const int j = blockIdx.x * MEANS_TC + cl;
+            if (j < p && cc < b) {
+                double v = 0.0;
+                for (int w = 0; w < MEANS_THREADS / 32; w++) v += red[w][cl][cc];
+                if (split) Bpart[((long)blockIdx.y * p + j) * MEANS_BMAX + cc] = v;
+                else Bout[(long)j * ldb + cc] = v;
+            }
+        }
+        if (split) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int t = atomicAdd(&counter[blockIdx.x], 1);
+                s_last = (t == (int)gridDim.y - 1);
+                if (s_last) counter[blockIdx.x] = 0;                  // ready for the next launch
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                for (int idx = threadIdx.x; idx < MEANS_TC * MEANS_BMAX; idx += MEANS_THREADS) {
+                    const int cl = idx / MEANS_BMAX, cc = idx % MEANS_BMAX;
+                    const int j = blockIdx.x * MEANS_TC + cl;
+                    if (j < p && cc < b) {
+                        double v = 0.0;
+                        for (int y = 0; y < (int)gridDim.y; y++) v += __ldcg(&Bpart[((long)y * p + j) * MEANS_BMAX + cc]);
+                        Bout[(long)j * ldb + cc] = v;
+                    }
                 }
             }
         }

@@ -3,11 +3,42 @@
 
 namespace bsfg {
 
+// launch helper: row splits chosen so that the grid is about eight waves of the 4-CTA/SM residency
+struct MeansScratch { double* Bpart = nullptr; int* counter = nullptr; long cap_part = 0, cap_cnt = 0; };
+inline void launch_means_theta(cudaStream_t st, int sms, MeansScratch& ms, const double* DtYt, long ldd, int br, int p, const double* s1,
+                               const double* s2, const double* rp, const double* ep, const VarSrc& z, double* theta, long ldt,
+                               double* thetat, long ldtt, const double* Ut, long ldu, int b, double* Bout, long ldb) {
+    if (p <= 0 || br <= 0) return;
+    const int tiles = ceil_div(p, MEANS_TC);
+    int rs = std::max(1, std::min(8, ceil_div(sms * 4 * 8, tiles)));
+    int rows_per_cta = (int)round_up(ceil_div(br, rs), 64);
+    rs = ceil_div(br, rows_per_cta);
+    if (Bout && rs > 1) {
+        const long need_part = (long)rs * p * MEANS_BMAX;
+        if (ms.cap_part < need_part) {
+            if (ms.Bpart) cudaFree(ms.Bpart);
+            BSFG_CUDA(cudaMalloc(&ms.Bpart, sizeof(double) * need_part));
+            ms.cap_part = need_part;
+        }
+        if (ms.cap_cnt < tiles) {
+            if (ms.counter) cudaFree(ms.counter);
+            BSFG_CUDA(cudaMalloc(&ms.counter, sizeof(int) * tiles));
+            BSFG_CUDA(cudaMemsetAsync(ms.counter, 0, sizeof(int) * tiles, st));
+            ms.cap_cnt = tiles;
+        }
+    }
+    dim3 grid(tiles, rs);
+    means_theta_kernel<<<grid, MEANS_THREADS, 0, st>>>(DtYt, ldd, br, p, s1, s2, rp, ep, z, theta, ldt, thetat, ldtt, Ut, ldu, b, Bout, ldb,
+                                                       rows_per_cta, ms.Bpart, ms.counter);
+    BSFG_CHECK_LAUNCH(); g_launch_counter++;
+}
+
 struct Device {
     cudaStream_t st = nullptr;
     int sms = 0;
     DVec ws;          // split-K workspace
     int* d_flag = nullptr;
+    MeansScratch means;   // row-split partial sums of the fused B reduction (launch_means_theta)
     std::map<int, uint16_t*> chol_maps;   // k -> packed-lower index -> tile offset (chol_blocked.cuh)
     static constexpr size_t WS_DOUBLES = (size_t)24 << 20;   // 192 MB of split-K partials
     void init() {
@@ -409,11 +440,10 @@ extern "C" int bsfg_sample_means_c(const double* Y_tilde, int n, int p, const do
     ds1.upload(s1, d.st); ds2.upload(s2, d.st); drp.upload(resid_Y_prec, d.st); dep.upload(E_a_prec, d.st);
     if (z) { dZ.alloc(br, p); dZ.upload(z, d.st); }
     d.gemm(1.0, dD, dY, 0.0, DtY);                       // Design_U' Y_tilde, cpp:65
-    VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_MEANS, 0, 0, br);
+    VarSrc zs = make_var(z ? &dZ : nullptr, seed, SITE_Z_MEANS, 0, 0, round_up(br, 2));   // even: a row pair = one Philox pair
     {
-        means_theta_kernel<<<ceil_div(p, MEANS_TC), 256, 0, d.st>>>(DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p,
-                                                                    theta.ld, nullptr, 0, nullptr, 0, 0, nullptr, 0);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        launch_means_theta(d.st, d.sms, d.means, DtY.p, DtY.ld, br, p, ds1.p, ds2.p, drp.p, dep.p, zs, theta.p, theta.ld, nullptr, 0,
+                           nullptr, 0, 0, nullptr, 0);
     }
     d.transpose(dU, dUt);
     d.gemm(1.0, dUt, theta, 0.0, out);                   // U * (mlam + z/sqrt(d)), cpp:78

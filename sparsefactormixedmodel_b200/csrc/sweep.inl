@@ -16,6 +16,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     void load() {
@@ -33,6 +34,7 @@ struct NcclApi {
         BSFG_NCCL_SYM(CommInitRank, "ncclCommInitRank");
         BSFG_NCCL_SYM(AllReduce, "ncclAllReduce");
         BSFG_NCCL_SYM(AllGather, "ncclAllGather");
+        BSFG_NCCL_SYM(Broadcast, "ncclBroadcast");
         BSFG_NCCL_SYM(CommDestroy, "ncclCommDestroy");
         BSFG_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef BSFG_NCCL_SYM
@@ -104,6 +106,13 @@ struct bsfg_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     bsfg::DVec gstage;            // row-block exchange staging for the row-sharded replicated draws
+    // side stream: the draws that depend on F only (F_h2, F_a) run beside the Lambda / theta chain, the delta chain beside the
+    // precision statistics; its collectives use a communicator of their own (NCCL orders operations per communicator)
+    bsfg::Device dev2;
+    bool side_ready = false;
+    ncclComm_t comm2 = nullptr;
+    bsfg::DVec gstage2;
+    cudaEvent_t ev_forkA = nullptr, ev_joinA = nullptr, ev_forkB = nullptr, ev_joinB = nullptr;
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_phase;     // (N_PHASES + 1) per iteration slot, reused
@@ -146,16 +155,20 @@ static DMat view_at(double* p, long rows, long cols, long ld) {
 }
 
 static void refresh_derived(bsfg_ctx* c);
-static void allreduce(bsfg_ctx* c, double* buf, size_t count) {
+// `side`: issue on the side stream with its own communicator (see bsfg_ctx::dev2)
+static void allreduce(bsfg_ctx* c, double* buf, size_t count, bool side = false) {
     if (c->cfg.world <= 1) return;
-    if (!c->comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
-    BSFG_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->dev.st));
+    ncclComm_t comm = side ? c->comm2 : c->comm;
+    if (!comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
+    BSFG_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, comm, side ? c->dev2.st : c->dev.st));
 }
 
-static void allgather_inplace(bsfg_ctx* c, double* buf, size_t chunk_doubles) {
+static void allgather_inplace(bsfg_ctx* c, double* buf, size_t chunk_doubles, bool side = false) {
     if (c->cfg.world <= 1) return;
-    if (!c->comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
-    BSFG_NCCL(g_nccl.AllGather(buf + (size_t)c->cfg.rank * chunk_doubles, buf, chunk_doubles, ncclDouble, c->comm, c->dev.st));
+    ncclComm_t comm = side ? c->comm2 : c->comm;
+    if (!comm) fail(BSFG_ESTATE, "world > 1 but bsfg_comm_init was not called");
+    BSFG_NCCL(g_nccl.AllGather(buf + (size_t)c->cfg.rank * chunk_doubles, buf, chunk_doubles, ncclDouble, comm,
+                               side ? c->dev2.st : c->dev.st));
 }
 
 // Row sharding of the REPLICATED work (everything that depends on F only): with `world` ranks each computes rows
@@ -182,18 +195,36 @@ static void gemm_rows(bsfg_ctx* c, const RowShard& sh, double alpha, const DMat&
     dgemm_tn(d.st, d.sms, (int)sh.cnt, (int)B.cols, (int)At.rows, alpha, At.p + sh.lo * At.ld, At.ld, B.p, B.ld, beta,
              C.p + sh.lo, C.ld, C.p + sh.lo, C.ld, d.ws.p, Device::WS_DOUBLES);
 }
-static void gather_rows(bsfg_ctx* c, const RowShard& sh, DMat& C) {
+static void gather_rows(bsfg_ctx* c, const RowShard& sh, DMat& C, bool side = false) {
     if (c->cfg.world <= 1 || !shard_replicated_enabled(1)) return;
-    Device& d = c->dev;
+    Device& d = side ? c->dev2 : c->dev;
+    DVec& stage = side ? c->gstage2 : c->gstage;
     const long cols = C.cols, per = sh.chunk * cols;
-    if ((long)c->gstage.n < per * c->cfg.world) c->gstage.alloc(per * c->cfg.world);
+    if ((long)stage.n < per * c->cfg.world) stage.alloc(per * c->cfg.world);
     const int blocks = (int)std::min<long>((per + 255) / 256, (long)d.sms * 8);
-    pack_rows_kernel<<<std::max(blocks, 1), 256, 0, d.st>>>(C.p, C.ld, sh.lo, sh.cnt, sh.chunk, cols, c->gstage.p + (long)c->cfg.rank * per);
+    pack_rows_kernel<<<std::max(blocks, 1), 256, 0, d.st>>>(C.p, C.ld, sh.lo, sh.cnt, sh.chunk, cols, stage.p + (long)c->cfg.rank * per);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
-    allgather_inplace(c, c->gstage.p, (size_t)per);
+    allgather_inplace(c, stage.p, (size_t)per, side);
     const int blocks2 = (int)std::min<long>((per * c->cfg.world + 255) / 256, (long)d.sms * 8);
-    unpack_rows_kernel<<<std::max(blocks2, 1), 256, 0, d.st>>>(c->gstage.p, sh.chunk, cols, c->cfg.world, c->cfg.rank, C.rows, C.p, C.ld);
+    unpack_rows_kernel<<<std::max(blocks2, 1), 256, 0, d.st>>>(stage.p, sh.chunk, cols, c->cfg.world, c->cfg.rank, C.rows, C.p, C.ld);
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
+}
+
+// side stream, created on first use (BSFG_OVERLAP=0 keeps everything on the sweep stream)
+static bool side_enabled(bsfg_ctx* c) {
+    static const bool on = [] { const char* e = getenv("BSFG_OVERLAP"); return !e || atoi(e) != 0; }();
+    if (!on) return false;
+    if (c->cfg.world > 1 && !c->comm2) return false;
+    if (!c->side_ready) {
+        c->dev2.init();
+        // the staging buffer is sized before any concurrent use (a cudaMalloc in the middle of the sweep would serialise the streams)
+        const long rows = std::max<long>(std::max(c->n, c->r), c->br);
+        if (c->cfg.world > 1) c->gstage2.alloc(round_up(ceil_div(rows, c->cfg.world), 2) * c->kmax * c->cfg.world);
+        for (cudaEvent_t* e : {&c->ev_forkA, &c->ev_joinA, &c->ev_forkB, &c->ev_joinB})
+            BSFG_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        c->side_ready = true;
+    }
+    return true;
 }
 
 struct IterVariates {   // device-side sources for one iteration
@@ -272,6 +303,36 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     DMat Lt = view(c->Lt, k, pl), Lam = view(c->Lam, pl, k), Lmsg = view(c->Lmsg, pl, k), LP = view(c->LP, pl, k);
     DMat Plamt = view(c->Plamt, k, pl);
 
+    // F_h2 | F and F_a | F, F_h2 (steps 4 and 5) depend on F only: with the side stream they start now and run beside the
+    // Lambda / theta chain; the sweep stream picks their results up before the F draw.  (The px sweep keeps one stream: its
+    // rescaled copies of F live in scratch the F step reuses.)
+    const bool side = !px && side_enabled(c);
+    auto draw_h2_and_Fa = [&](Device& dd, bool on_side) {
+        // 4. F_h2 | F (marginal over F_a)                         R:221 -> cpp:196-238
+        //    px sweep: both draws see F_temp = F_px / sqrt(px_factor)  (fast_BSFG_sampler_px.R:232-238); YL / ZFa are free here
+        DMat Fh = px ? view(c->YL, n, k) : view(c->F, n, k);
+        DMat UtFh = px ? view(c->ZFa, n, k) : view(c->UtF, n, k);
+        if (px) {
+            px_vectors_kernel<<<ceil_div(k, 128), 128, 0, dd.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            dd.scale(F, nullptr, c->px_isq.p, Fh);
+            dd.scale(UtF, nullptr, c->px_isq.p, UtFh);
+        }
+        h2s_core(dd, UtFh, Fh, c->s.p, H, c->h2_prior.p, v.uh2, c->F_h2.p, c->aux_on ? c->aux_logps.p : nullptr, c->det, c->ll);
+        if (!on_side) phase_mark(c, 5);
+        // 5. F_a | F, F_h2                                        R:226 -> cpp:293-339
+        DMat T1 = view(c->T1, r, k), b3 = view(c->b3, r, k), vfa = view(c->vfa, r, k);
+        const RowShard sr = row_shard(c, r);
+        std::function<void(DMat&)> gather = [&](DMat& M) { gather_rows(c, sr, M, on_side); };
+        fa_core(dd, Fh, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa,
+                sr.lo, sr.cnt, (c->cfg.world > 1 && shard_replicated_enabled(1)) ? &gather : nullptr);
+    };
+    if (side) {
+        BSFG_CUDA(cudaEventRecord(c->ev_forkA, d.st));
+        BSFG_CUDA(cudaStreamWaitEvent(c->dev2.st, c->ev_forkA, 0));
+        draw_h2_and_Fa(c->dev2, true);
+        BSFG_CUDA(cudaEventRecord(c->ev_joinA, c->dev2.st));
+    }
     // 0. missing phenotypes                                  R:180-184
     if (c->has_missing) impute_missing(c, v.zY);
     // 1. Lambda | F, B, precisions (marginal over E_a)      R:189-191 -> cpp:86-135
@@ -306,10 +367,9 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     {
         const bool fuse_b = b > 0 && b <= MEANS_BMAX;      // B = location_sample[1:b,] (R:206) reduced in the same pass
         // theta and theta' (the K = p operand of step 6) leave the same kernel: no transpose pass over the br x p array
-        means_theta_kernel<<<ceil_div(pl, MEANS_TC), 256, 0, d.st>>>(c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p,
-                                                                     c->ep.p, v.zM, c->theta.p, c->theta.ld, c->thetat.p, c->thetat.ld,
-                                                                     c->U2t.p, c->U2t.ld, b, fuse_b ? c->Bfix.p : nullptr, c->Bfix.ld);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        launch_means_theta(d.st, d.sms, d.means, c->tmp_brp.p, c->tmp_brp.ld, br, pl, c->s1_2.p, c->s2_2.p, c->rp.p, c->ep.p, v.zM,
+                           c->theta.p, c->theta.ld, c->thetat.p, c->thetat.ld, c->U2t.p, c->U2t.ld, b,
+                           fuse_b ? c->Bfix.p : nullptr, c->Bfix.ld);
         if (b > 0 && !fuse_b) {
             DMat U2Bt = view(c->U2t, br, b);               // first b columns of U2' = rows 0..b-1 of U2
             d.gemm(1.0, U2Bt, c->theta, 0.0, c->Bfix);
@@ -325,34 +385,15 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
                  d.ws.p, Device::WS_DOUBLES);                                             // Z_2'Y - Z_2'F Lambda'
         d.gemm(1.0, c->Uw, c->gW, 0.0, c->tmpw);
         d.gemm(-1.0, c->Uw, c->Z2DUth, 1.0, c->tmpw);
-        means_theta_kernel<<<ceil_div(pl, MEANS_TC), 256, 0, d.st>>>(c->tmpw.p, c->tmpw.ld, r2, pl, c->s1w.p, c->s2w.p, c->rp.p, c->wp.p,
-                                                                     v.zW, c->thw.p, c->thw.ld, nullptr, 0, nullptr, 0, 0, nullptr, 0);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        launch_means_theta(d.st, d.sms, d.means, c->tmpw.p, c->tmpw.ld, r2, pl, c->s1w.p, c->s2w.p, c->rp.p, c->wp.p, v.zW, c->thw.p,
+                           c->thw.ld, nullptr, 0, nullptr, 0, 0, nullptr, 0);
         d.gemm(1.0, c->Uwt, c->thw, 0.0, c->W);                                            // W = U theta_w (cpp:78)
         d.transpose(c->W, c->Wt);
     }
     phase_mark(c, 4);
 
-    // 4. F_h2 | F (marginal over F_a)                         R:221 -> cpp:196-238
-    //    px sweep: both draws see F_temp = F_px / sqrt(px_factor)  (fast_BSFG_sampler_px.R:232-238); YL / ZFa are free here
-    DMat Fh = px ? view(c->YL, n, k) : view(c->F, n, k);
-    DMat UtFh = px ? view(c->ZFa, n, k) : view(c->UtF, n, k);
-    if (px) {
-        px_vectors_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->px.p, k, c->px_sq.p, c->px_isq.p, c->px_ipx.p);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        d.scale(F, nullptr, c->px_isq.p, Fh);
-        d.scale(UtF, nullptr, c->px_isq.p, UtFh);
-    }
-    h2s_core(d, UtFh, Fh, c->s.p, H, c->h2_prior.p, v.uh2, c->F_h2.p, c->aux_on ? c->aux_logps.p : nullptr, c->det, c->ll);
-    phase_mark(c, 5);
-    // 5. F_a | F, F_h2                                        R:226 -> cpp:293-339
-    {
-        DMat T1 = view(c->T1, r, k), b3 = view(c->b3, r, k), vfa = view(c->vfa, r, k);
-        const RowShard sr = row_shard(c, r);
-        std::function<void(DMat&)> gather = [&](DMat& M) { gather_rows(c, sr, M); };
-        fa_core(d, Fh, c->z1_identity ? nullptr : &c->Z1, c->U3, c->U3t, c->s1_3.p, c->s2_3.p, c->F_h2.p, v.zFa, T1, b3, vfa, Fa,
-                sr.lo, sr.cnt, (c->cfg.world > 1 && shard_replicated_enabled(1)) ? &gather : nullptr);
-    }
+    if (side) phase_mark(c, 5);             // steps 4 and 5 are on the side stream: their phases read ~0 on this one
+    else draw_h2_and_Fa(d, false);
     phase_mark(c, 6);
 
     // 6. F | Lambda, B, E_a, F_a, F_h2                        R:230-232 -> cpp:138-163
@@ -370,6 +411,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     if (r2 > 0) d.gemm(1.0, c->Wt, Lmsg, 0.0, P3);                                         // W Lmsg
     phase_mark(c, 7);
     allreduce(c, c->red1.p, (size_t)c->red1.ld * (size_t)k);
+    if (side) BSFG_CUDA(cudaStreamWaitEvent(d.st, c->ev_joinA, 0));        // F_h2 and F_a of this iteration are ready
     phase_mark(c, 8);
     {
         // rows of F are independent given the k x k factor: each rank forms and solves its own block of individuals,
@@ -423,6 +465,29 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
                                                      c->aux_on ? c->aux_lp_rate.p : nullptr);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
     }
+    // 11-12. delta, tauh, Plam                                R:253-257 -> BSFG_functions.R:272-308
+    //        needs Lambda and the new Lambda_prec only: with the side stream it runs beside the precision statistics below
+    auto delta_chain = [&](Device& dd, bool on_side) {
+        factor_reduce_kernel<<<k, 256, 0, dd.st>>>(LP.p, LP.ld, LamS.p, LamS.ld, pl, k, c->pri.epsilon, c->colsum_cnt.p,
+                                                   c->colsum_cnt.p + c->kmax);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        allreduce(c, c->colsum_cnt.p, (size_t)2 * c->kmax, on_side);
+        delta_recursion_kernel<<<1, 128, (4 * k + 2) * sizeof(double), dd.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
+                                                                    c->pri.delta_1_shape, c->pri.delta_1_rate,
+                                                                    c->pri.delta_2_shape, c->pri.delta_2_rate, v.gD, c->tauh.p,
+                                                                    c->delta_shapes.p, c->delta_rates.p, c->d_ndraws);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        dim3 grid(ceil_div(pl, 32), ceil_div(k, 32)), block(32, 8);
+        plam_kernel<<<grid, block, 0, dd.st>>>(LP.p, LP.ld, pl, k, c->tauh.p, Plamt.p, Plamt.ld);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        if (px) dd.scale(Plamt, c->px_ipx.p, nullptr, Plamt);      // Plam = Plam / px_factor (:290); rows of Plamt are factors
+    };
+    if (side && !fixed_lambda) {
+        BSFG_CUDA(cudaEventRecord(c->ev_forkB, d.st));
+        BSFG_CUDA(cudaStreamWaitEvent(c->dev2.st, c->ev_forkB, 0));
+        delta_chain(c->dev2, true);
+        BSFG_CUDA(cudaEventRecord(c->ev_joinB, c->dev2.st));
+    }
     // 8-9. resid_Y_prec, E_a_prec from sufficient statistics of the NEW F   R:239-245
     refresh_derived(c);
     {
@@ -467,22 +532,8 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     phase_mark(c, 10);
 
     if (fixed_lambda) { phase_mark(c, 11); return; }
-    // 11-12. delta, tauh, Plam                                R:253-257 -> BSFG_functions.R:272-308
-    factor_reduce_kernel<<<k, 256, 0, d.st>>>(LP.p, LP.ld, LamS.p, LamS.ld, pl, k, c->pri.epsilon, c->colsum_cnt.p,
-                                              c->colsum_cnt.p + c->kmax);
-    BSFG_CHECK_LAUNCH(); g_launch_counter++;
-    allreduce(c, c->colsum_cnt.p, (size_t)2 * c->kmax);
-    delta_recursion_kernel<<<1, 128, (4 * k + 2) * sizeof(double), d.st>>>(c->delta.p, k, c->colsum_cnt.p, (double)c->p_total,
-                                                               c->pri.delta_1_shape, c->pri.delta_1_rate,
-                                                               c->pri.delta_2_shape, c->pri.delta_2_rate, v.gD, c->tauh.p,
-                                                               c->delta_shapes.p, c->delta_rates.p, c->d_ndraws);
-    BSFG_CHECK_LAUNCH(); g_launch_counter++;
-    {
-        dim3 grid(ceil_div(pl, 32), ceil_div(k, 32)), block(32, 8);
-        plam_kernel<<<grid, block, 0, d.st>>>(LP.p, LP.ld, pl, k, c->tauh.p, Plamt.p, Plamt.ld);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        if (px) d.scale(Plamt, c->px_ipx.p, nullptr, Plamt);      // Plam = Plam / px_factor (:290); rows of Plamt are factors
-    }
+    if (side) BSFG_CUDA(cudaStreamWaitEvent(d.st, c->ev_joinB, 0));       // delta, tauh, Plam of this iteration are in place
+    else delta_chain(d, false);
     phase_mark(c, 11);
 }
 
@@ -584,7 +635,19 @@ extern "C" int bsfg_destroy(bsfg_ctx* c) {
     BSFG_API_BEGIN
     if (!c) return BSFG_OK;
     cudaStreamSynchronize(c->dev.st);
+    if (c->side_ready) {
+        cudaStreamSynchronize(c->dev2.st);
+        for (cudaEvent_t e : {c->ev_forkA, c->ev_joinA, c->ev_forkB, c->ev_joinB})
+            if (e) cudaEventDestroy(e);
+        if (c->dev2.d_flag) cudaFree(c->dev2.d_flag);
+        if (c->dev2.means.Bpart) cudaFree(c->dev2.means.Bpart);
+        if (c->dev2.means.counter) cudaFree(c->dev2.means.counter);
+        if (c->dev2.st) cudaStreamDestroy(c->dev2.st);
+    }
+    if (c->comm2) g_nccl.CommDestroy(c->comm2);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->dev.means.Bpart) cudaFree(c->dev.means.Bpart);
+    if (c->dev.means.counter) cudaFree(c->dev.means.counter);
     if (c->d_ndraws) cudaFree(c->d_ndraws);
     if (c->d_map) cudaFree(c->d_map);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -955,7 +1018,7 @@ static int sweep_impl(bsfg_ctx* c, int n_iter, bool px) {
         const uint32_t ii = (uint32_t)i;
         IterVariates v;
         v.zL = make_var(nullptr, seed, SITE_Z_LAMBDA, ii, c->p_off, c->k);
-        v.zM = make_var(nullptr, seed, SITE_Z_MEANS, ii, c->p_off, c->br);
+        v.zM = make_var(nullptr, seed, SITE_Z_MEANS, ii, c->p_off, round_up(c->br, 2));    // even: a row pair = one Philox pair
         v.uh2 = make_var(nullptr, seed, SITE_U_H2, ii, 0, c->k);
         v.zFa = make_var(nullptr, seed, SITE_Z_FA, ii, 0, c->r);
         v.zF = make_var(nullptr, seed, SITE_Z_F, ii, 0, c->n);
@@ -963,7 +1026,7 @@ static int sweep_impl(bsfg_ctx* c, int n_iter, bool px) {
         v.gR = make_var(nullptr, seed, SITE_G_RESID, ii, c->p_off, 1);
         v.gE = make_var(nullptr, seed, SITE_G_EA, ii, c->p_off, 1);
         v.gD = make_var(nullptr, seed, SITE_G_DELTA, ii, 0, 1);
-        v.zW = make_var(nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? c->r2 : 1);
+        v.zW = make_var(nullptr, seed, SITE_Z_MEANS_W, ii, c->p_off, c->r2 > 0 ? round_up(c->r2, 2) : 2);
         v.gW = make_var(nullptr, seed, SITE_G_W, ii, c->p_off, 1);
         v.zY = make_var(nullptr, seed, SITE_Z_Y, ii, c->p_off, c->n);
         v.gPX = make_var(nullptr, seed, SITE_G_PX, ii, 0, 1);
@@ -1249,6 +1312,19 @@ extern "C" int bsfg_comm_init(bsfg_ctx* c, const char id_in[128]) {
     ncclUniqueId id;
     memcpy(&id, id_in, 128);
     BSFG_NCCL(g_nccl.CommInitRank(&c->comm, c->cfg.world, id, c->cfg.rank));
+    {   // second communicator for the side stream: rank 0 draws its id and hands it out over the first one
+        ncclUniqueId id2;
+        memset(&id2, 0, sizeof id2);
+        if (c->cfg.rank == 0) BSFG_NCCL(g_nccl.GetUniqueId(&id2));
+        char* dbuf = nullptr;
+        BSFG_CUDA(cudaMalloc(&dbuf, sizeof id2));
+        BSFG_CUDA(cudaMemcpyAsync(dbuf, &id2, sizeof id2, cudaMemcpyHostToDevice, c->dev.st));
+        BSFG_NCCL(g_nccl.Broadcast(dbuf, dbuf, sizeof id2, ncclChar, 0, c->comm, c->dev.st));
+        BSFG_CUDA(cudaMemcpyAsync(&id2, dbuf, sizeof id2, cudaMemcpyDeviceToHost, c->dev.st));
+        c->dev.sync();
+        cudaFree(dbuf);
+        BSFG_NCCL(g_nccl.CommInitRank(&c->comm2, c->cfg.world, id2, c->cfg.rank));
+    }
     if (shard_replicated_enabled(2)) {
         c->lsc.rank = c->cfg.rank; c->lsc.world = c->cfg.world;
         c->lsc.allgather = [c](double* buf, size_t chunk) { allgather_inplace(c, buf, chunk); };
