@@ -38,6 +38,7 @@ int bsfg_version(void);                 /* 100*major + minor */
 const char* bsfg_last_error(void);
 int bsfg_device_count(void);            /* number of visible CUDA devices (0 if none) */
 long long bsfg_launch_count(void);      /* CUDA kernels launched by this library in this process so far */
+int bsfg_k_limit(void);                /* largest supported number of factors k (and k_max); update_k may grow k towards 2p, BSFG_functions.R:332 */
 
 /* ------------------------------------------------------------------------------------------
  * Stateless drop-ins: one per Rcpp export on the hot path.

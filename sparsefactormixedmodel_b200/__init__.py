@@ -10,3 +10,8 @@ from .samplers import (GSVD_2_c, dgemm_tn, update_k_c, sample_delta_c, sample_F_
                        sample_h2s_discrete_c, sample_Lambda_c, sample_lambda_c, sample_means_c,
                        sample_prec_discrete_conditional_c, sample_px_factors_scores_c)
 from .driver import BSFGSweep, fast_BSFG_sampler, init_lists, set_gram_default  # noqa: F401
+
+
+def k_limit():
+    """Largest supported number of factors (k and k_max)."""
+    return int(load().bsfg_k_limit())

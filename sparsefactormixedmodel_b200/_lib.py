@@ -96,7 +96,7 @@ EXPORTS = [
     "bsfg_create", "bsfg_destroy", "bsfg_set_priors", "bsfg_upload_constants", "bsfg_set_state",
     "bsfg_get_state", "bsfg_get_aux", "bsfg_sweep", "bsfg_sweep_injected", "bsfg_sweep_fixed_lambda", "bsfg_sweep_px", "bsfg_sweep_px_injected",
     "bsfg_init_lists", "bsfg_posterior_begin", "bsfg_sweep_collect", "bsfg_posterior_count", "bsfg_get_posterior", "bsfg_get_mode",
-    "bsfg_get_timing", "bsfg_nccl_unique_id", "bsfg_comm_init", "bsfg_launch_count",
+    "bsfg_get_timing", "bsfg_nccl_unique_id", "bsfg_comm_init", "bsfg_launch_count", "bsfg_k_limit",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def load():
     lib.bsfg_version.restype = C.c_int
     lib.bsfg_device_count.restype = C.c_int
     lib.bsfg_launch_count.restype = C.c_longlong
+    lib.bsfg_k_limit.restype = C.c_int
     for name in EXPORTS:
         getattr(lib, name)      # AttributeError if a declared symbol is not exported
     _lib = lib

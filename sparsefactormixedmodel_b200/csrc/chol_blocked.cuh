@@ -137,27 +137,27 @@ __device__ long long cb_prof_cycles[8][8];      // [warp][stage], plain stores (
 #define CB_FLUSH()
 #endif
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1)
-chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, const uint16_t* __restrict__ tile_off,
-                    const double* __restrict__ dadd, long dadd_sys_stride, long dadd_elem_stride,
-                    const double* __restrict__ rhs, long ldr, VarSrc zsrc, double* __restrict__ out, long ldo,
-                    double* __restrict__ Lout, int* __restrict__ fail_flag) {
-    extern __shared__ __align__(16) double sm[];
+// BIG = true (k + 1 > 8 * 27, i.e. the tiles no longer fit 227 KB of shared memory; update_k may grow k towards 2p,
+// BSFG_functions.R:332): the same algorithm with the tile array in a per-CTA slice of a global workspace (L2 resident), plain
+// loads instead of cp.async for staging, and a persistent grid whose CTAs walk the systems.  Latency bound on L2 instead of
+// shared memory -- a correctness path for factor counts the reference allows, not a tuned one.
+template <int NW, bool BIG>
+__device__ __forceinline__ void
+cb_system(double* sm, double* T, const int sys, const double* __restrict__ Qp, long ldq, int k, const uint16_t* __restrict__ tile_off,
+          const double* __restrict__ dadd, long dadd_sys_stride, long dadd_elem_stride,
+          const double* __restrict__ rhs, long ldr, const VarSrc& zsrc, double* __restrict__ out, long ldo,
+          double* __restrict__ Lout, int* __restrict__ fail_flag) {
     constexpr int T_ = NW * 32, PW = NW - 1, PT = PW * 32;
     const bool aug = rhs != nullptr;               // right-hand side stored as matrix row k
     const int kk = k + (aug ? 1 : 0);
     const int NB = (kk + 7) >> 3;
     const int ntile = NB * (NB + 1) / 2;
     const int npairs = k * (k + 1) / 2;
-    double* T = sm;                       // ntile * 64
-    double* Dtmp = T + ntile * 64;        // 64 : the diagonal tile being factored, DMMA fragment -> one row per register set
+    double* Dtmp = BIG ? sm : T + ntile * 64;     // 64 : the diagonal tile being factored, DMMA fragment -> one row per register set
     double* Lpub = Dtmp + 64;             // 64 : factored diagonal block for the panel rows (tile layout, 1/L[c][c] on the diagonal)
     double* Dinv = Lpub + 64;             // NB * 64 : inverse of each factored diagonal block (row-major r*8+c, c <= r)
     double* xv = Dinv + NB * 64;          // 8 NB : backward-solve vector
     int* s_bad = (int*)(xv + 8 * NB);
-    const int sys = blockIdx.x;
-    if (sys >= nsys) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     CB_T0();
 
@@ -176,7 +176,10 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
             const double* qa = q + (long)a * (a + 1) / 2;
             double* Ta = T + cb_tile_id(a >> 3, 0) * 64 + (a & 7) * 8;
             const int sw4 = (a & 2) << 1;
-            for (int b = lane; b <= a; b += 32) cb_cp_async8(Ta + (b >> 3) * 64 + ((b & 7) ^ sw4), qa + b);
+            for (int b = lane; b <= a; b += 32) {
+                if constexpr (BIG) Ta[(b >> 3) * 64 + ((b & 7) ^ sw4)] = qa[b];
+                else cb_cp_async8(Ta + (b >> 3) * 64 + ((b & 7) ^ sw4), qa + b);
+            }
         }
         for (int a = kk + tid; a < 8 * NB; a += T_) T[cb_tile_id(a >> 3, a >> 3) * 64 + cb_swz(a & 7, a & 7)] = 1.0;
         if (aug) {
@@ -184,7 +187,7 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
             for (int j = tid; j < k; j += T_) T[cb_tile_id(Ik, j >> 3) * 64 + cb_swz(rk, j & 7)] = rhs[(long)sys * ldr + j];
             if (tid == 0) T[cb_tile_id(Ik, Ik) * 64 + cb_swz(rk, rk)] = 1e300;   // keeps the pivot of row k positive; its factor is never used
         }
-        cb_cp_async_wait_all();
+        if constexpr (!BIG) cb_cp_async_wait_all();
     }
     __syncthreads();
     if (dadd) {
@@ -280,12 +283,16 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
             // panel warp pw takes items pw, pw + PW, ...
             const int ntl = NB - J - 1;                                  // off-diagonal tiles of this column
             const int nt = ntl > pw ? (ntl - pw + PW - 1) / PW : 0;
-            switch (nt) {
-                case 1: cb_update_tiles<1, false>(T, J, J + 1 + pw, PW, fa0, fa1, fc); break;
-                case 2: cb_update_tiles<2, false>(T, J, J + 1 + pw, PW, fa0, fa1, fc); break;
-                case 3: cb_update_tiles<3, false>(T, J, J + 1 + pw, PW, fa0, fa1, fc); break;
-                case 4: cb_update_tiles<4, false>(T, J, J + 1 + pw, PW, fa0, fa1, fc); break;
-                case 5: cb_update_tiles<5, false>(T, J, J + 1 + pw, PW, fa0, fa1, fc); break;
+            int I0 = J + 1 + pw, rem = nt;
+            if constexpr (BIG) {      // more than 5 tiles per warp only beyond 28 block rows
+                while (rem > 5) { cb_update_tiles<4, false>(T, J, I0, PW, fa0, fa1, fc); I0 += 4 * PW; rem -= 4; }
+            }
+            switch (rem) {
+                case 1: cb_update_tiles<1, false>(T, J, I0, PW, fa0, fa1, fc); break;
+                case 2: cb_update_tiles<2, false>(T, J, I0, PW, fa0, fa1, fc); break;
+                case 3: cb_update_tiles<3, false>(T, J, I0, PW, fa0, fa1, fc); break;
+                case 4: cb_update_tiles<4, false>(T, J, I0, PW, fa0, fa1, fc); break;
+                case 5: cb_update_tiles<5, false>(T, J, I0, PW, fa0, fa1, fc); break;
                 default: break;
             }
             if (ntl > 0 && ntl % PW == pw) cb_update_tiles<1, true>(T, J, J + 1, 0, fa0, fa1, fc);
@@ -334,7 +341,13 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
         return;
     }
     if (Lout) {
-        for (int idx = tid; idx < npairs; idx += T_) Lout[(long)sys * npairs + idx] = T[tile_off[idx]];
+        if constexpr (BIG) {      // no uint16 offset table beyond 65535 tile elements
+            for (int a = warp; a < k; a += NW)
+                for (int b = lane; b <= a; b += 32)
+                    Lout[(long)sys * npairs + (long)a * (a + 1) / 2 + b] = T[cb_tile_id(a >> 3, b >> 3) * 64 + cb_swz(a & 7, b & 7)];
+        } else {
+            for (int idx = tid; idx < npairs; idx += T_) Lout[(long)sys * npairs + idx] = T[tile_off[idx]];
+        }
     }
     if (!out || !aug) return;
 
@@ -391,6 +404,41 @@ chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, co
     for (int i = lane; i < k; i += 32) out[(long)sys * ldo + i] = xv[i];
     CB_TICK(6);
     CB_FLUSH();
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1)
+chol_blocked_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys, const uint16_t* __restrict__ tile_off,
+                    const double* __restrict__ dadd, long dadd_sys_stride, long dadd_elem_stride,
+                    const double* __restrict__ rhs, long ldr, VarSrc zsrc, double* __restrict__ out, long ldo,
+                    double* __restrict__ Lout, int* __restrict__ fail_flag) {
+    extern __shared__ __align__(16) double sm[];
+    const int sys = blockIdx.x;
+    if (sys >= nsys) return;
+    cb_system<NW, false>(sm, sm, sys, Qp, ldq, k, tile_off, dadd, dadd_sys_stride, dadd_elem_stride, rhs, ldr, zsrc, out, ldo, Lout, fail_flag);
+}
+
+// shared-memory bytes of the BIG variant: scratch diagonal tile, published factor, inverted diagonal blocks, solve vector, flag
+inline size_t cb_big_smem_bytes(int k, bool with_rhs) {
+    const int NB = (k + (with_rhs ? 1 : 0) + 7) / 8;
+    return sizeof(double) * (64 + 64 + (size_t)NB * 64 + (size_t)NB * 8) + 16;
+}
+// doubles of global workspace per CTA of the BIG variant (the tile array)
+inline long cb_big_ws_doubles(int k, bool with_rhs) {
+    const long NB = (k + (with_rhs ? 1 : 0) + 7) / 8;
+    return NB * (NB + 1) / 2 * 64;
+}
+__global__ void __launch_bounds__(256, 2)
+chol_blocked_big_kernel(const double* __restrict__ Qp, long ldq, int k, int nsys,
+                        const double* __restrict__ dadd, long dadd_sys_stride, long dadd_elem_stride,
+                        const double* __restrict__ rhs, long ldr, VarSrc zsrc, double* __restrict__ out, long ldo,
+                        double* __restrict__ Lout, int* __restrict__ fail_flag, double* __restrict__ gws, long gws_stride) {
+    extern __shared__ __align__(16) double sm[];
+    double* T = gws + (long)blockIdx.x * gws_stride;
+    for (int sys = blockIdx.x; sys < nsys; sys += gridDim.x) {
+        cb_system<8, true>(sm, T, sys, Qp, ldq, k, nullptr, dadd, dadd_sys_stride, dadd_elem_stride, rhs, ldr, zsrc, out, ldo, Lout, fail_flag);
+        __syncthreads();          // the backward-solve warp is done with T before the next system is staged
+    }
 }
 
 }  // namespace bsfg

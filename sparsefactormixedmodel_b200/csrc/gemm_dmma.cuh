@@ -47,6 +47,9 @@ struct GemmArgs {
     const int* run_if;     // optional device flag: the whole launch is a no-op when *run_if == 0
     int trans_out;         // 1: the product is stored transposed, element (m, n) at C[m * ldc + n] (and Cin likewise);
                            // lets an N = k product run as the M = k product of the swapped operands (short row tile)
+    int* tile_counter;     // != null: split-K partials are summed by the LAST CTA to finish a tile (fixed split order, so the
+                           // result is the same as splitk_reduce_kernel's) -- no separate reduce launch; one self-resetting
+                           // counter per output tile
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -133,10 +136,11 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tiles = g.tiles_m * g.tiles_n;
     const int work_total = tiles * g.splits;
     const int total_ktiles = (g.K + GEMM_BK - 1) / GEMM_BK;
-    struct Item { int m0, n0, kt_begin, nkt, split; };
+    struct Item { int m0, n0, kt_begin, nkt, split, tile; };
     auto decode = [&](int w) {
         Item it;
         const int tile = w % tiles;
+        it.tile = tile;
         it.split = w / tiles;
         const int group_sz = g.group_n * g.tiles_m;
         const int grp = tile / group_sz;
@@ -258,6 +262,32 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int c = 0; c < 2; c++) {
                         const int n = n0 + wn0 + 8 * j + 2 * q + c;
                         if (n < g.N) ws[(size_t)n * g.M + m] = acc[i][j][c];
+                    }
+                }
+            }
+            if (g.tile_counter) {
+                // the last CTA to deliver a partial of this tile sums all of them, in split order
+                __shared__ int s_last;
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int t = atomicAdd(&g.tile_counter[cur.tile], 1);
+                    s_last = (t == g.splits - 1);
+                    if (s_last) g.tile_counter[cur.tile] = 0;
+                }
+                __syncthreads();
+                if (s_last) {
+                    __threadfence();
+                    const size_t total = (size_t)g.M * (size_t)g.N;
+                    const int rows = min(BM, g.M - m0), cols = min(BN, g.N - n0);
+                    for (int idx = threadIdx.x; idx < rows * cols; idx += GEMM_THREADS) {
+                        const int m = m0 + idx % rows, n = n0 + idx / rows;
+                        const size_t e = (size_t)n * g.M + m;
+                        double a = 0.0;
+                        for (int sp = 0; sp < g.splits; sp++) a += __ldcg(g.ws + (size_t)sp * total + e);
+                        double v = g.alpha * a;
+                        if (g.Cin) v += g.beta * g.Cin[g.trans_out ? (size_t)m * g.ldcin + n : (size_t)n * g.ldcin + m];
+                        g.C[g.trans_out ? (size_t)m * g.ldc + n : (size_t)n * g.ldc + m] = v;
                     }
                 }
             }

@@ -77,6 +77,13 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     // over the s x M x N partials plus the reduce launch.  E.g. M=k=100, N=p=20000, K=5000 (157 tiles = 2 waves at 53%):
     // s=5 -> ~750 us instead of 1330; Lambda'Lmsg (1 tile, K=20000): s=148.  Partials are summed in a fixed order by
     // splitk_reduce_kernel, so results stay bit-reproducible.
+    // the last 64 Ki ints of the workspace are the per-tile arrival counters of the fused split-K reduction
+    constexpr size_t COUNTER_DOUBLES = 32768;
+    int* counters = nullptr;
+    if (ws && ws_doubles > 4 * COUNTER_DOUBLES) {
+        ws_doubles -= COUNTER_DOUBLES;
+        counters = reinterpret_cast<int*>(ws + ws_doubles);
+    }
     int splits = 1;
     if (ws) {
         const double per = (double)M * (double)N;
@@ -99,6 +106,13 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     splits = ceil_div(ktiles, g.ktiles_per_split);    // no empty splits
     g.splits = splits;
     g.ws = ws;
+    // Fused reduction (the last CTA to deliver a partial of a tile sums them): OFF by default.  Measured at C4 on one B200
+    // (profiles/r02c_bench_c4_n1_fused_reduce_{on,off}.json): 11.64 ms per iteration with it, 10.81 ms without -- the summing
+    // CTA reads splits x 112 x 128 partials through one SM while its neighbours idle at the end of the wave, which costs
+    // more than the 14 reduce launches it saves.  BSFG_GEMM_FUSED_REDUCE=1 turns it on (results are identical: same order).
+    static const bool fuse_ok = [] { const char* e = getenv("BSFG_GEMM_FUSED_REDUCE"); return e && atoi(e) != 0; }();
+    const bool fused = fuse_ok && splits > 1 && splits <= 16 && counters && tiles <= 65536 && run_if == nullptr;
+    g.tile_counter = fused ? counters : nullptr;
     // persistent launch: one CTA per SM walks the (tile, split) items; BSFG_GEMM_PERSISTENT=0 launches one CTA per item
     static const bool persistent = [] { const char* e = getenv("BSFG_GEMM_PERSISTENT"); return !e || atoi(e) != 0; }();
     const long items = (long)tiles * splits;
@@ -112,7 +126,7 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     }
     BSFG_CHECK_LAUNCH();
     g_launch_counter++;
-    if (splits > 1) {
+    if (splits > 1 && !fused) {
         const size_t total = (size_t)M * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > sm_count * 8) blocks = sm_count * 8;

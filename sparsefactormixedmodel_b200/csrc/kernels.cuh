@@ -97,7 +97,7 @@ __global__ void scale_kernel(const double* __restrict__ in, long ldi, long rows,
 __global__ void gram_features_kernel(const double* __restrict__ UtF, long ldf, int n, int k,
                                      double* __restrict__ Gt, long ldg, int pair_lo, int pair_hi,
                                      const int* __restrict__ need_all) {
-    const int pair = blockIdx.y;
+    const int pair = blockIdx.x;                   // pairs on grid.x: k(k+1)/2 exceeds the 65535 limit of grid.y from k = 362
     if ((pair < pair_lo || pair >= pair_hi) && !(need_all && *need_all != 0)) return;
     int a = (int)((sqrt(8.0 * pair + 1.0) - 1.0) * 0.5);
     while ((a + 1) * (a + 2) / 2 <= pair) a++;
@@ -106,7 +106,7 @@ __global__ void gram_features_kernel(const double* __restrict__ UtF, long ldf, i
     const double* fa = UtF + (long)a * ldf;
     const double* fb = UtF + (long)b * ldf;
     double* g = Gt + (long)pair * ldg;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) g[i] = fa[i] * fb[i];
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) g[i] = fa[i] * fb[i];
 }
 
 // W[i,j]  = ep_j / (s_i + ep_j / rp_j)                                   (cpp:120, the sweep weights)
@@ -263,12 +263,14 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __restrict__ YL, long ldy,
                    const double* __restrict__ ZFa, long ldz, const double* __restrict__ tau_e, VarSrc zsrc, int row0,
-                   double* __restrict__ Fout, long ldf) {
+                   double* __restrict__ Fout, long ldf, int stage_l /* 0: read the factor from global memory (large k) */) {
     extern __shared__ double sm[];
     const int npairs = k * (k + 1) / 2;
-    for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) sm[idx] = Lp[idx];
-    __syncthreads();
-    const double* L = sm;
+    if (stage_l) {
+        for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) sm[idx] = Lp[idx];
+        __syncthreads();
+    }
+    const double* L = stage_l ? sm : Lp;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (int row_i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row_i < n; row_i += gridDim.x * warps_per_block) {

@@ -38,6 +38,7 @@ struct Device {
     int sms = 0;
     DVec ws;          // split-K workspace
     int* d_flag = nullptr;
+    DVec chol_ws;         // tile workspace of the large-k Cholesky (k > BSFG_K_SMEM_LIMIT)
     MeansScratch means;   // row-split partial sums of the fused B reduction (launch_means_theta)
     std::map<int, uint16_t*> chol_maps;   // k -> packed-lower index -> tile offset (chol_blocked.cuh)
     static constexpr size_t WS_DOUBLES = (size_t)24 << 20;   // 192 MB of split-K partials
@@ -126,13 +127,18 @@ static VarSrc make_var(const DMat* injected, uint64_t seed, uint32_t site, uint3
 }
 
 // ---- reusable device-level pieces (also used by the sweep) -----------------------------------
-constexpr int BSFG_K_LIMIT = 216;   // (k + 1 rows) -> 28 block rows: 406 tiles + 28 inverted diagonal blocks of 8 x 8 doubles fit 227 KB
+// Up to k = 216 a system's tiles fit 227 KB of shared memory (28 block rows incl. the right-hand-side row); above that the
+// batched Cholesky keeps them in a global (L2) workspace (chol_blocked_big_kernel) and the F row solves read the factor from
+// L2.  The cap itself is the 16 x 32 columns a warp of factor_rows_kernel holds in registers.
+constexpr int BSFG_K_SMEM_LIMIT = 216;
+constexpr int BSFG_K_LIMIT = 504;
 static int kt_for(int k) {
     if (k > BSFG_K_LIMIT) fail(BSFG_ESHAPE, "k = %d exceeds the supported maximum of %d factors", k, BSFG_K_LIMIT);
     if (k <= 32) return 1;
     if (k <= 64) return 2;
     if (k <= 128) return 4;
-    return 8;
+    if (k <= 256) return 8;
+    return 16;
 }
 
 // batched Cholesky + solves (chol_blocked.cuh): 4 warps per system up to 13 block rows (k + 1 <= 104), 8 warps above
@@ -142,7 +148,17 @@ static void launch_chol_solve(Device& d, const double* Qp, long ldq, int k, int 
     if (nsys <= 0) return;
     kt_for(k);
     const size_t smem = cb_smem_bytes(k, rhs != nullptr);
-    if (smem > 227 * 1024) fail(BSFG_ESHAPE, "k = %d: the tiled Cholesky needs %zu B of shared memory", k, smem);
+    if (smem > 227 * 1024) {      // large k: tiles in a global workspace, persistent grid (chol_blocked.cuh, BIG variant)
+        const int grid = std::min(nsys, d.sms * 2);
+        const long stride = cb_big_ws_doubles(k, rhs != nullptr);
+        if ((long)d.chol_ws.n < stride * grid) d.chol_ws.alloc(stride * grid);
+        const size_t smem_big = cb_big_smem_bytes(k, rhs != nullptr);
+        BSFG_CUDA(cudaFuncSetAttribute(chol_blocked_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        chol_blocked_big_kernel<<<grid, 256, smem_big, d.st>>>(Qp, ldq, k, nsys, dadd, dadd_sys_stride, dadd_elem_stride, rhs, ldr, z, out,
+                                                              ldo, Lout, d.d_flag, d.chol_ws.p, stride);
+        BSFG_CHECK_LAUNCH(); g_launch_counter++;
+        return;
+    }
     const uint16_t* map = d.chol_map(k);
     if (cb_warps(k, rhs != nullptr) == 4) {
         BSFG_CUDA(cudaFuncSetAttribute(chol_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -160,19 +176,23 @@ static void launch_factor_rows(Device& d, const double* Lp, int k, int n, const 
                                const double* ZFa, long ldz, const double* tau_e, const VarSrc& z, double* F, long ldf,
                                int row0 = 0 /* data pointers are offset to row0; z is addressed with row0 + i */) {
     if (n <= 0) return;
-    const size_t smem = sizeof(double) * ((size_t)k * (k + 1) / 2);
+    // the packed factor is staged in shared memory while it fits (k <= 226); larger factors are read from global memory (L2)
+    const size_t lbytes = sizeof(double) * ((size_t)k * (k + 1) / 2);
+    const bool l_in_smem = lbytes <= 200 * 1024;
+    const size_t smem = l_in_smem ? lbytes : 0;
     const int wpb = 8;
     int blocks = std::min(ceil_div(n, wpb), d.sms * 4);
 #define BSFG_LAUNCH_FR(KT)                                                                                     \
     do {                                                                                                       \
         BSFG_CUDA(cudaFuncSetAttribute(factor_rows_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        factor_rows_kernel<KT><<<blocks, wpb * 32, smem, d.st>>>(Lp, k, n, YL, ldy, ZFa, ldz, tau_e, z, row0, F, ldf); \
+        factor_rows_kernel<KT><<<blocks, wpb * 32, smem, d.st>>>(Lp, k, n, YL, ldy, ZFa, ldz, tau_e, z, row0, F, ldf, l_in_smem ? 1 : 0); \
     } while (0)
     switch (kt_for(k)) {
         case 1: BSFG_LAUNCH_FR(1); break;
         case 2: BSFG_LAUNCH_FR(2); break;
         case 4: BSFG_LAUNCH_FR(4); break;
-        default: BSFG_LAUNCH_FR(8); break;
+        case 8: BSFG_LAUNCH_FR(8); break;
+        default: BSFG_LAUNCH_FR(16); break;
     }
 #undef BSFG_LAUNCH_FR
     BSFG_CHECK_LAUNCH(); g_launch_counter++;
@@ -288,7 +308,7 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
             pair_lo = (int)std::min<long>(np, (long)sc.rank * chunk);
             pair_hi = (int)std::min<long>(np, pair_lo + chunk);
         }
-        dim3 grid(std::min(ceil_div(n, 256), 64), np);
+        dim3 grid(np, std::min(ceil_div(n, 256), 64));
         gram_features_kernel<<<grid, 256, 0, d.st>>>(UtF.p, UtF.ld, n, k, sc.Gt.p, sc.Gt.ld, pair_lo, pair_hi,
                                                      shard_pairs ? sc.need_exact : nullptr);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;

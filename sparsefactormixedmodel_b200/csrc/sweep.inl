@@ -582,6 +582,7 @@ static void finish_timing(bsfg_ctx* c, long long launches_before, int n_iter_tim
 }  // namespace bsfg
 
 extern "C" long long bsfg_launch_count(void) { return bsfg::g_launch_counter; }
+extern "C" int bsfg_k_limit(void) { return bsfg::BSFG_K_LIMIT; }
 
 extern "C" int bsfg_create(const bsfg_config* cfg, bsfg_ctx** out) {
     BSFG_API_BEGIN
@@ -782,8 +783,23 @@ extern "C" int bsfg_upload_constants(bsfg_ctx* c, const bsfg_constants* k) {
     memcpy(&r1, &h_mx[0], 8); memcpy(&r2, &h_mx[1], 8);
     c->resid_s1 = have_m1 ? r1 : -1.0;
     c->resid_s2 = r2;
+    // the residuals are judged relative to the size of the diagonal they are compared with
+    double tol1 = 1e-11, tol2 = 1e-11;
+    {
+        std::vector<double> h1(br), h2(br);
+        c->s1_2.download(h1.data(), d.st); c->s2_2.download(h2.data(), d.st);
+        d.sync();
+        double m1 = 1.0, m2 = 1.0;
+        for (int i = 0; i < br; i++) { m1 = std::max(m1, fabs(h1[i])); m2 = std::max(m2, fabs(h2[i])); }
+        tol1 *= m1; tol2 *= m2;
+    }
     int mode = c->cfg.mode;
-    if (mode == 0) mode = (have_m1 && r1 <= 1e-11 && r2 <= 1e-11) ? 2 : (have_m1 ? 1 : 2);
+    if (mode == 0) {
+        if (have_m1) mode = (r1 <= tol1 && r2 <= tol2) ? 2 : 1;
+        else if (r2 <= tol2) mode = 2;
+        else fail(BSFG_EARG, "Design_U'Design_U differs from diag(s2) by %.3g (tolerance %.3g): the diagonal shortcuts for "
+                             "resid_Y_prec / E_a_prec would be inaccurate; pass Ainv in bsfg_constants so the direct forms can be used", r2, tol2);
+    }
     if (mode == 1 && !have_m1) fail(BSFG_EARG, "mode 'direct' needs Ainv");
     c->mode = mode;
     if (mode == 1) { c->M1th.alloc(br, pl); c->M2th.alloc(br, pl); }

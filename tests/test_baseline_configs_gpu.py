@@ -102,3 +102,11 @@ def test_C5_factor_count_k200():
     reference finishes in seconds (n = 2000, p = 3000), both Gram evaluations."""
     _parity(2000, 3000, 200, "random", 501, gram="expsum")
     _parity(2000, 3000, 200, "random", 501, gram="exact")
+
+
+def test_factor_count_beyond_shared_memory_k300():
+    """k = 300 > 216: the per-trait systems no longer fit shared memory (tiles in the L2 workspace, chol_blocked_big_kernel),
+    the F row solves read the 300 x 300 factor from L2 (factor_rows_kernel<16>), k(k+1)/2 = 45150 Gram features.  The reference
+    allows k < 2p (BSFG_functions.R:332): p = 200."""
+    _parity(260, 200, 300, "random", 601, gram="expsum")
+    _parity(260, 200, 300, "random", 601, gram="exact")

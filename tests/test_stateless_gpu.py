@@ -72,10 +72,11 @@ def test_sample_Lambda_c(pkg, small_problem, gram):
 
 
 @pytest.mark.parametrize("n,p,k", [(33, 17, 3), (100, 257, 20), (250, 100, 40), (64, 50, 70), (96, 24, 128), (80, 21, 136),
-                                   (120, 19, 200), (72, 9, 216)])
+                                   (120, 19, 200), (72, 9, 216), (90, 12, 217), (110, 10, 300), (64, 6, 448)])
 def test_sample_Lambda_c_shapes(pkg, n, p, k, gram):
     """ragged sizes incl. odd n (padded leading dimensions); k across the 4-warp (k <= 128) and 8-warp (k <= 216, the
-    shared-memory limit) instantiations of the blocked Cholesky, incl. k not a multiple of 8."""
+    shared-memory limit) instantiations of the blocked Cholesky, incl. k not a multiple of 8, and beyond the shared-memory
+    limit (tiles in the L2 workspace: k = 217, 300, 448; update_k may grow k towards 2p, BSFG_functions.R:332)."""
     from oracle import checker as O
     rng = np.random.default_rng(n + p + k)
     A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n) * 0.1

@@ -379,7 +379,7 @@ def test_sweep_rejects_inconsistent_calls():
     finally:
         sw.close()
     with pytest.raises(BSFGError) as ei:
-        BSFGSweep(d, rv, pri, rp, k_init=3, k_max=400)
+        BSFGSweep(d, rv, pri, rp, k_init=3, k_max=600)             # beyond bsfg_k_limit() = 504
     assert ei.value.code == _lib.BSFG_ESHAPE
 
 
