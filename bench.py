@@ -519,20 +519,24 @@ def run_ours(args):
     kk_ = k_now
     h2d = 8 * (3 * sw.pl * kk_ + 2 * n * kk_ + sw.b * sw.pl + 2 * sw.pl + 3 * kk_)     # Lambda, Lambda_prec, Plam, F, F_a, B, precisions, delta/tauh/F_h2
     d2h = 8 * (3 * sw.pl * kk_ + n * kk_ + n * kk_ + kk_ + sw.b * sw.pl + 2 * sw.pl + 2 * kk_)
-    sw.set_state(full, local=True); sw.sweep(1); sw.get_state(with_E_a=False, out=host)         # warm the path
+    # N > 1: the replicated members (F, F_a, F_h2, delta, tauh -- bit-identical on every rank) cross PCIe ONCE per direction:
+    # rank 0 uploads them and the library hands them to the other GPUs over NVLink (bsfg_state::bcast_replicated), and only
+    # rank 0 reads them back; every rank moves its own trait shard both ways.  h2d / d2h bytes below are rank 0's (the largest).
+    rep = world == 1 or rank == 0
+    sw.set_state(full, local=True, bcast_replicated=True); sw.sweep(1); sw.get_state(with_E_a=False, out=host, with_replicated=rep)   # warm the path
     barrier()
     t0 = time.perf_counter()
     e2e_parts = [0.0, 0.0, 0.0]
     for _ in range(e2e_steps):
         ta = time.perf_counter()
-        sw.set_state(full, local=True)
+        sw.set_state(full, local=True, bcast_replicated=True)
         tb = time.perf_counter()
         sw.sweep(1)
         tc = time.perf_counter()
-        out = sw.get_state(with_E_a=False, out=host)
+        out = sw.get_state(with_E_a=False, out=host, with_replicated=rep)
         td = time.perf_counter()
         e2e_parts[0] += tb - ta; e2e_parts[1] += tc - tb; e2e_parts[2] += td - tc
-        if not live_k:
+        if not live_k and rep:
             full.update({nm: out[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})   # replicated members carry over
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -621,7 +625,10 @@ def run_ours(args):
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "what": f"{e2e_steps} x [set_state(pinned host current_state) -> bsfg_sweep(1) -> get_state(posterior-sample fields, pinned)]; "
-                        "E_a (r x p) is resampled before use and only read back on request",
+                        "E_a (r x p) is resampled before use and only read back on request"
+                        + ("; replicated members (F, F_a, F_h2, delta, tauh) cross PCIe once per direction on rank 0 (NCCL broadcast "
+                           "to the other GPUs on the way in, read back by rank 0 only); every rank moves its own trait shard; "
+                           "bytes are rank 0's" if world > 1 else ""),
                 "ms_per_step_parts": {"set_state_h2d": 1e3 * e2e_parts[0] / e2e_steps, "sweep": 1e3 * e2e_parts[1] / e2e_steps,
                                       "get_state_d2h": 1e3 * e2e_parts[2] / e2e_steps}},
         "gpu_launches": int(launches),

@@ -214,6 +214,12 @@ typedef struct bsfg_state {
     /* parameter-expanded sampler (fast_BSFG_sampler_px.R): px_factor k, F_px n x k.  Supplying both on set_state puts
      * the context in px mode (F is then ignored: F = F_px / sqrt(px_factor)); get_state returns them when non-NULL. */
     double* px_factor; double* F_px;
+    /* multi-GPU set_state only (world > 1): 1 = the replicated members (F or F_px, F_a, F_h2, delta, tauh, px_factor) are
+     * read from RANK 0's call and handed to the other ranks over NCCL (NVLink) instead of one PCIe upload per GPU; the
+     * other ranks may pass NULL for them.  Every rank must make the call with the same flag, k and nrun.  0: each rank
+     * uploads what it is given.  Ignored by get_state (NULL members are skipped there: only one rank needs to read the
+     * replicated members back, they are bit-identical). */
+    int bcast_replicated;
 } bsfg_state;
 
 /* One iteration's injected variates (NULL members fall back to device Philox).

@@ -60,7 +60,8 @@ class bsfg_state(C.Structure):
     _fields_ = [(nm, c_double_p) for nm in
                 ("Lambda", "Lambda_prec", "Plam", "F", "F_a", "F_h2", "B", "E_a", "resid_Y_prec",
                  "E_a_prec", "delta", "tauh")] + [("k", C.c_int), ("nrun", C.c_int)] + \
-               [("W", c_double_p), ("W_prec", c_double_p), ("px_factor", c_double_p), ("F_px", c_double_p)]
+               [("W", c_double_p), ("W_prec", c_double_p), ("px_factor", c_double_p), ("F_px", c_double_p),
+                ("bcast_replicated", C.c_int)]
 
 
 class bsfg_variates(C.Structure):

@@ -82,6 +82,7 @@ struct bsfg_ctx {
     bsfg::DMat Lt, Lam, Lmsg, LP, Plamt, Ptmp, F, Fa, Bfix, theta, thetat, Ea_in;
     bsfg::DVec F_h2, delta, tauh, rp, ep;
     bool theta_valid = false, derived_valid = false;
+    bool bc_have_fa = false, bc_have_h2 = false;      // set_state with bcast_replicated: what rank 0 supplied
     // derived from F
     bsfg::DMat UtF, FtD, DtF;
     // scratch
@@ -850,8 +851,12 @@ extern "C" int bsfg_get_gram_stats(bsfg_ctx* c, int* mode, int* terms, double* s
 extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
     BSFG_API_BEGIN
     REQUIRE_PTR(c); REQUIRE_PTR(st);
-    REQUIRE_PTR(st->F); REQUIRE_PTR(st->resid_Y_prec); REQUIRE_PTR(st->E_a_prec); REQUIRE_PTR(st->Plam);
-    REQUIRE_PTR(st->delta); REQUIRE_PTR(st->tauh);
+    // replicated members by broadcast from rank 0 (bsfg_state::bcast_replicated): only rank 0 has to supply them
+    const bool bcast = st->bcast_replicated != 0 && c->cfg.world > 1;
+    const bool give = !bcast || c->cfg.rank == 0;
+    if (bcast && !c->comm) fail(BSFG_ESTATE, "bcast_replicated needs bsfg_comm_init");
+    if (give) { REQUIRE_PTR(st->delta); REQUIRE_PTR(st->tauh); }
+    REQUIRE_PTR(st->resid_Y_prec); REQUIRE_PTR(st->E_a_prec); REQUIRE_PTR(st->Plam);
     if (c->b > 0) REQUIRE_PTR(st->B);
     if (c->has_missing) { REQUIRE_PTR(st->Lambda); REQUIRE_PTR(st->E_a); }     // the imputation step conditions on them (R:181)
     const int k = st->k;
@@ -860,17 +865,33 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
     const int n = c->n, pl = c->pl, r = c->r, b = c->b;
     c->k = k;
     c->iter = st->nrun;
-    c->px_mode = st->px_factor != nullptr && st->F_px != nullptr;
+    int px_flag = (st->px_factor != nullptr && st->F_px != nullptr) ? 1 : 0;
+    if (bcast) {    // every rank learns from rank 0 whether this is a px chain and whether F_a / F_h2 come along
+        int flags[3] = {px_flag, st->F_a ? 1 : 0, st->F_h2 ? 1 : 0};
+        int* dflags = reinterpret_cast<int*>(c->colsum_cnt.p);       // 2 k_max doubles of scratch: room for three ints
+        if (c->cfg.rank == 0) BSFG_CUDA(cudaMemcpyAsync(dflags, flags, sizeof flags, cudaMemcpyHostToDevice, d.st));
+        BSFG_NCCL(g_nccl.Broadcast(dflags, dflags, sizeof flags, ncclChar, 0, c->comm, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(flags, dflags, sizeof flags, cudaMemcpyDeviceToHost, d.st));
+        d.sync();
+        px_flag = flags[0];
+        c->bc_have_fa = flags[1] != 0; c->bc_have_h2 = flags[2] != 0;
+    }
+    c->px_mode = px_flag != 0;
     DMat F = view(c->F, n, k);
-    if (c->px_mode) {      // parameter-expanded state: the device keeps F_px (F = F_px / sqrt(px_factor) is derived on get_state)
-        F.upload(st->F_px, d.st);
-        BSFG_CUDA(cudaMemcpyAsync(c->px.p, st->px_factor, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
-    } else {
-        F.upload(st->F, d.st);
+    if (give) {
+        if (c->px_mode) {      // parameter-expanded state: the device keeps F_px (F = F_px / sqrt(px_factor) is derived on get_state)
+            F.upload(st->F_px, d.st);
+            BSFG_CUDA(cudaMemcpyAsync(c->px.p, st->px_factor, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+        } else {
+            REQUIRE_PTR(st->F);
+            F.upload(st->F, d.st);
+        }
     }
     c->rp.upload(st->resid_Y_prec, d.st); c->ep.upload(st->E_a_prec, d.st);
-    BSFG_CUDA(cudaMemcpyAsync(c->delta.p, st->delta, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
-    BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, st->tauh, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    if (give) {
+        BSFG_CUDA(cudaMemcpyAsync(c->delta.p, st->delta, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+        BSFG_CUDA(cudaMemcpyAsync(c->tauh.p, st->tauh, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    }
     if (b > 0) c->Bfix.upload(st->B, d.st);
     {
         DMat Plam = view(c->Ptmp, pl, k), Plamt = view(c->Plamt, k, pl);   // persistent scratch: no cudaMalloc on the state path
@@ -888,8 +909,16 @@ extern "C" int bsfg_set_state(bsfg_ctx* c, const bsfg_state* st) {
         d.transpose(Lam, Lt);
     }
     if (st->Lambda_prec) { DMat LP = view(c->LP, pl, k); LP.upload(st->Lambda_prec, d.st); }
-    if (st->F_a) { DMat Fa = view(c->Fa, r, k); Fa.upload(st->F_a, d.st); }
-    if (st->F_h2) BSFG_CUDA(cudaMemcpyAsync(c->F_h2.p, st->F_h2, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    if (give && st->F_a) { DMat Fa = view(c->Fa, r, k); Fa.upload(st->F_a, d.st); }
+    if (give && st->F_h2) BSFG_CUDA(cudaMemcpyAsync(c->F_h2.p, st->F_h2, sizeof(double) * k, cudaMemcpyHostToDevice, d.st));
+    if (bcast) {
+        auto bc = [&](double* p, size_t count) { BSFG_NCCL(g_nccl.Broadcast(p, p, count, ncclDouble, 0, c->comm, d.st)); };
+        bc(c->F.p, (size_t)c->F.ld * (size_t)k);
+        if (c->bc_have_fa) bc(c->Fa.p, (size_t)c->Fa.ld * (size_t)k);
+        if (c->bc_have_h2) bc(c->F_h2.p, (size_t)k);
+        bc(c->delta.p, (size_t)k); bc(c->tauh.p, (size_t)k);
+        if (c->px_mode) bc(c->px.p, (size_t)k);
+    }
     if (st->E_a) {
         if (c->Ea_in.rows != r) c->Ea_in.alloc(r, pl);
         c->Ea_in.upload(st->E_a, d.st);

@@ -154,12 +154,16 @@ class BSFGSweep:
         return buf.raw
 
     # -- state -----------------------------------------------------------------------------
-    def set_state(self, current_state, local=False):
+    def set_state(self, current_state, local=False, bcast_replicated=False):
         """Upload `current_state` (fast_BSFG_sampler_init.R:238-254 field names); trait-indexed members
         are given for ALL traits and sliced to this rank's shard here, or -- `local=True` -- already hold this
-        rank's shard (what get_state returns), which avoids a host copy per call."""
+        rank's shard (what get_state returns), which avoids a host copy per call.
+        `bcast_replicated=True` (world > 1, a collective call): the replicated members (F / F_px, F_a, F_h2, delta, tauh,
+        px_factor) are uploaded by rank 0 only and reach the other GPUs over NCCL; on ranks > 0 they may be missing from
+        `current_state` (then `k` must be given as current_state["k"])."""
         cs = current_state
-        k = int(np.asarray(cs["F"]).shape[1])
+        k = int(np.asarray(cs["F"]).shape[1]) if cs.get("F") is not None else int(cs["k"])
+        giver = not (bcast_replicated and self.world > 1) or self.rank == 0
         sl = slice(None) if local else slice(self.lo, self.hi)
         arrs = {}
 
@@ -171,19 +175,21 @@ class BSFGSweep:
         st.Lambda = put("Lambda", as_f(np.asarray(cs["Lambda"])[sl, :])) if cs.get("Lambda") is not None else None
         st.Lambda_prec = put("Lambda_prec", as_f(np.asarray(cs["Lambda_prec"])[sl, :])) if cs.get("Lambda_prec") is not None else None
         st.Plam = put("Plam", as_f(np.asarray(cs["Plam"])[sl, :]))
-        st.F = put("F", as_f(cs["F"]))
-        st.F_a = put("F_a", as_f(cs["F_a"])) if cs.get("F_a") is not None else None
-        st.F_h2 = put("F_h2", np.ascontiguousarray(np.asarray(cs["F_h2"], dtype=np.float64).ravel())) if cs.get("F_h2") is not None else None
+        st.F = put("F", as_f(cs["F"])) if giver else None
+        st.F_a = put("F_a", as_f(cs["F_a"])) if giver and cs.get("F_a") is not None else None
+        st.F_h2 = put("F_h2", np.ascontiguousarray(np.asarray(cs["F_h2"], dtype=np.float64).ravel())) if giver and cs.get("F_h2") is not None else None
         st.B = put("B", as_f(np.asarray(cs["B"]).reshape(self.b, -1)[:, sl])) if self.b > 0 else None
         st.E_a = put("E_a", as_f(np.asarray(cs["E_a"])[:, sl])) if cs.get("E_a") is not None else None
         st.resid_Y_prec = put("rp", np.ascontiguousarray(np.asarray(cs["resid_Y_prec"], dtype=np.float64).ravel()[sl]))
         st.E_a_prec = put("ep", np.ascontiguousarray(np.asarray(cs["E_a_prec"], dtype=np.float64).ravel()[sl]))
-        st.delta = put("delta", np.ascontiguousarray(np.asarray(cs["delta"], dtype=np.float64).ravel()))
-        st.tauh = put("tauh", np.ascontiguousarray(np.asarray(cs["tauh"], dtype=np.float64).ravel()))
+        if giver:
+            st.delta = put("delta", np.ascontiguousarray(np.asarray(cs["delta"], dtype=np.float64).ravel()))
+            st.tauh = put("tauh", np.ascontiguousarray(np.asarray(cs["tauh"], dtype=np.float64).ravel()))
         st.k = k
         st.nrun = int(cs.get("nrun", 0))
+        st.bcast_replicated = 1 if (bcast_replicated and self.world > 1) else 0
         self.px_mode = cs.get("px_factor") is not None and cs.get("F_px") is not None
-        if self.px_mode:      # parameter-expanded state (fast_BSFG_sampler_init_px.R:221-222)
+        if self.px_mode and giver:      # parameter-expanded state (fast_BSFG_sampler_init_px.R:221-222)
             st.px_factor = put("px_factor", np.ascontiguousarray(np.asarray(cs["px_factor"], dtype=np.float64).ravel()))
             st.F_px = put("F_px", as_f(cs["F_px"]))
         if self.r2 > 0:
@@ -191,10 +197,11 @@ class BSFGSweep:
             st.W_prec = put("W_prec", np.ascontiguousarray(np.asarray(cs["W_prec"], dtype=np.float64).ravel()[sl]))
         check(self.lib.bsfg_set_state(self._ctx, C.byref(st)))
 
-    def get_state(self, with_E_a=True, out=None):
+    def get_state(self, with_E_a=True, out=None, with_replicated=True):
         """Download this rank's shard of `current_state` (same field names; trait-indexed members cover
         columns [lo, hi) only).  `out`: dict of preallocated F-ordered arrays from `alloc_state` to fill in place
-        (e.g. pinned host memory); valid while k is unchanged."""
+        (e.g. pinned host memory); valid while k is unchanged.  `with_replicated=False` leaves F, F_px, F_a, F_h2, delta,
+        tauh and px_factor where they are (bit-identical on every rank: one rank reading them back is enough)."""
         probe = _lib.bsfg_state()
         check(self.lib.bsfg_get_state(self._ctx, C.byref(probe)))     # all-NULL call: just k and nrun
         k = probe.k
@@ -204,6 +211,8 @@ class BSFGSweep:
         if getattr(self, "px_mode", False) and "px_factor" not in out:
             out["px_factor"] = np.zeros(k); out["F_px"] = np.zeros((self.n, k), order="F")
         for name in _STATE_FIELDS + ("W", "W_prec", "px_factor", "F_px"):
+            if not with_replicated and name in ("F", "F_px", "F_a", "F_h2", "delta", "tauh", "px_factor"):
+                continue
             if name in out and out[name] is not None and out[name].size:
                 setattr(st, name, ptr(out[name]))
         check(self.lib.bsfg_get_state(self._ctx, C.byref(st)))

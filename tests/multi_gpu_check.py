@@ -82,6 +82,20 @@ def main():
         assert torch.equal(t, ref), f"replicated member {name} differs between rank {rank} and rank 0"
     gathered = [None] * world
     dist.all_gather_object(gathered, {nm: got[nm] for nm in ("Lambda", "resid_Y_prec", "E_a_prec", "Lambda_prec")})
+    # the same chain with the replicated members supplied by rank 0 only (bsfg_state::bcast_replicated): the other ranks hand
+    # over just their trait shards; the result must be bit-identical to the run above
+    shard = {nm: cs[nm] for nm in ("Lambda", "Lambda_prec", "Plam", "B", "E_a", "resid_Y_prec", "E_a_prec")}
+    shard["nrun"] = cs.get("nrun", 0); shard["k"] = k
+    if rank == 0:
+        shard.update({nm: cs[nm] for nm in ("F", "F_a", "F_h2", "delta", "tauh")})
+    sw.set_state(shard, bcast_replicated=True)
+    sw.sweep(6)
+    again = sw.get_state(with_E_a=False, with_replicated=(rank == 0))
+    for nm in ("Lambda", "resid_Y_prec", "E_a_prec", "Lambda_prec"):
+        assert np.array_equal(again[nm], got[nm]), f"bcast_replicated changed {nm} on rank {rank}"
+    if rank == 0:
+        for nm in ("F", "F_a", "F_h2", "delta", "tauh"):
+            assert np.array_equal(again[nm], got[nm]), f"bcast_replicated changed {nm}"
     sw.close()
     if rank == 0:
         one = BSFGSweep(d, rv, pri, rp, k_init=k, k_max=12, seed=99)

@@ -31,6 +31,12 @@ def test_trait_sharded_sweep_matches_oracle_and_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    try:        # keep the ranks' own report (evidence of the world size the check ran at) next to the other GPU-side outputs
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"multi_gpu_check_world{world}.log"), "w") as f:
+            f.write(out.stdout[-20000:] + "\n--- stderr (tail) ---\n" + out.stderr[-4000:])
+    except OSError:
+        pass
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"multi_gpu_check ok world={world}" in out.stdout
     assert f"multi_gpu_check ok (Z_2 + missing data) world={world}" in out.stdout
