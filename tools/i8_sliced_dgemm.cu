@@ -1,5 +1,6 @@
-// Round-2 scaffolding, NOT part of the product and NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent;
-// it compiles for sm_100a).  Second step after tools/i8_umma_gemm.cu: the whole INT8-slice emulation of an FP64 "TN" GEMM
+// Stand-alone experiment, NOT part of the product.
+// Run on a B200 in round 2 with S = 6, 7, 8: accuracy and rates in profiles/r02_i8_sliced_dgemm.log.
+// Second step after tools/i8_umma_gemm.cu: the whole INT8-slice emulation of an FP64 "TN" GEMM
 // (numerics in tools/ozaki_prototype.py) as one stand-alone program, so that accuracy and speed
 // of the scheme can be measured on a B200 before anything is wired into the sweep:
 //

@@ -1,5 +1,6 @@
-// Round-2 scaffolding, NOT part of the product and NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent;
-// it compiles for sm_100a).  Stand-alone microbenchmark of the building block that DESIGN.md section 9 plans for the
+// Stand-alone experiment, NOT part of the product.
+// Run on a B200 in round 2: both self-checks exact, 73.8 / 441.8 / 1691.5 TOP/s on the three timing shapes (profiles/r02_i8_umma_gemm.log).
+// Stand-alone microbenchmark of the building block that DESIGN.md section 9 plans for the
 // sweep's GEMMs: an INT8 x INT8 -> INT32 GEMM on the tcgen05 tensor pipe with TMEM accumulators, i.e. one "slice
 // product" of the INT8-slice emulation of FP64 (tools/ozaki_prototype.py).  It answers two questions before any
 // integration work: (1) are the hand-built shared-memory / instruction descriptors right (self-check against a CPU
