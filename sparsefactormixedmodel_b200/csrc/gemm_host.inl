@@ -37,18 +37,26 @@ constexpr int GEMM_STAGES = 6;
 
 static long long g_launch_counter = 0;   // kernels launched by this library (bench.py's gpu_launches)
 
+static bool persistent_enabled() {
+    static const bool on = [] { const char* e = getenv("BSFG_GEMM_PERSISTENT"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
 template <int BM>
-static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, dim3 grid) {
+static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, dim3 grid, bool streamk) {
     using Cfg = GemmSmem<BM, 128, GEMM_STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
         BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
+        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_streamk_kernel<BM, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
         attr_set = true;
     }
     // WM = 2 ((BM/2) x 32 warp tiles) for every shape: the all-rows / all-columns layouts (WM = 1 / 8) that skip the empty
     // fragments of M = k or N = k products evenly were measured SLOWER on B200 (sweep 13.3 -> 14.0 ms at C4: 18 instead
     // of 12 fragment loads per 32 DMMAs and a predicated DMMA sequence), so they are not instantiated.
-    dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
+    // The stream-K decomposition is a separate kernel (gemm_dmma.cuh says why).
+    if (streamk) dgemm_tn_streamk_kernel<BM, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
+    else dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
 }
 
 static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
@@ -88,11 +96,13 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     if (ws) {
         const double per = (double)M * (double)N;
         const double kt_us = 2.1 * BM / 128.0;
+        static const double item_us = [] { const char* e = getenv("BSFG_GEMM_ITEM_US"); return e ? atof(e) : 8.0; }();
+        static const double red_scale = [] { const char* e = getenv("BSFG_GEMM_RED_SCALE"); return e ? atof(e) : 1.0; }();
         auto cost = [&](int s) {
             const long ctas = (long)tiles * s;
             const double waves = (double)((ctas + sm_count - 1) / sm_count);
-            double c = waves * (ceil_div(ktiles, s) * kt_us + 8.0);
-            if (s > 1) c += 16e-6 * s * per / 5.0 + 5.0;
+            double c = waves * (ceil_div(ktiles, s) * kt_us + item_us);
+            if (s > 1) c += red_scale * (16e-6 * s * per / 5.0 + 5.0);
             return c;
         };
         double best = cost(1);
@@ -106,27 +116,54 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     splits = ceil_div(ktiles, g.ktiles_per_split);    // no empty splits
     g.splits = splits;
     g.ws = ws;
+    // Stream-K (BSFG_GEMM_STREAMK=0 turns it off): when the (tile, split) items of the plan above do not fill whole waves
+    // -- 157 column tiles x 5 splits = 5.3 waves of 148 SMs run as 6 -- cut the tiles x k-tiles work into one equal
+    // contiguous run per SM instead.  Complete tiles are stored directly; only the (at most two per CTA, when a run is
+    // longer than a tile) partial pieces go through the workspace.  Used when it removes at least 4% of idle SM time and the
+    // slots fit the workspace; products with many waves of whole tiles keep the plain persistent tiling.
+    static const bool sk_ok = [] { const char* e = getenv("BSFG_GEMM_STREAMK"); return !e || atoi(e) != 0; }();
+    bool use_sk = false;
+    long sk_total = 0;
+    if (sk_ok && ws && persistent_enabled()) {
+        const long items0 = (long)tiles * splits;
+        const double fill = (double)items0 / ((double)sm_count * (double)((items0 + sm_count - 1) / sm_count));
+        const long U = (long)tiles * ktiles;
+        const long G = std::min<long>(sm_count, std::max<long>(1, U / 4));       // at least 4 k-tiles per CTA
+        const int P = (int)((U + G - 1) / G);
+        const long slots = (ktiles + P - 1) / P + 1;
+        if (fill < 0.96 && G == sm_count && (double)slots * (double)M * (double)N <= (double)ws_doubles) {
+            use_sk = true; sk_total = U;
+            g.ktiles_per_split = P;
+            g.splits = 1;
+        }
+    }
     // Fused reduction (the last CTA to deliver a partial of a tile sums them): OFF by default.  Measured at C4 on one B200
     // (profiles/r02c_bench_c4_n1_fused_reduce_{on,off}.json): 11.64 ms per iteration with it, 10.81 ms without -- the summing
     // CTA reads splits x 112 x 128 partials through one SM while its neighbours idle at the end of the wave, which costs
     // more than the 14 reduce launches it saves.  BSFG_GEMM_FUSED_REDUCE=1 turns it on (results are identical: same order).
     static const bool fuse_ok = [] { const char* e = getenv("BSFG_GEMM_FUSED_REDUCE"); return e && atoi(e) != 0; }();
-    const bool fused = fuse_ok && splits > 1 && splits <= 16 && counters && tiles <= 65536 && run_if == nullptr;
+    const bool fused = fuse_ok && !use_sk && splits > 1 && splits <= 16 && counters && tiles <= 65536 && run_if == nullptr;
     g.tile_counter = fused ? counters : nullptr;
     // persistent launch: one CTA per SM walks the (tile, split) items; BSFG_GEMM_PERSISTENT=0 launches one CTA per item
-    static const bool persistent = [] { const char* e = getenv("BSFG_GEMM_PERSISTENT"); return !e || atoi(e) != 0; }();
+    const bool persistent = persistent_enabled();
     const long items = (long)tiles * splits;
-    dim3 grid((unsigned)(persistent ? std::min<long>(items, sm_count) : items));
+    dim3 grid((unsigned)(use_sk ? ceil_div(sk_total, g.ktiles_per_split) : (persistent ? std::min<long>(items, sm_count) : items)));
     switch (BM) {
-        case 32: launch_gemm<32>(st, tmA, tmB, g, grid); break;
-        case 64: launch_gemm<64>(st, tmA, tmB, g, grid); break;
-        case 96: launch_gemm<96>(st, tmA, tmB, g, grid); break;
-        case 112: launch_gemm<112>(st, tmA, tmB, g, grid); break;
-        default: launch_gemm<128>(st, tmA, tmB, g, grid); break;
+        case 32: launch_gemm<32>(st, tmA, tmB, g, grid, use_sk); break;
+        case 64: launch_gemm<64>(st, tmA, tmB, g, grid, use_sk); break;
+        case 96: launch_gemm<96>(st, tmA, tmB, g, grid, use_sk); break;
+        case 112: launch_gemm<112>(st, tmA, tmB, g, grid, use_sk); break;
+        default: launch_gemm<128>(st, tmA, tmB, g, grid, use_sk); break;
     }
     BSFG_CHECK_LAUNCH();
     g_launch_counter++;
-    if (splits > 1 && !fused) {
+    if (use_sk) {
+        const size_t total = (size_t)M * N;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count * 8);
+        streamk_reduce_kernel<128><<<blocks, 256, 0, st>>>(g, BM);
+        BSFG_CHECK_LAUNCH();
+        g_launch_counter++;
+    } else if (splits > 1 && !fused) {
         const size_t total = (size_t)M * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > sm_count * 8) blocks = sm_count * 8;

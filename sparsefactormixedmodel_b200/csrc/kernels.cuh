@@ -345,6 +345,10 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 // row pair is one aligned Philox pair (an odd rows_total falls back to one block per draw).
 constexpr int MEANS_BMAX = 4;
 constexpr int MEANS_TC = 16;
+#ifndef MEANS_CPL
+#define MEANS_CPL 4          // traits per lane: 4 -> 8 row pairs x 4 trait groups per warp, 2 -> 4 row pairs x 8 trait groups
+#endif
+constexpr int MEANS_NRP = 32 / (MEANS_TC / MEANS_CPL);      // row pairs per warp step
 constexpr int MEANS_THREADS = 128;
 // gridDim.y CTAs split the rows of a trait tile (rows_per_cta each, a multiple of 64); with Bout they leave partial sums in
 // Bpart[gridDim.y][p][MEANS_BMAX] and the last one to finish (counter[blockIdx.x], self-resetting) adds them in split order.
@@ -358,15 +362,15 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
     __shared__ double red[MEANS_THREADS / 32][MEANS_TC][MEANS_BMAX];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rpi = lane & 7, cg = lane >> 3;
-    const int j0 = blockIdx.x * MEANS_TC + cg * 4;          // first of this lane's four traits
-    const int nc = max(0, min(4, p - j0));
-    double rpj[4], epj[4];
-    const double* dcol[4];
-    double* tcol[4];
-    uint64_t base[4];
+    const int rpi = lane % MEANS_NRP, cg = lane / MEANS_NRP;
+    const int j0 = blockIdx.x * MEANS_TC + cg * MEANS_CPL;          // first of this lane's traits
+    const int nc = max(0, min(MEANS_CPL, p - j0));
+    double rpj[MEANS_CPL], epj[MEANS_CPL];
+    const double* dcol[MEANS_CPL];
+    double* tcol[MEANS_CPL];
+    uint64_t base[MEANS_CPL];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < MEANS_CPL; c++) {
         const int j = min(j0 + c, p - 1);
         rpj[c] = rp[j]; epj[c] = ep[j];
         dcol[c] = DtYt + (long)j * ldd;
@@ -374,13 +378,13 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
         base[c] = (uint64_t)(j + zsrc.col_offset) * (uint64_t)zsrc.rows_total;
     }
     const bool paired = (zsrc.rows_total & 1) == 0;
-    double acc[4][MEANS_BMAX];
+    double acc[MEANS_CPL][MEANS_BMAX];
 #pragma unroll
-    for (int c = 0; c < 4; c++)
+    for (int c = 0; c < MEANS_CPL; c++)
 #pragma unroll
         for (int cc = 0; cc < MEANS_BMAX; cc++) acc[c][cc] = 0.0;
     const int row_lo = blockIdx.y * rows_per_cta, row_hi = min(br, row_lo + rows_per_cta);
-    for (int r0 = row_lo + (warp * 8 + rpi) * 2; r0 < row_hi; r0 += (MEANS_THREADS / 32) * 16) {
+    for (int r0 = row_lo + (warp * MEANS_NRP + rpi) * 2; r0 < row_hi; r0 += (MEANS_THREADS / 32) * MEANS_NRP * 2) {
         const bool has1 = r0 + 1 < br;
         const double s1a = s1[r0], s2a = s2[r0];
         const double s1b = has1 ? s1[r0 + 1] : 1.0, s2b = has1 ? s2[r0 + 1] : 1.0;
@@ -392,12 +396,12 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
                 ub[cc] = (cc < b && has1) ? Ut[(long)cc * ldu + r0 + 1] : 0.0;
             }
         }
-        double2 vin[4];                          // the four 16-byte loads are in flight before the first Box-Muller starts
+        double2 vin[MEANS_CPL];                          // the four 16-byte loads are in flight before the first Box-Muller starts
 #pragma unroll
-        for (int c = 0; c < 4; c++) vin[c] = c < nc ? *reinterpret_cast<const double2*>(dcol[c] + r0) : make_double2(0.0, 0.0);
-        double th[4][2];
+        for (int c = 0; c < MEANS_CPL; c++) vin[c] = c < nc ? *reinterpret_cast<const double2*>(dcol[c] + r0) : make_double2(0.0, 0.0);
+        double th[MEANS_CPL][2];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < MEANS_CPL; c++) {
             th[c][0] = th[c][1] = 0.0;
             if (c < nc) {
                 double z0, z1;
@@ -430,9 +434,9 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
             for (int e = 0; e < 2; e++) {
                 if (e == 1 && !has1) break;
                 double* dst = thetat + (long)(r0 + e) * ldtt + j0;       // ldtt even, j0 % 4 == 0: 16-byte aligned
-                if (nc == 4) {
-                    reinterpret_cast<double2*>(dst)[0] = make_double2(th[0][e], th[1][e]);
-                    reinterpret_cast<double2*>(dst)[1] = make_double2(th[2][e], th[3][e]);
+                if (nc == MEANS_CPL) {
+#pragma unroll
+                    for (int c = 0; c < MEANS_CPL; c += 2) reinterpret_cast<double2*>(dst)[c >> 1] = make_double2(th[c][e], th[c + 1][e]);
                 } else {
                     for (int c = 0; c < nc; c++) dst[c] = th[c][e];
                 }
@@ -441,14 +445,13 @@ means_theta_kernel(const double* __restrict__ DtYt, long ldd, int br, int p,
     }
     if (Bout) {
 #pragma unroll
-        for (int c = 0; c < 4; c++)
+        for (int c = 0; c < MEANS_CPL; c++)
 #pragma unroll
             for (int cc = 0; cc < MEANS_BMAX; cc++) {
                 double v = acc[c][cc];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                if (rpi == 0) red[warp][cg * 4 + c][cc] = v;
+#pragma unroll
+                for (int o = 1; o < MEANS_NRP; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (rpi == 0) red[warp][cg * MEANS_CPL + c][cc] = v;
             }
         __syncthreads();
         const bool split = gridDim.y > 1;
