@@ -331,12 +331,13 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 // sample_means element-wise step (cpp:75-78 without the U product):
 //   theta[i,j] = (DtYt[i,j] * rp_j) / d + z[i,j] / sqrt(d),  d = s1_i ep_j + s2_i rp_j
 // ------------------------------------------------------------------------------------
-// One CTA per MEANS_TC = 16 consecutive traits.  A warp covers a 16-row x 16-trait tile: lane (rp, cg) owns the row pair
-// (2 rp, 2 rp + 1) of the four traits 4 cg .. 4 cg + 3, so
+// One CTA per MEANS_TC = 16 consecutive traits.  A warp covers an 8-row x 16-trait tile per step: lane (rp, cg) owns the row
+// pair (2 rp, 2 rp + 1), rp = 0..3, of the two traits 2 cg, 2 cg + 1, cg = 0..7 (MEANS_CPL = 2 traits per lane: measured 7%
+// faster than 4 traits x 8 row pairs, 122 instead of 128 registers and no spills), so
 //   * the two rows of a pair share one Philox block (one Box-Muller transform per two draws),
-//   * DtYt is read and theta written as 16-byte pairs, 8 lanes side by side = one 128-byte line per trait,
+//   * DtYt is read and theta written as 16-byte pairs, 4 lanes side by side = 64 contiguous bytes per trait,
 //   * theta' (p x br; the K = p operand of theta Lmsg, R:230), when thetat != null, is written from the same registers as
-//     32 bytes per lane, 4 lanes side by side = one 128-byte line per row -- no transpose pass over the br x p array.
+//     16 bytes per lane, 8 lanes side by side = one 128-byte line per row -- no transpose pass over the br x p array.
 // When Bout != null the first b (<= MEANS_BMAX) rows of location_sample = U theta (cpp:78), i.e. B
 // (fast_BSFG_sampler.R:206), are reduced in the same pass: B[c,j] = sum_i U[c,i] theta[i,j], U given transposed
 // (Ut[i,c], column c contiguous); fixed summation order (shuffles, then warps in order).
@@ -346,7 +347,7 @@ factor_rows_kernel(const double* __restrict__ Lp, int k, int n, const double* __
 constexpr int MEANS_BMAX = 4;
 constexpr int MEANS_TC = 16;
 #ifndef MEANS_CPL
-#define MEANS_CPL 4          // traits per lane: 4 -> 8 row pairs x 4 trait groups per warp, 2 -> 4 row pairs x 8 trait groups
+#define MEANS_CPL 2          // traits per lane: 4 -> 8 row pairs x 4 trait groups per warp, 2 -> 4 row pairs x 8 trait groups
 #endif
 constexpr int MEANS_NRP = 32 / (MEANS_TC / MEANS_CPL);      // row pairs per warp step
 constexpr int MEANS_THREADS = 128;
