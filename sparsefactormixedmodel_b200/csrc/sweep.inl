@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <nccl.h>
+#include <cuda_profiler_api.h>
 
 namespace bsfg {
 
@@ -113,7 +114,7 @@ struct bsfg_ctx {
     bool side_ready = false;
     ncclComm_t comm2 = nullptr;
     bsfg::DVec gstage2;
-    cudaEvent_t ev_forkA = nullptr, ev_joinA = nullptr, ev_forkB = nullptr, ev_joinB = nullptr;
+    cudaEvent_t ev_forkA = nullptr, ev_joinA = nullptr, ev_forkB = nullptr, ev_joinB = nullptr, ev_forkC = nullptr, ev_joinC = nullptr;
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_phase;     // (N_PHASES + 1) per iteration slot, reused
@@ -218,10 +219,12 @@ static bool side_enabled(bsfg_ctx* c) {
     if (c->cfg.world > 1 && !c->comm2) return false;
     if (!c->side_ready) {
         c->dev2.init();
+        cudaFree(c->dev2.d_flag);
+        c->dev2.d_flag = c->dev.d_flag;          // one not-positive-definite flag for the context
         // the staging buffer is sized before any concurrent use (a cudaMalloc in the middle of the sweep would serialise the streams)
         const long rows = std::max<long>(std::max(c->n, c->r), c->br);
         if (c->cfg.world > 1) c->gstage2.alloc(round_up(ceil_div(rows, c->cfg.world), 2) * c->kmax * c->cfg.world);
-        for (cudaEvent_t* e : {&c->ev_forkA, &c->ev_joinA, &c->ev_forkB, &c->ev_joinB})
+        for (cudaEvent_t* e : {&c->ev_forkA, &c->ev_joinA, &c->ev_forkB, &c->ev_joinB, &c->ev_forkC, &c->ev_joinC})
             BSFG_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         c->side_ready = true;
     }
@@ -419,6 +422,23 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
         // then the blocks are all-gathered (bit-identical F on every rank)
         DMat YL = view(c->YL, n, k);
         const RowShard sn = row_shard(c, n);
+        // the k x k factor of Lambda'Lmsg + diag(tau_e) (cpp:149) needs the reduced Lambda'Lmsg and F_h2 only: with the side
+        // stream it is formed beside the Design_U product below
+        auto factor_kxk = [&](Device& dd) {
+            if (px) tau_e_px_kernel<<<ceil_div(k, 128), 128, 0, dd.st>>>(c->F_h2.p, c->px.p, k, c->tau_e.p);
+            else tau_e_kernel<<<ceil_div(k, 128), 128, 0, dd.st>>>(c->F_h2.p, k, c->tau_e.p);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            pack_lower_kernel<<<ceil_div((long)k * (k + 1) / 2, 256), 256, 0, dd.st>>>(LtL.p, LtL.ld, k, c->Lp.p);
+            BSFG_CHECK_LAUNCH(); g_launch_counter++;
+            VarSrc none = make_var(nullptr, 0, 0, 0, 0, 1);
+            launch_chol_solve(dd, c->Lp.p, 0, k, 1, c->tau_e.p, 0, 1, nullptr, 0, none, nullptr, 0, c->Lfac.p);
+        };
+        if (side) {
+            BSFG_CUDA(cudaEventRecord(c->ev_forkC, d.st));
+            BSFG_CUDA(cudaStreamWaitEvent(c->dev2.st, c->ev_forkC, 0));
+            factor_kxk(c->dev2);
+            BSFG_CUDA(cudaEventRecord(c->ev_joinC, c->dev2.st));
+        }
         if (sn.cnt > 0)                                                                  // YL = Y Lmsg - Design_U (theta Lmsg)
             dgemm_tn(d.st, d.sms, (int)sn.cnt, k, br, -1.0, c->DUt.p + sn.lo * c->DUt.ld, c->DUt.ld, P2.p, P2.ld, 1.0,
                      P1.p + sn.lo, P1.ld, YL.p + sn.lo, YL.ld, d.ws.p, Device::WS_DOUBLES);
@@ -434,13 +454,8 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
             else gemm_rows(c, sn, 1.0, c->Z1t, Fa_use, 0.0, ZFa);
             zfa_p = ZFa.p; zfa_ld = ZFa.ld;
         }
-        if (px) tau_e_px_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, c->px.p, k, c->tau_e.p);
-        else tau_e_kernel<<<ceil_div(k, 128), 128, 0, d.st>>>(c->F_h2.p, k, c->tau_e.p);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        pack_lower_kernel<<<ceil_div((long)k * (k + 1) / 2, 256), 256, 0, d.st>>>(LtL.p, LtL.ld, k, c->Lp.p);
-        BSFG_CHECK_LAUNCH(); g_launch_counter++;
-        VarSrc none = make_var(nullptr, 0, 0, 0, 0, 1);
-        launch_chol_solve(d, c->Lp.p, 0, k, 1, c->tau_e.p, 0, 1, nullptr, 0, none, nullptr, 0, c->Lfac.p);
+        if (side) BSFG_CUDA(cudaStreamWaitEvent(d.st, c->ev_joinC, 0));
+        else factor_kxk(d);
         launch_factor_rows(d, c->Lfac.p, k, (int)sn.cnt, YL.p + sn.lo, YL.ld, zfa_p + sn.lo, zfa_ld, c->tau_e.p, v.zF,
                            F.p + sn.lo, F.ld, (int)sn.lo);
         gather_rows(c, sn, F);
@@ -639,9 +654,8 @@ extern "C" int bsfg_destroy(bsfg_ctx* c) {
     cudaStreamSynchronize(c->dev.st);
     if (c->side_ready) {
         cudaStreamSynchronize(c->dev2.st);
-        for (cudaEvent_t e : {c->ev_forkA, c->ev_joinA, c->ev_forkB, c->ev_joinB})
+        for (cudaEvent_t e : {c->ev_forkA, c->ev_joinA, c->ev_forkB, c->ev_joinB, c->ev_forkC, c->ev_joinC})
             if (e) cudaEventDestroy(e);
-        if (c->dev2.d_flag) cudaFree(c->dev2.d_flag);
         if (c->dev2.means.Bpart) cudaFree(c->dev2.means.Bpart);
         if (c->dev2.means.counter) cudaFree(c->dev2.means.counter);
         if (c->dev2.st) cudaStreamDestroy(c->dev2.st);
@@ -1076,7 +1090,15 @@ static int sweep_impl(bsfg_ctx* c, int n_iter, bool px) {
         v.zY = make_var(nullptr, seed, SITE_Z_Y, ii, c->p_off, c->n);
         v.gPX = make_var(nullptr, seed, SITE_G_PX, ii, 0, 1);
         c->phase_timing = (it == n_iter - 1);
+        // BSFG_PROFILE_ITER=<n>: bracket the n-th Gibbs iteration of this process (0-based) with cudaProfilerStart/Stop, so that
+        // `ncu --profile-from-start off` captures exactly one warm iteration (tools/profile_iteration.sh)
+        static const long prof_iter = [] { const char* e = getenv("BSFG_PROFILE_ITER"); return e ? atol(e) : -1L; }();
+        static long iters_run = 0;
+        const bool prof = prof_iter >= 0 && iters_run == prof_iter;
+        if (prof) { d.sync(); cudaProfilerStart(); }
         gibbs_iteration(c, v, false, px);
+        if (prof) { d.sync(); if (c->side_ready) cudaStreamSynchronize(c->dev2.st); cudaProfilerStop(); }
+        iters_run++;
         RngStream rs{seed, SITE_U_K, ii};
         c->iter = i;             // the Gibbs body of iteration i has run: an update_k failure must not leave the chain half-stepped
         update_k_step(c, i, philox_uniform(rs, 0), nullptr);               // uu = runif(1) every iteration, R:325

@@ -1,4 +1,4 @@
-"""One table per `ncu --set full` capture: `python tools/summarize_ncu.py gpurun_out/prof_X.ncu-rep profiles/rNN_ncu_X.md "title"`.
+"""One table per `ncu --set full` capture: `python tools/summarize_ncu.py gpurun_out/prof_X.ncu-rep|X_raw.csv profiles/rNN_ncu_X.md "title"`.
 Per launch: duration, DRAM bytes read / written, achieved GB/s against the measured HBM copy rate (MEASURED_PEAKS.json),
 occupancy, registers, FP64-pipe and issue utilisation, shared-memory bank conflicts, the top stall reasons."""
 import csv
@@ -17,7 +17,10 @@ def main():
         hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         hbm = 6553.9
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):        # already exported on the GPU box (`ncu -i X.ncu-rep --page raw --csv`)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
