@@ -115,7 +115,7 @@ struct GemmSmem {
 template <int BM, int BN, int STAGES, int WM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
-    static_assert(BN == 128 && BM % 16 == 0 && BM >= 16 && BM <= 128, "128-column CTA tiles of 16..128 rows");
+    static_assert(BN == 128 && BM % (8 * WM) == 0 && BM >= 16 && BM <= 128, "128-column CTA tiles of 16..128 rows");
     static_assert(WM == 1 || WM == 2 || WM == 8, "supported warp layouts");
     constexpr int WN = GEMM_CONSUMERS / WM;
     constexpr int FM = (BM / 8) / WM;      // 8-row fragments per warp
@@ -338,7 +338,7 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BM, int BN, int STAGES, int WM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_tn_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
-    static_assert(BN == 128 && BM % 16 == 0 && BM >= 16 && BM <= 128, "128-column CTA tiles of 16..128 rows");
+    static_assert(BN == 128 && BM % (8 * WM) == 0 && BM >= 16 && BM <= 128, "128-column CTA tiles of 16..128 rows");
     static_assert(WM == 1 || WM == 2 || WM == 8, "supported warp layouts");
     constexpr bool SK = true;
     constexpr int WN = GEMM_CONSUMERS / WM;

@@ -45,26 +45,42 @@ static bool persistent_enabled() {
 template <int BM>
 static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, dim3 grid, bool streamk) {
     using Cfg = GemmSmem<BM, 128, GEMM_STAGES>;
+    // Warp layout WM x (8 / WM): WM = 2 ((BM/2) x 32 warp tiles) for every multiple of 16; the one tile height that is not,
+    // BM = 104 (13 row fragments: M = k = 97..104 factors, e.g. the k = 100 of C4 without the 12% zero fill of a 112-row
+    // tile), runs as WM = 1 (104 x 16 warp tiles, 15 fragment loads per 26 DMMAs, no predicated DMMA).  The all-rows /
+    // all-columns layouts for the OTHER heights were measured slower on B200 (sweep 13.3 -> 14.0 ms at C4: 18 instead of 12
+    // fragment loads per 32 DMMAs and a predicated DMMA sequence) and are not instantiated.
+    constexpr int WM = (BM % 16 == 0) ? 2 : 1;
     static bool attr_set = false;
     if (!attr_set) {
-        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
-        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_streamk_kernel<BM, 128, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
+        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_kernel<BM, 128, GEMM_STAGES, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
+        BSFG_CUDA(cudaFuncSetAttribute(dgemm_tn_streamk_kernel<BM, 128, GEMM_STAGES, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL));
         attr_set = true;
     }
-    // WM = 2 ((BM/2) x 32 warp tiles) for every shape: the all-rows / all-columns layouts (WM = 1 / 8) that skip the empty
-    // fragments of M = k or N = k products evenly were measured SLOWER on B200 (sweep 13.3 -> 14.0 ms at C4: 18 instead
-    // of 12 fragment loads per 32 DMMAs and a predicated DMMA sequence), so they are not instantiated.
     // The stream-K decomposition is a separate kernel (gemm_dmma.cuh says why).
-    if (streamk) dgemm_tn_streamk_kernel<BM, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
-    else dgemm_tn_kernel<BM, 128, GEMM_STAGES, 2><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
+    if (streamk) dgemm_tn_streamk_kernel<BM, 128, GEMM_STAGES, WM><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
+    else dgemm_tn_kernel<BM, 128, GEMM_STAGES, WM><<<grid, GEMM_THREADS, Cfg::TOTAL, st>>>(tmA, tmB, g);
 }
 
 static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, double alpha, const double* At, long lda,
                           const double* Bm, long ldb, double beta, const double* Cin, long ldcin, double* C, long ldc,
                           double* ws, size_t ws_doubles, const int* run_if, int trans_out) {
     // row-tile height: the smallest instantiated BM that holds a single short row tile, else 128
+    // row-tile height: 128 unless another instantiated height wastes at least 3% fewer rows on zero fill (a single short row
+    // tile for M = k factors: 104 rows for k = 100 instead of 112 (measured: sweep 10.30 -> 10.05 ms at C4); two 104-row tiles
+    // for k = 200 instead of two of 128)
+    static const bool bm104 = [] { const char* e = getenv("BSFG_GEMM_BM104"); return !e || atoi(e) != 0; }();
     int BM = 128;
-    if (M <= 112) BM = M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 96 ? 96 : 112));
+    {
+        const long pad128 = (long)ceil_div(M, 128) * 128;
+        long best = pad128;
+        for (int cand : {112, 104, 96, 64, 32}) {
+            if (cand == 104 && !bm104) continue;
+            if (cand < 96 && M > cand) continue;          // the short tiles only as a single row tile
+            const long pad = (long)ceil_div(M, cand) * cand;
+            if (pad < best && (double)pad <= 0.97 * (double)pad128) { best = pad; BM = cand; }
+        }
+    }
     CUtensorMap tmA, tmB;
     make_operand_map(&tmA, At, K, M, lda, BM);
     make_operand_map(&tmB, Bm, K, N, ldb, 128);
@@ -152,6 +168,7 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
         case 32: launch_gemm<32>(st, tmA, tmB, g, grid, use_sk); break;
         case 64: launch_gemm<64>(st, tmA, tmB, g, grid, use_sk); break;
         case 96: launch_gemm<96>(st, tmA, tmB, g, grid, use_sk); break;
+        case 104: launch_gemm<104>(st, tmA, tmB, g, grid, use_sk); break;
         case 112: launch_gemm<112>(st, tmA, tmB, g, grid, use_sk); break;
         default: launch_gemm<128>(st, tmA, tmB, g, grid, use_sk); break;
     }
