@@ -8,6 +8,7 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-exact-leg"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 BSFG_PROFILE_ITER=4 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+[ "${PROFILE_FULL:-1}" = "1" ] || exit 0
 BSFG_PROFILE_ITER=4 ncu --profile-from-start off --set full --clock-control none \
     -o /tmp/prof_${TAG}_iteration $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
