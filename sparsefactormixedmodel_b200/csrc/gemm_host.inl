@@ -147,7 +147,9 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
         const long G = std::min<long>(sm_count, std::max<long>(1, U / 4));       // at least 4 k-tiles per CTA
         const int P = (int)((U + G - 1) / G);
         const long slots = (ktiles + P - 1) / P + 1;
-        if (fill < 0.96 && G == sm_count && (double)slots * (double)M * (double)N <= (double)ws_doubles) {
+        // not for products with few k-tiles per tile (K = k, K = R): they are mostly epilogue, and a partial piece costs a
+        // workspace round trip on top of it (measured at N = 8: the K = 100 product of the theta step 0.28 -> 0.39 ms)
+        if (fill < 0.96 && ktiles >= 48 && G == sm_count && (double)slots * (double)M * (double)N <= (double)ws_doubles) {
             use_sk = true; sk_total = U;
             g.ktiles_per_split = P;
             g.splits = 1;
@@ -164,6 +166,9 @@ static void dgemm_tn_impl(cudaStream_t st, int sm_count, int M, int N, int K, do
     const bool persistent = persistent_enabled();
     const long items = (long)tiles * splits;
     dim3 grid((unsigned)(use_sk ? ceil_div(sk_total, g.ktiles_per_split) : (persistent ? std::min<long>(items, sm_count) : items)));
+    // (Tried in round 2 and removed: a variant of the kernel for the nearly-all-epilogue K = k product that sends every thread's
+    // 64 Cin values to a private shared-memory slot with 8-byte cp.async at the start of the tile -- three ring stages + a
+    // 128 KB staging tile.  Measured SLOWER at C4: the product 0.91 -> 1.09 ms, theta phase 1.73 -> 1.91 ms.)
     switch (BM) {
         case 32: launch_gemm<32>(st, tmA, tmB, g, grid, use_sk); break;
         case 64: launch_gemm<64>(st, tmA, tmB, g, grid, use_sk); break;

@@ -22,7 +22,9 @@ def pkg():
                                    (257, 129, 33), (64, 64, 4097), (300, 20, 515),
                                    # stream-K decompositions: several pieces per tile, pieces spanning tile boundaries, complete
                                    # and partial tiles in one launch, the transposed-store path, a single tile over a long K
-                                   (100, 5000, 2000), (3000, 100, 4000), (700, 650, 333), (100, 100, 20000), (1275, 2500, 256)])
+                                   (100, 5000, 2000), (3000, 100, 4000), (700, 650, 333), (100, 100, 20000), (1275, 2500, 256),
+                                   # the K = k product with a Cin: many tiles, few k-tiles (Cin-prefetch kernel), ragged edges
+                                   (2601, 4003, 100)])
 def test_dgemm_tn(pkg, M, N, K):
     rng = np.random.default_rng(M * 1000 + N * 10 + K)
     At = rng.standard_normal((K, M)); B = rng.standard_normal((K, N)); C0 = rng.standard_normal((M, N))
