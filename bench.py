@@ -221,7 +221,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
@@ -236,6 +236,11 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped, except the last one if the timed region turns out shorter
+        than one sampling period."""
+        self.first = max(0, len(self.lines) - 1)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -247,7 +252,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -469,9 +474,10 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident throughput -------------------------------------------------------
+    clocks = ClockSampler(local); clocks.start()      # nvidia-smi needs ~0.2 s to deliver its first line: start it before the warm-up
     sw.sweep(args.warmup)
     barrier()
-    clocks = ClockSampler(local); clocks.start()
+    clocks.mark()                                     # samples from here on belong to the timed region
     launches0 = lib.bsfg_launch_count()
     wall0 = time.perf_counter()
     k_per_iter = None
@@ -693,7 +699,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))

@@ -114,7 +114,7 @@ struct bsfg_ctx {
     bool side_ready = false;
     ncclComm_t comm2 = nullptr;
     bsfg::DVec gstage2;
-    cudaEvent_t ev_forkA = nullptr, ev_joinA = nullptr, ev_forkB = nullptr, ev_joinB = nullptr, ev_forkC = nullptr, ev_joinC = nullptr;
+    cudaEvent_t ev_forkA = nullptr, ev_joinA = nullptr, ev_forkB = nullptr, ev_joinB = nullptr, ev_forkC = nullptr, ev_joinC = nullptr, ev_forkD = nullptr, ev_joinD = nullptr;
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_phase;     // (N_PHASES + 1) per iteration slot, reused
@@ -156,7 +156,7 @@ static DMat view_at(double* p, long rows, long cols, long ld) {
     return v;
 }
 
-static void refresh_derived(bsfg_ctx* c);
+static void refresh_derived(bsfg_ctx* c, bool fork_side = false);
 // `side`: issue on the side stream with its own communicator (see bsfg_ctx::dev2)
 static void allreduce(bsfg_ctx* c, double* buf, size_t count, bool side = false) {
     if (c->cfg.world <= 1) return;
@@ -191,9 +191,9 @@ static RowShard row_shard(const bsfg_ctx* c, long rows) {
     return s;
 }
 // C[lo:lo+cnt, :] (+)= alpha * At[:, lo:lo+cnt]' B
-static void gemm_rows(bsfg_ctx* c, const RowShard& sh, double alpha, const DMat& At, const DMat& B, double beta, DMat& C) {
+static void gemm_rows(bsfg_ctx* c, const RowShard& sh, double alpha, const DMat& At, const DMat& B, double beta, DMat& C, bool side = false) {
     if (sh.cnt <= 0) return;
-    Device& d = c->dev;
+    Device& d = side ? c->dev2 : c->dev;
     dgemm_tn(d.st, d.sms, (int)sh.cnt, (int)B.cols, (int)At.rows, alpha, At.p + sh.lo * At.ld, At.ld, B.p, B.ld, beta,
              C.p + sh.lo, C.ld, C.p + sh.lo, C.ld, d.ws.p, Device::WS_DOUBLES);
 }
@@ -224,7 +224,7 @@ static bool side_enabled(bsfg_ctx* c) {
         // the staging buffer is sized before any concurrent use (a cudaMalloc in the middle of the sweep would serialise the streams)
         const long rows = std::max<long>(std::max(c->n, c->r), c->br);
         if (c->cfg.world > 1) c->gstage2.alloc(round_up(ceil_div(rows, c->cfg.world), 2) * c->kmax * c->cfg.world);
-        for (cudaEvent_t* e : {&c->ev_forkA, &c->ev_joinA, &c->ev_forkB, &c->ev_joinB, &c->ev_forkC, &c->ev_joinC})
+        for (cudaEvent_t* e : {&c->ev_forkA, &c->ev_joinA, &c->ev_forkB, &c->ev_joinB, &c->ev_forkC, &c->ev_joinC, &c->ev_forkD, &c->ev_joinD})
             BSFG_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         c->side_ready = true;
     }
@@ -239,17 +239,27 @@ static void phase_mark(bsfg_ctx* c, int idx) {
     if (c->phase_timing) BSFG_CUDA(cudaEventRecord(c->ev_phase[idx], c->dev.st));
 }
 
-static void refresh_derived(bsfg_ctx* c) {
+static bool side_enabled(bsfg_ctx* c);
+// fork_side: Design_U'F (with its all-gather and transpose) goes to the side stream while U'F is formed on the sweep stream;
+// the caller waits for c->ev_joinD before it touches DtF / FtD
+static void refresh_derived(bsfg_ctx* c, bool fork_side) {
     // UtF = U'F (t(FtU), cpp:107) and DtF = Design_U'F (+ F'Z_2): depend only on F -> row-sharded over the ranks
     Device& d = c->dev;
     DMat F = view(c->F, c->n, c->k), UtF = view(c->UtF, c->n, c->k), FtD = view(c->FtD, c->k, c->br);
     DMat DtF = view(c->DtF, c->br, c->k);
     const RowShard sn = row_shard(c, c->n), sb = row_shard(c, c->br);
+    const bool side = fork_side && side_enabled(c);
+    if (side) {
+        BSFG_CUDA(cudaEventRecord(c->ev_forkD, d.st));
+        BSFG_CUDA(cudaStreamWaitEvent(c->dev2.st, c->ev_forkD, 0));
+    }
+    Device& dd = side ? c->dev2 : d;
+    gemm_rows(c, sb, 1.0, c->DU, F, 0.0, DtF, side);
+    gather_rows(c, sb, DtF, side);
+    dd.transpose(DtF, FtD);
+    if (side) BSFG_CUDA(cudaEventRecord(c->ev_joinD, c->dev2.st));
     gemm_rows(c, sn, 1.0, c->U1, F, 0.0, UtF);
     gather_rows(c, sn, UtF);
-    gemm_rows(c, sb, 1.0, c->DU, F, 0.0, DtF);
-    gather_rows(c, sb, DtF);
-    d.transpose(DtF, FtD);
     if (c->r2 > 0) {
         DMat FtZ2 = view(c->FtZ2, c->k, c->r2), Z2tF = view(c->Z2tF, c->r2, c->k);
         d.gemm(1.0, F, c->Z2, 0.0, FtZ2);          // F' Z_2
@@ -505,12 +515,13 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
         BSFG_CUDA(cudaEventRecord(c->ev_joinB, c->dev2.st));
     }
     // 8-9. resid_Y_prec, E_a_prec from sufficient statistics of the NEW F   R:239-245
-    refresh_derived(c);
+    refresh_derived(c, /*fork_side=*/side);
     {
         DMat FtF = view(c->FtF, k, k), FtY = view(c->FtY, k, pl), G2 = view(c->G2, k, pl);
         d.gemm(1.0, F, F, 0.0, FtF);
         d.gemm(1.0, UtF, c->UtY, 0.0, FtY);                // F'Y = (U'F)'(U'Y)
         d.gemm(1.0, FtF, Lt, 0.0, G2);                     // F'F lambda_j
+        if (side) BSFG_CUDA(cudaStreamWaitEvent(d.st, c->ev_joinD, 0));     // Design_U'F from the side stream
         DMat DtF = view(c->DtF, br, k), FDth = view(c->FDth, k, pl);
         d.gemm(1.0, DtF, c->theta, 0.0, FDth);             // (F' Design_U) theta_j: k values per trait
         if (c->mode == 1) {
@@ -654,7 +665,7 @@ extern "C" int bsfg_destroy(bsfg_ctx* c) {
     cudaStreamSynchronize(c->dev.st);
     if (c->side_ready) {
         cudaStreamSynchronize(c->dev2.st);
-        for (cudaEvent_t e : {c->ev_forkA, c->ev_joinA, c->ev_forkB, c->ev_joinB, c->ev_forkC, c->ev_joinC})
+        for (cudaEvent_t e : {c->ev_forkA, c->ev_joinA, c->ev_forkB, c->ev_joinB, c->ev_forkC, c->ev_joinC, c->ev_forkD, c->ev_joinD})
             if (e) cudaEventDestroy(e);
         if (c->dev2.means.Bpart) cudaFree(c->dev2.means.Bpart);
         if (c->dev2.means.counter) cudaFree(c->dev2.means.counter);
