@@ -190,6 +190,17 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return fma(q, p, y);
 }
 
+// Box-Muller radius sqrt(-2 ln u) for u in (0, 1): on the device x * rsqrt(x) with the 5-operation reciprocal square root
+// (x = -2 ln u lies in [2e-16, 74]: positive, normal), on the host the library call.
+__host__ __device__ inline double bm_radius(double u) {
+    const double x = -2.0 * log(u);
+#ifdef __CUDA_ARCH__
+    return x * fast_rsqrt(x);
+#else
+    return sqrt(x);
+#endif
+}
+
 // draw sites (the `site` word of the Philox counter); one per reference RNG call site
 enum Site : uint32_t {
     SITE_Z_LAMBDA = 1,     // randn(k,p)            BSFG_functions_c.cpp:110
@@ -231,7 +242,7 @@ __host__ __device__ inline void philox_normal_pair(const RngStream& s, uint64_t 
     ph((uint32_t)pair, (uint32_t)(pair >> 32), s.site, s.iter, o);
     const double u1 = u01_from_bits(o[0], o[1]);
     const double u2 = u01_from_bits(o[2], o[3]);
-    const double r = sqrt(-2.0 * log(u1));
+    const double r = bm_radius(u1);
     double sn, cs;
     sincospi(2.0 * u2, &sn, &cs);
     *z_even = r * cs;
@@ -244,7 +255,7 @@ __host__ __device__ inline double philox_normal(const RngStream& s, uint64_t idx
     ph((uint32_t)pair, (uint32_t)(pair >> 32), s.site, s.iter, o);
     const double u1 = u01_from_bits(o[0], o[1]);
     const double u2 = u01_from_bits(o[2], o[3]);
-    const double r = sqrt(-2.0 * log(u1));
+    const double r = bm_radius(u1);
     return (idx & 1) ? r * sinpi(2.0 * u2) : r * cospi(2.0 * u2);
 }
 
@@ -273,7 +284,7 @@ __host__ __device__ inline double philox_gamma(const RngStream& s, uint64_t idx,
         ph((uint32_t)idx, (uint32_t)(idx >> 32) | (attempt << 24), s.site, s.iter, o);
         double u1 = u01_from_bits(o[0], o[1]);
         double u2 = u01_from_bits(o[2], o[3]);
-        double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        double x = bm_radius(u1) * cospi(2.0 * u2);
         // the acceptance uniform comes from a second block so it is independent of x
         uint32_t o2[4];
         ph((uint32_t)idx, (uint32_t)(idx >> 32) | (attempt << 24) | 0x40000000u, s.site, s.iter, o2);

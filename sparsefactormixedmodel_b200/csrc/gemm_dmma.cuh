@@ -203,6 +203,14 @@ dgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncwarp();
 
     for (;;) {
+        // the tile's Cin lines are asked into L2 now: the epilogue of a K = k product (seven k-tiles per tile) otherwise waits
+        // four times for HBM while the DMMA pipe idles
+        if (g.Cin && g.splits == 1 && !g.trans_out) {
+            for (int t = threadIdx.x; t < BN * (BM / 16); t += GEMM_THREADS) {
+                const int n = cur.n0 + t / (BM / 16), m = cur.m0 + (t % (BM / 16)) * 16;
+                if (n < g.N && m < g.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.Cin + (size_t)n * g.ldcin + m));
+            }
+        }
         double acc[FM][FN][2];
 #pragma unroll
         for (int i = 0; i < FM; i++)

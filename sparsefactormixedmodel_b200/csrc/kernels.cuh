@@ -129,7 +129,7 @@ __global__ void lambda_weights_kernel(const double* __restrict__ UtY, long ldy, 
     const double* __restrict__ ycol = UtY + (long)j * ldy;
     double* __restrict__ wycol = WY + (long)j * ldwy;
     double* __restrict__ wcol = write_w ? W + (long)j * ldw : nullptr;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x) {
         const bool has1 = i + 1 < n;
         const double w0 = epj / (s[i] + c);
