@@ -91,3 +91,20 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_update_k_add_arm_draw_families_have_their_own_philox_sites():
+    """Gamma draws address Philox blocks by element, normal draws by element pair, so two families on one
+    site share blocks.  Every site word is unique and the add arm of update_k uses one site per vector family."""
+    import re
+    csrc = os.path.join(ROOT, "sparsefactormixedmodel_b200", "csrc")
+    common = open(os.path.join(csrc, "common.cuh")).read()
+    body = common[common.index("enum Site"):]
+    body = body[:body.index("};")]
+    sites = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"(SITE_\w+)\s*=\s*(\d+)", body))
+    assert len(sites) >= 20 and len(set(sites.values())) == len(sites), sites
+    stateless = open(os.path.join(csrc, "stateless.inl")).read()
+    arm = stateless[stateless.index("one Philox site per draw family"):]
+    arm = arm[:arm.index("addk_traits_kernel")]
+    used = re.findall(r"make_var\(nullptr, s\.seed, (SITE_\w+),", arm)
+    assert used == ["SITE_K_ADD_LP", "SITE_K_ADD_ZL", "SITE_K_ADD_ZFA", "SITE_K_ADD_ZF"], used
