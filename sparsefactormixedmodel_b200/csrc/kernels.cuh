@@ -106,7 +106,11 @@ __global__ void gram_features_kernel(const double* __restrict__ UtF, long ldf, i
     const double* fa = UtF + (long)a * ldf;
     const double* fb = UtF + (long)b * ldf;
     double* g = Gt + (long)pair * ldg;
-    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) g[i] = fa[i] * fb[i];
+    // Gt and UtF are DMat storage (even leading dimension, zero pad row): rows as 16-byte pairs
+    for (int i = 2 * (blockIdx.y * blockDim.x + threadIdx.x); i < n; i += 2 * gridDim.y * blockDim.x) {
+        const double2 x = *reinterpret_cast<const double2*>(fa + i), y = *reinterpret_cast<const double2*>(fb + i);
+        *reinterpret_cast<double2*>(g + i) = make_double2(x.x * y.x, x.y * y.y);
+    }
 }
 
 // W[i,j]  = ep_j / (s_i + ep_j / rp_j)                                   (cpp:120, the sweep weights)

@@ -308,7 +308,7 @@ static void lambda_core(Device& d, LambdaScratch& sc, const GramOpts& go, const 
             pair_lo = (int)std::min<long>(np, (long)sc.rank * chunk);
             pair_hi = (int)std::min<long>(np, pair_lo + chunk);
         }
-        dim3 grid(np, std::min(ceil_div(n, 256), 64));
+        dim3 grid(np, std::min(ceil_div(n, 1024), 16));        // four rows per thread: a quarter of the CTAs of a one-row-per-thread grid
         gram_features_kernel<<<grid, 256, 0, d.st>>>(UtF.p, UtF.ld, n, k, sc.Gt.p, sc.Gt.ld, pair_lo, pair_hi,
                                                      shard_pairs ? sc.need_exact : nullptr);
         BSFG_CHECK_LAUNCH(); g_launch_counter++;
