@@ -644,6 +644,8 @@ def run_ours(args):
                      "flop_per_launch": kern_flop, "ms_per_launch": kern_ms, "peak_source": peak_src,
                      "dmma_issue_peak_tflops": 37.1},
         "phases_ms_last_iter": phases,
+        "phases_note": "CUDA-event intervals of the last timed iteration, which the library runs on one stream so that every interval "
+                       "measures the kernels it brackets; the other iterations overlap the F-only draws and the delta chain on a side stream",
         "iteration_roofline": iteration_roofline(n, pl_local, k_now, 1, phases, gstats, peak_tf, dev_ms / args.steps),
         "sweep_algorithmic_tflops": algorithmic_flops(n, p, k) / world / (dev_ms / args.steps * 1e-3) * 1e-12,
         "sweep_algorithmic_tflops_note": "SURVEY.md 8d W_flop of the exact formulation (k(k+1)np weighted Gram) per GPU / time; in expsum "

@@ -122,6 +122,7 @@ struct bsfg_ctx {
     long long last_launches = 0;
     double phase_ms[BSFG_N_PHASES] = {0};
     bool phase_timing = false;
+    bool serial_iter = false;     // this iteration runs on the sweep stream alone (the phase-timed last iteration of a multi-iteration call)
 };
 
 namespace bsfg {
@@ -320,7 +321,7 @@ static void gibbs_iteration(bsfg_ctx* c, const IterVariates& v, bool fixed_lambd
     // F_h2 | F and F_a | F, F_h2 (steps 4 and 5) depend on F only: with the side stream they start now and run beside the
     // Lambda / theta chain; the sweep stream picks their results up before the F draw.  (The px sweep keeps one stream: its
     // rescaled copies of F live in scratch the F step reuses.)
-    const bool side = !px && side_enabled(c);
+    const bool side = !px && !c->serial_iter && side_enabled(c);
     auto draw_h2_and_Fa = [&](Device& dd, bool on_side) {
         // 4. F_h2 | F (marginal over F_a)                         R:221 -> cpp:196-238
         //    px sweep: both draws see F_temp = F_px / sqrt(px_factor)  (fast_BSFG_sampler_px.R:232-238); YL / ZFa are free here
@@ -1101,6 +1102,11 @@ static int sweep_impl(bsfg_ctx* c, int n_iter, bool px) {
         v.zY = make_var(nullptr, seed, SITE_Z_Y, ii, c->p_off, c->n);
         v.gPX = make_var(nullptr, seed, SITE_G_PX, ii, 0, 1);
         c->phase_timing = (it == n_iter - 1);
+        // The phase-timed iteration of a multi-iteration call runs on ONE stream: with the side stream on, its kernels land inside
+        // whatever phase happens to be running (the F_a products inside the trait product, say) and the CUDA-event intervals
+        // no longer measure the kernels they bracket.  One iteration in n_iter pays ~3% for clean phase times; single-iteration
+        // calls (the end-to-end path) keep the overlap.
+        c->serial_iter = c->phase_timing && n_iter > 1;
         // BSFG_PROFILE_ITER=<n>: bracket the n-th Gibbs iteration of this process (0-based) with cudaProfilerStart/Stop, so that
         // `ncu --profile-from-start off` captures exactly one warm iteration (tools/profile_iteration.sh)
         static const long prof_iter = [] { const char* e = getenv("BSFG_PROFILE_ITER"); return e ? atol(e) : -1L; }();
@@ -1284,6 +1290,7 @@ static int sweep_injected_impl(bsfg_ctx* c, const bsfg_variates* hv, bool px) {
     d.sync();
     c->aux_on = true;
     c->phase_timing = true;
+    c->serial_iter = false;
     const long long launches_before = g_launch_counter;
     BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
     gibbs_iteration(c, v, false, px);
@@ -1354,6 +1361,7 @@ extern "C" int bsfg_sweep_fixed_lambda(bsfg_ctx* c, const double* Lambda, int k,
     d.sync();
     c->aux_on = true;
     c->phase_timing = true;
+    c->serial_iter = false;
     const long long launches_before = g_launch_counter;
     BSFG_CUDA(cudaEventRecord(c->ev_begin, d.st));
     gibbs_iteration(c, v, /*fixed_lambda=*/true);

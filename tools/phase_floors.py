@@ -59,11 +59,12 @@ def main():
         if name == "F_solve":
             m += ph.get("F_comm", 0.0)
         tot_f += f; tot_m += m
-        frac = f"{f / m:.0%}" if m >= 0.02 else "(side stream)"
+        frac = f"{f / m:.0%}" if m >= 0.02 else "(side stream)"      # bench lines taken before the one-stream phase iteration
         print(f"| {name} | {flop / 1e9:.1f} | {byts / 1e9:.2f} | {f:.2f} | {m:.2f} | {frac} | {what} |")
     print(f"| **sum** | | | **{tot_f:.2f}** | **{tot_m:.2f}** | **{tot_f / line['ms_per_step']:.0%}** of the iteration | iteration: {line['ms_per_step']:.2f} ms |")
-    print("\nPhases are CUDA-event intervals on the sweep stream of the last timed iteration.  With the side stream (default) h2, F_a and delta")
-    print("run beside other phases and read ~0 here; their work is still part of the floor, and the fraction of record is floor / iteration.")
+    print("\nPhases are CUDA-event intervals of the last timed iteration, which the library runs on ONE stream so that every interval measures")
+    print("the kernels it brackets; the other iterations overlap h2, F_a, the k x k factor, the Design_U'F refresh and the delta chain on a")
+    print("side stream, which is why the iteration (ms_per_step) is shorter than the sum of the phases.  The fraction of record is floor / iteration.")
 
 
 if __name__ == "__main__":

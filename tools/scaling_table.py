@@ -22,8 +22,8 @@ def main():
               f"{e['value'] / (n * base['e2e']['value']):.2f} | {parts.get('set_state_h2d', 0):.2f} | {parts.get('sweep', 0):.2f} | "
               f"{parts.get('get_state_d2h', 0):.2f} | {d['gpu_launches'] / d['steps']:.0f} |")
     names = [k for k in base["phases_ms_last_iter"] if k != "update_k"]
-    print("\nCUDA-event phases on the sweep stream, last timed iteration (ms).  h2, F_a and delta run on the side stream (DESIGN.md section 6)")
-    print("and read ~0 here; `ideal` = the 1-GPU phase / N.\n")
+    print("\nCUDA-event phases of the last timed iteration (ms); `ideal` = the 1-GPU phase / N.  (In bench lines taken before the library ran")
+    print("its phase-timed iteration on one stream, h2, F_a and delta were on the side stream and read ~0.)\n")
     print("| phase | " + " | ".join(f"N={d['n_gpus']}" + (f" (ideal {1})" if False else "") for d in lines) + " | N=8 ideal |")
     print("|---|" + "---|" * (len(lines) + 1))
     for nm in names:
